@@ -1,0 +1,79 @@
+// Shared host-side plumbing of libaslam_b200: context, error reporting, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/aslam_b200.h"
+
+struct aslam_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    // scratch for the host-buffer matching entry points (grown on demand)
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *h_scratch = nullptr;     // pinned
+    size_t h_scratch_bytes = 0;
+    // optional per-kernel timing (aslam_prof_*): CUDA event pairs around every launch
+    bool prof_on = false;
+    struct ProfRec { int kind; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0};
+    long long prof_n[16] = {0};
+};
+
+namespace aslam {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+int fail(int code, const char *fmt, ...);
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int ensure_scratch(aslam_ctx *ctx, size_t dev_bytes, size_t host_bytes);
+
+enum ProfKind { PK_RESIZE = 0, PK_FAST, PK_BLUR, PK_SELECT, PK_DESCRIBE, PK_KNN_PARTIAL, PK_KNN_FINISH,
+                PK_MERGE, PK_MISC, PK_COUNT };
+
+// Brackets one kernel launch with an event pair when profiling is enabled on the context.
+struct ProfScope {
+    aslam_ctx *c;
+    int kind;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(aslam_ctx *ctx, int k);
+    ~ProfScope();
+};
+
+}  // namespace aslam
+
+#define ASLAM_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return aslam::fail(ASLAM_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,    \
+                               cudaGetErrorString(e__));                                      \
+    } while (0)
+
+#define ASLAM_LAUNCH_CHECK()                                                                  \
+    do {                                                                                      \
+        aslam::count_launch();                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess)                                                               \
+            return aslam::fail(ASLAM_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, \
+                               cudaGetErrorString(e__));                                      \
+    } while (0)
+
+#define ASLAM_REQUIRE(cond, msg)                                                              \
+    do {                                                                                      \
+        if (!(cond)) return aslam::fail(ASLAM_E_INVALID, "%s: %s", __func__, msg);            \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -1,0 +1,490 @@
+// Brute-force Hamming kNN (k = 2) over 256-bit descriptors: XOR + POPC on the integer pipes,
+// queries register-blocked, train rows streamed through shared memory and broadcast to the warp.
+//
+// Replaces cv::cuda::DescriptorMatcher::knnMatch as the reference calls it
+// (src/adapters/gpu/CudaMatcher.cpp:56, src/main.cpp:159, src/euroc_eval.cpp:168) and the CPU
+// cv::BFMatcher::knnMatch of src/legacy/LoopClosure.cpp:87; results follow the CPU matcher:
+// ascending (distance, train index).
+#include "match.cuh"
+
+namespace aslam {
+
+constexpr int KNN_TILE = 128;   // train rows per shared-memory stage (4 KB)
+
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4 a, const uint4 b)
+{
+#if ASLAM_KNN_CSA
+    // Carry-save compression of six of the eight XOR words (two full adders = 4 LOP3) trades two
+    // quarter-rate POPCs for four full-rate logic ops: sum = popc(s0)+popc(s1)+popc(x6)+popc(x7)
+    // + 2*(popc(c0)+popc(c1)).
+    uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 ^ x1));
+    uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 ^ x4));
+    uint32_t ones = __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7);
+    uint32_t twos = __popc(c0) + __popc(c1);
+    return ones + 2u * twos;
+#else
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+           __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+#endif
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride)
+{
+    __shared__ uint4 tile[2][KNN_TILE * 2];
+
+    const KnnProblem P = probs[blockIdx.y];
+    const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
+    const int nt = P.nt_dev ? min(*P.nt_dev, P.nt) : P.nt;
+    const int qbase = blockIdx.x * KNN_QBLOCK;
+    if (qbase >= nq) return;
+    const int t_lo = P.t_lo, t_hi = min(P.t_hi, nt);
+    const int tid = threadIdx.x;
+
+    uint32_t qd[KNN_RQ][8];
+    uint32_t b1[KNN_RQ], b2[KNN_RQ];
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        const int qi = qbase + j * KNN_THREADS + tid;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (qi < nq) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.q) + (size_t)qi * 2;
+            lo = __ldg(src); hi = __ldg(src + 1);
+        }
+        qd[j][0] = lo.x; qd[j][1] = lo.y; qd[j][2] = lo.z; qd[j][3] = lo.w;
+        qd[j][4] = hi.x; qd[j][5] = hi.y; qd[j][6] = hi.z; qd[j][7] = hi.w;
+        b1[j] = KEY_EMPTY; b2[j] = KEY_EMPTY;
+    }
+
+    const uint4 *trows = reinterpret_cast<const uint4 *>(P.t);
+    // stage 0
+    uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
+    {
+        const int e0 = t_lo * 2 + tid, e1 = e0 + KNN_THREADS;
+        if (e0 < t_hi * 2) pre0 = __ldg(trows + e0);
+        if (e1 < t_hi * 2) pre1 = __ldg(trows + e1);
+    }
+    int buf = 0;
+    for (int t0 = t_lo; t0 < t_hi; t0 += KNN_TILE, buf ^= 1) {
+        tile[buf][tid] = pre0;
+        tile[buf][tid + KNN_THREADS] = pre1;
+        __syncthreads();
+        // prefetch the next stage into registers while this one is consumed
+        {
+            const int e0 = (t0 + KNN_TILE) * 2 + tid, e1 = e0 + KNN_THREADS;
+            if (e0 < t_hi * 2) pre0 = __ldg(trows + e0);
+            if (e1 < t_hi * 2) pre1 = __ldg(trows + e1);
+        }
+        const int rows = min(KNN_TILE, t_hi - t0);
+        const uint4 *tb = tile[buf];
+        uint32_t keybase = (uint32_t)t0;
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r) {
+            const uint4 a = tb[2 * r], b = tb[2 * r + 1];
+#pragma unroll
+            for (int j = 0; j < KNN_RQ; ++j) {
+                const uint32_t d = hamming256(qd[j], a, b);
+                const uint32_t key = (d << KEY_IDX_BITS) + keybase;
+                b2[j] = min(b2[j], max(b1[j], key));
+                b1[j] = min(b1[j], key);
+            }
+            ++keybase;
+        }
+        // the other buffer is rewritten next iteration only after everyone passed this barrier
+        // in the following loop trip; with two buffers one barrier per stage suffices.
+    }
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        const int qi = qbase + j * KNN_THREADS + tid;
+        if (qi < nq) partial[(size_t)blockIdx.y * q_stride + qi] = make_uint2(b1[j], b2[j]);
+    }
+}
+
+// Merge `splits` partial (best, second) pairs of one query: keys are distinct across splits
+// (disjoint row ranges), so the two smallest of the union are the answer.
+__device__ __forceinline__ void merge_pair(uint32_t &k1, uint32_t &k2, const uint2 p)
+{
+    // p.x <= p.y always
+    const uint32_t n2 = min(max(k1, p.x), min(k2, p.y));
+    k1 = min(k1, p.x);
+    k2 = n2;
+}
+
+__device__ __forceinline__ bool ratio_pass(uint32_t d0, uint32_t d1, const RatioTest rt)
+{
+    if (rt.disabled) return true;
+    if (rt.as_double) return (double)d0 < __dmul_rn(rt.ratio, (double)d1);
+    return (float)d0 < __fmul_rn((float)rt.ratio, (float)d1);
+}
+
+constexpr int FIN_THREADS = 256;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int &total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();   // protect warp_sums from the previous use
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < FIN_THREADS / 32; ++i) {
+        int s = warp_sums[i];
+        if (i < w) base += s;
+        tot += s;
+    }
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__restrict__ partial,
+                           int splits, int q_stride, RatioTest rt,
+                           aslam_match *__restrict__ out, int out_stride, int32_t *__restrict__ nout,
+                           int32_t *__restrict__ raw_idx, int32_t *__restrict__ raw_dist)
+{
+    __shared__ int warp_sums[FIN_THREADS / 32];
+    const int g = blockIdx.x;
+    const KnnProblem P = probs[g * splits];
+    const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
+    int written = 0;
+    for (int q0 = 0; q0 < nq; q0 += FIN_THREADS) {
+        const int q = q0 + threadIdx.x;
+        uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
+        if (q < nq)
+            for (int s = 0; s < splits; ++s)
+                merge_pair(k1, k2, partial[(size_t)(g * splits + s) * q_stride + q]);
+        const uint32_t d0 = k1 >> KEY_IDX_BITS, d1 = k2 >> KEY_IDX_BITS;
+        const int i0 = (int)(k1 & (KNN_MAX_ROWS - 1)), i1 = (int)(k2 & (KNN_MAX_ROWS - 1));
+        if (q < nq && raw_idx) {
+            const size_t o = ((size_t)g * q_stride + q) * 2;
+            raw_idx[o] = k1 == KEY_EMPTY ? -1 : i0;      raw_dist[o] = k1 == KEY_EMPTY ? -1 : (int)d0;
+            raw_idx[o + 1] = k2 == KEY_EMPTY ? -1 : i1;  raw_dist[o + 1] = k2 == KEY_EMPTY ? -1 : (int)d1;
+        }
+        const int pass = (q < nq && k2 != KEY_EMPTY && ratio_pass(d0, d1, rt)) ? 1 : 0;
+        int total;
+        const int pos = block_exclusive_scan(pass, warp_sums, total);
+        if (pass && out) {
+            aslam_match m;
+            m.query_idx = q; m.train_idx = i0; m.distance = (float)d0;
+            if (written + pos < out_stride) out[(size_t)g * out_stride + written + pos] = m;
+        }
+        written += total;
+    }
+    if (threadIdx.x == 0 && nout) nout[g] = written;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+knn2_finish_counts_kernel(const KnnProblem *__restrict__ probs, const uint2 *__restrict__ partial,
+                          int q_stride, RatioTest rt, int32_t *__restrict__ good)
+{
+    __shared__ int warp_sums[FIN_THREADS / 32];
+    const int s = blockIdx.x;
+    const KnnProblem P = probs[s];
+    const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
+    int cnt = 0;
+    for (int q = threadIdx.x; q < nq; q += FIN_THREADS) {
+        const uint2 p = partial[(size_t)s * q_stride + q];
+        if (p.y != KEY_EMPTY && ratio_pass(p.x >> KEY_IDX_BITS, p.y >> KEY_IDX_BITS, rt)) ++cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < FIN_THREADS / 32; ++i) t += warp_sums[i];
+        good[s] = t;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+knn2_finish_global_kernel(const uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
+                          long long row_base, unsigned long long *__restrict__ top2)
+{
+    const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
+    for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
+    const unsigned long long e = ~0ull;
+    top2[2 * (size_t)q] = k1 == KEY_EMPTY ? e
+        : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
+    top2[2 * (size_t)q + 1] = k2 == KEY_EMPTY ? e
+        : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
+}
+
+// Merge of all-gathered shard results: parts[nparts][nq][2] packed 64-bit keys.
+__global__ void __launch_bounds__(FIN_THREADS)
+merge_top2_kernel(const unsigned long long *__restrict__ parts, int nparts, int nq,
+                  unsigned long long *__restrict__ out)
+{
+    const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long k1 = ~0ull, k2 = ~0ull;
+    for (int p = 0; p < nparts; ++p) {
+        const unsigned long long a = parts[((size_t)p * nq + q) * 2], b = parts[((size_t)p * nq + q) * 2 + 1];
+        const unsigned long long n2 = min(max(k1, a), min(k2, b));
+        k1 = min(k1, a);
+        k2 = n2;
+    }
+    out[2 * (size_t)q] = k1;
+    out[2 * (size_t)q + 1] = k2;
+}
+
+// Problem table of one (q, t) pair cut into `splits` row ranges, written on the device so that
+// fully asynchronous callers never depend on a host staging buffer staying untouched.
+__global__ void fill_split_problems_kernel(KnnProblem *probs, const uint8_t *q, const uint8_t *t,
+                                           const int32_t *nq_dev, const int32_t *nt_dev,
+                                           int nq, int nt, int splits, int rows_per)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= splits) return;
+    KnnProblem P;
+    P.q = q; P.t = t; P.nq_dev = nq_dev; P.nt_dev = nt_dev; P.nq = nq; P.nt = nt;
+    P.t_lo = min(s * rows_per, nt);
+    P.t_hi = min((s + 1) * rows_per, nt);
+    probs[s] = P;
+}
+
+int launch_fill_split_problems(aslam_ctx *ctx, KnnProblem *d_probs, const uint8_t *q, const uint8_t *t,
+                               const int32_t *nq_dev, const int32_t *nt_dev, int nq, int nt, int splits)
+{
+    const int rows_per = (nt + splits - 1) / splits;
+    ProfScope ps(ctx, PK_MISC);
+    fill_split_problems_kernel<<<(splits + 127) / 128, 128, 0, ctx->stream>>>(d_probs, q, t, nq_dev, nt_dev,
+                                                                              nq, nt, splits, rows_per);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int max_nq,
+                        uint2 *d_partial, int q_stride)
+{
+    if (nprobs <= 0 || max_nq <= 0) return ASLAM_OK;
+    dim3 grid((max_nq + KNN_QBLOCK - 1) / KNN_QBLOCK, nprobs);
+    ProfScope ps(ctx, PK_KNN_PARTIAL);
+    knn2_partial_kernel<<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
+                               int ngroups, int splits, int q_stride, RatioTest rt,
+                               aslam_match *d_out, int out_stride, int32_t *d_nout,
+                               int32_t *d_raw_idx, int32_t *d_raw_dist)
+{
+    if (ngroups <= 0) return ASLAM_OK;
+    ProfScope ps(ctx, PK_KNN_FINISH);
+    knn2_finish_matches_kernel<<<ngroups, FIN_THREADS, 0, ctx->stream>>>(
+        d_probs, d_partial, splits, q_stride, rt, d_out, out_stride, d_nout, d_raw_idx, d_raw_dist);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
+                              int nslots, int q_stride, RatioTest rt, int32_t *d_good)
+{
+    if (nslots <= 0) return ASLAM_OK;
+    ProfScope ps(ctx, PK_KNN_FINISH);
+    knn2_finish_counts_kernel<<<nslots, FIN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, rt, d_good);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_finish_global(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
+                              int q_stride, int64_t row_base, uint64_t *d_top2)
+{
+    if (nq <= 0) return ASLAM_OK;
+    ProfScope ps(ctx, PK_KNN_FINISH);
+    knn2_finish_global_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
+        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *)d_top2);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+static RatioTest make_ratio(double ratio, int as_double)
+{
+    RatioTest rt;
+    rt.ratio = ratio; rt.as_double = as_double; rt.disabled = ratio < 0 ? 1 : 0;
+    return rt;
+}
+
+// How many row ranges to cut a train set of nt rows into so the grid covers the GPU a few times.
+int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets)
+{
+    const int qblocks = (nq + KNN_QBLOCK - 1) / KNN_QBLOCK;
+    const long long want = 8LL * ctx->sm_count;               // CTAs
+    long long s = (want + (long long)qblocks * nsets - 1) / ((long long)qblocks * nsets);
+    const long long max_by_rows = (nt + 255) / 256;           // at least 256 rows per split
+    if (s > max_by_rows) s = max_by_rows;
+    if (s < 1) s = 1;
+    if (s > 4096) s = 4096;
+    return (int)s;
+}
+
+}  // namespace aslam
+
+using namespace aslam;
+
+// ------------------------------------------------------------------ host-buffer entry points
+// Scratch layout (device): [problems][q rows][t rows][partial][matches][nout][raw idx][raw dist]
+static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                      bool inputs_on_device, RatioTest rt, aslam_match *out, int *nout,
+                      int32_t *raw_idx, int32_t *raw_dist, aslam_match *d_out_user, int32_t *d_nout_user)
+{
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    if (nt > KNN_MAX_ROWS) return fail(ASLAM_E_INVALID, "train set has %d rows; at most %d per call", nt, KNN_MAX_ROWS);
+    const int splits = choose_splits(ctx, nq, nt, 1);
+    const int q_stride = (int)align_up((size_t)nq, 64);
+    const size_t o_prob = 0;
+    const size_t o_q = align_up(o_prob + sizeof(KnnProblem) * splits, 256);
+    const size_t o_t = align_up(o_q + (inputs_on_device ? 0 : (size_t)nq * 32), 256);
+    const size_t o_part = align_up(o_t + (inputs_on_device ? 0 : (size_t)nt * 32), 256);
+    const size_t o_match = align_up(o_part + sizeof(uint2) * (size_t)splits * q_stride, 256);
+    const size_t o_nout = align_up(o_match + sizeof(aslam_match) * (size_t)nq, 256);
+    const size_t o_ridx = align_up(o_nout + 256, 256);
+    const size_t o_rdist = align_up(o_ridx + sizeof(int32_t) * 2 * (size_t)q_stride, 256);
+    const size_t total = align_up(o_rdist + sizeof(int32_t) * 2 * (size_t)q_stride, 256);
+    const size_t h_need = 256;
+    int rc = ensure_scratch(ctx, total, h_need);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    const uint8_t *dq = inputs_on_device ? q : base + o_q;
+    const uint8_t *dt = inputs_on_device ? t : base + o_t;
+    if (!inputs_on_device) {
+        ASLAM_CUDA(cudaMemcpyAsync(base + o_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ASLAM_CUDA(cudaMemcpyAsync(base + o_t, t, (size_t)nt * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    KnnProblem *dp = (KnnProblem *)(base + o_prob);
+    rc = launch_fill_split_problems(ctx, dp, dq, dt, nullptr, nullptr, nq, nt, splits);
+    if (rc) return rc;
+    uint2 *dpart = (uint2 *)(base + o_part);
+    rc = launch_knn2_partial(ctx, dp, splits, nq, dpart, q_stride);
+    if (rc) return rc;
+    aslam_match *dm = d_out_user ? d_out_user : (aslam_match *)(base + o_match);
+    int32_t *dn = d_nout_user ? d_nout_user : (int32_t *)(base + o_nout);
+    int32_t *dri = raw_idx ? (int32_t *)(base + o_ridx) : nullptr;
+    int32_t *drd = raw_idx ? (int32_t *)(base + o_rdist) : nullptr;
+    rc = launch_knn2_finish_matches(ctx, dp, dpart, 1, splits, q_stride, rt, dm, nq, dn, dri, drd);
+    if (rc) return rc;
+    if (d_out_user) return ASLAM_OK;     // fully asynchronous device form
+    if (raw_idx) {
+        ASLAM_CUDA(cudaMemcpyAsync(raw_idx, dri, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+        ASLAM_CUDA(cudaMemcpyAsync(raw_dist, drd, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int32_t *hn = (int32_t *)ctx->h_scratch;
+    ASLAM_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nout) *nout = *hn;
+    if (out && *hn > 0)
+        ASLAM_CUDA(cudaMemcpy(out, dm, sizeof(aslam_match) * (size_t)*hn, cudaMemcpyDeviceToHost));
+    return ASLAM_OK;
+}
+
+extern "C" int aslam_match_knn2(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                                float ratio, aslam_match *out, int *nout)
+{
+    ASLAM_REQUIRE(ctx && nout, "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nt >= 0, "negative row count");
+    *nout = 0;
+    // CudaMatcher.cpp:35-37 returns early on an empty side; :60 needs two neighbours.
+    if (nq == 0 || nt < 2) return ASLAM_OK;
+    ASLAM_REQUIRE(q && t && out, "NULL descriptor or output pointer");
+    return run_single(ctx, q, nq, t, nt, false, make_ratio((double)ratio, 0), out, nout, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int aslam_knn2_raw(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                              int32_t *idx, int32_t *dist)
+{
+    ASLAM_REQUIRE(ctx && (nq == 0 || (idx && dist)), "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nt >= 0, "negative row count");
+    if (nq == 0) return ASLAM_OK;
+    if (nt == 0) {
+        for (int i = 0; i < 2 * nq; ++i) { idx[i] = -1; dist[i] = -1; }
+        return ASLAM_OK;
+    }
+    ASLAM_REQUIRE(q && t, "NULL descriptor pointer");
+    int n = 0;
+    return run_single(ctx, q, nq, t, nt, false, make_ratio(-1.0, 0), nullptr, &n, idx, dist, nullptr, nullptr);
+}
+
+extern "C" int aslam_match_knn2_device(aslam_ctx *ctx, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
+                                       float ratio, aslam_match *d_out, int32_t *d_nout)
+{
+    ASLAM_REQUIRE(ctx && d_out && d_nout, "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nt >= 0, "negative row count");
+    if (nq == 0 || nt < 2) {
+        ASLAM_CUDA(cudaMemsetAsync(d_nout, 0, sizeof(int32_t), ctx->stream));
+        return ASLAM_OK;
+    }
+    ASLAM_REQUIRE(d_q && d_t, "NULL descriptor pointer");
+    return run_single(ctx, d_q, nq, d_t, nt, true, make_ratio((double)ratio, 0), nullptr, nullptr, nullptr, nullptr, d_out, d_nout);
+}
+
+extern "C" int aslam_match_multi(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t,
+                                 const int32_t *t_start, int nsets, float ratio,
+                                 aslam_match *out, int32_t *nout)
+{
+    ASLAM_REQUIRE(ctx && nout && t_start, "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nsets >= 0, "negative count");
+    for (int s = 0; s < nsets; ++s) nout[s] = 0;
+    if (nq == 0 || nsets == 0) return ASLAM_OK;
+    const long long rows = t_start[nsets];
+    ASLAM_REQUIRE(q && out && (rows == 0 || t), "NULL descriptor or output pointer");
+    for (int s = 0; s < nsets; ++s) {
+        ASLAM_REQUIRE(t_start[s + 1] >= t_start[s], "t_start must be non-decreasing");
+        if (t_start[s + 1] - t_start[s] > KNN_MAX_ROWS) return fail(ASLAM_E_INVALID, "train set %d too large", s);
+    }
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    const int q_stride = (int)align_up((size_t)nq, 64);
+    const size_t o_q = align_up(sizeof(KnnProblem) * (size_t)nsets, 256);
+    const size_t o_t = align_up(o_q + (size_t)nq * 32, 256);
+    const size_t o_part = align_up(o_t + (size_t)rows * 32, 256);
+    const size_t o_match = align_up(o_part + sizeof(uint2) * (size_t)nsets * q_stride, 256);
+    const size_t o_nout = align_up(o_match + sizeof(aslam_match) * (size_t)nsets * nq, 256);
+    const size_t total = align_up(o_nout + sizeof(int32_t) * (size_t)nsets, 256);
+    int rc = ensure_scratch(ctx, total, sizeof(KnnProblem) * (size_t)nsets);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_scratch;
+    ASLAM_CUDA(cudaMemcpyAsync(base + o_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (rows) ASLAM_CUDA(cudaMemcpyAsync(base + o_t, t, (size_t)rows * 32, cudaMemcpyHostToDevice, ctx->stream));
+    KnnProblem *hp = (KnnProblem *)ctx->h_scratch;
+    for (int s = 0; s < nsets; ++s) {
+        hp[s].q = base + o_q; hp[s].t = base + o_t + (size_t)t_start[s] * 32;
+        hp[s].nq_dev = nullptr; hp[s].nt_dev = nullptr;
+        hp[s].nq = nq; hp[s].nt = t_start[s + 1] - t_start[s];
+        hp[s].t_lo = 0; hp[s].t_hi = hp[s].nt;
+    }
+    KnnProblem *dp = (KnnProblem *)base;
+    ASLAM_CUDA(cudaMemcpyAsync(dp, hp, sizeof(KnnProblem) * (size_t)nsets, cudaMemcpyHostToDevice, ctx->stream));
+    uint2 *dpart = (uint2 *)(base + o_part);
+    rc = launch_knn2_partial(ctx, dp, nsets, nq, dpart, q_stride);
+    if (rc) return rc;
+    rc = launch_knn2_finish_matches(ctx, dp, dpart, nsets, 1, q_stride, make_ratio((double)ratio, 0),
+                                    (aslam_match *)(base + o_match), nq, (int32_t *)(base + o_nout), nullptr, nullptr);
+    if (rc) return rc;
+    ASLAM_CUDA(cudaMemcpyAsync(nout, base + o_nout, sizeof(int32_t) * (size_t)nsets, cudaMemcpyDeviceToHost, ctx->stream));
+    ASLAM_CUDA(cudaMemcpyAsync(out, base + o_match, sizeof(aslam_match) * (size_t)nsets * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ASLAM_OK;
+}
+
+extern "C" int aslam_loop_merge_top2_device(aslam_ctx *ctx, const uint64_t *d_parts, int nparts, int nq, uint64_t *d_out)
+{
+    ASLAM_REQUIRE(ctx && d_parts && d_out, "NULL argument");
+    ASLAM_REQUIRE(nparts >= 1 && nq >= 0, "bad sizes");
+    if (nq == 0) return ASLAM_OK;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    ProfScope ps(ctx, PK_MERGE);
+    merge_top2_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
+        (const unsigned long long *)d_parts, nparts, nq, (unsigned long long *)d_out);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}

@@ -1,0 +1,62 @@
+// Hamming kNN (k=2) building blocks shared by the matcher, the tracker and the loop database.
+#pragma once
+#include "common.cuh"
+
+namespace aslam {
+
+// One scan of a query set against a row range of a train set.  Counts may live on the device
+// (results of an extraction that has not been read back): *_dev overrides the host value.
+struct KnnProblem {
+    const uint8_t *q;     // query rows (32 B each, 16-B aligned)
+    const uint8_t *t;     // train rows; reported indices are relative to this base
+    const int32_t *nq_dev;
+    const int32_t *nt_dev;
+    int32_t nq, nt;       // host-known counts, or capacities when *_dev is set
+    int32_t t_lo, t_hi;   // rows of t this problem scans
+};
+
+// Packed neighbour: distance in the top 9 bits, train row in the low 23 (rows < 2^23 per
+// problem).  Unsigned order of keys == lexicographic (distance, row); empty == 0xFFFFFFFF.
+constexpr int KEY_IDX_BITS = 23;
+constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+constexpr int KNN_MAX_ROWS = 1 << KEY_IDX_BITS;
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_RQ = 4;                          // queries held in registers per thread
+constexpr int KNN_QBLOCK = KNN_THREADS * KNN_RQ;   // queries per CTA
+
+struct RatioTest {
+    double ratio;
+    int as_double;   // 0: float arithmetic (CudaMatcher.cpp:60); 1: double (LoopClosure.cpp:92)
+    int disabled;    // ratio < 0: keep every query that has two neighbours (extension)
+};
+
+// Number of row ranges to cut a train set into so the grid covers the GPU a few times.
+int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets);
+// d_probs[0..splits) = the pair (q, t) cut into equal row ranges (device-side table build).
+int launch_fill_split_problems(aslam_ctx *ctx, KnnProblem *d_probs, const uint8_t *q, const uint8_t *t,
+                               const int32_t *nq_dev, const int32_t *nt_dev, int nq, int nt, int splits);
+
+// partial[slot * q_stride + q] = (best, second) keys of problem `slot`.
+int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int max_nq,
+                        uint2 *d_partial, int q_stride);
+
+// Groups of `splits` consecutive slots are merged per query; survivors of the ratio test are
+// written in query order to d_out[group * out_stride ...], their number to d_nout[group].
+// d_raw_idx/d_raw_dist (optional, [group][q_stride][2]) receive the merged neighbours.
+int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
+                               int ngroups, int splits, int q_stride, RatioTest rt,
+                               aslam_match *d_out, int out_stride, int32_t *d_nout,
+                               int32_t *d_raw_idx, int32_t *d_raw_dist);
+
+// One count per slot: queries passing the ratio test within that slot alone.
+int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
+                              int nslots, int q_stride, RatioTest rt, int32_t *d_good);
+
+// All slots merged into one top-2 per query, as 64-bit keys (distance << 40 | row_base + row
+// + slot_row_offset), where slot rows are relative to the problem's t base and row_base is
+// added on top.
+int launch_knn2_finish_global(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
+                              int q_stride, int64_t row_base, uint64_t *d_top2);
+
+}  // namespace aslam

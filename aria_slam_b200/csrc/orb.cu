@@ -1,0 +1,436 @@
+// ORB extractor handle: memory plan in HBM, launch sequence, host/device entry points and the
+// batched extract+match ("track") path.
+//
+// Stands in for OrbCudaExtractor (src/adapters/gpu/OrbCudaExtractor.cpp) and the legacy Frame
+// constructors (src/legacy/Frame.cpp:6-49) of the reference.
+#include <vector>
+
+#include "match.cuh"
+#include "orb_kernels.cuh"
+
+using namespace aslam;
+
+static const int8_t k_brief_pattern[256][4] = {
+#include "brief_pattern_31.inc"
+};
+
+struct aslam_orb {
+    aslam_ctx *ctx = nullptr;
+    aslam_orb_params prm{};
+    int width = 0, height = 0, max_batch = 0;
+    OrbGeom g{};
+    OrbBuffers b{};
+    uint32_t *d_tabs = nullptr;
+    uint32_t *d_pattern = nullptr;
+    // tracking
+    aslam_match *d_matches = nullptr;      // [B][kp_cap]
+    int32_t *d_match_counts = nullptr;     // [B]
+    KnnProblem *d_probs = nullptr;
+    uint2 *d_partial = nullptr;
+    int track_splits = 1;
+    bool have_carry = false;
+    // box filter scratch
+    aslam_box *d_boxes = nullptr; int boxes_cap = 0;
+    aslam_keypoint *d_tmp_kps = nullptr; uint8_t *d_tmp_desc = nullptr;
+    // staging for host images when row_stride != pitch of level 0 is handled by cudaMemcpy2DAsync
+    int pending = 0;        // frames of the call awaiting sync (0 = none)
+    bool pending_track = false;
+    // pinned result staging
+    int32_t *h_counts = nullptr;   // [B+1] counts, [B+1] overflow, [B] match counts
+};
+
+static void orb_free_buffers(aslam_orb *o)
+{
+    cudaFree(o->b.pyr); cudaFree(o->b.blur); cudaFree(o->b.mask); cudaFree(o->b.cand); cudaFree(o->b.cand_cnt);
+    cudaFree(o->b.tile_base); cudaFree(o->b.surv); cudaFree(o->b.hresp); cudaFree(o->b.sel_xy);
+    cudaFree(o->b.sel_resp); cudaFree(o->b.sel_cnt); cudaFree(o->b.kps); cudaFree(o->b.desc);
+    cudaFree(o->b.counts); cudaFree(o->b.overflow); cudaFree(o->d_tabs);
+    cudaFree(o->d_matches); cudaFree(o->d_match_counts); cudaFree(o->d_probs); cudaFree(o->d_partial);
+    cudaFree(o->d_tmp_kps); cudaFree(o->d_tmp_desc);
+    if (o->h_counts) cudaFreeHost(o->h_counts);
+    o->b = OrbBuffers();
+    o->d_tabs = nullptr; o->d_matches = nullptr; o->d_match_counts = nullptr; o->d_probs = nullptr;
+    o->d_partial = nullptr; o->d_tmp_kps = nullptr; o->d_tmp_desc = nullptr; o->h_counts = nullptr;
+}
+
+__global__ void fill_track_problems_kernel(KnnProblem *probs, const uint8_t *desc, const int32_t *counts,
+                                           int n, int splits, int kp_cap, int rows_per)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * splits) return;
+    const int f = i / splits, s = i - f * splits;
+    KnnProblem P;
+    P.q = desc + (size_t)(f + 1) * kp_cap * 32;      // frame f of the batch lives in slot f+1
+    P.t = desc + (size_t)f * kp_cap * 32;            // its predecessor (slot 0 = carry)
+    P.nq_dev = counts + f + 1; P.nt_dev = counts + f;
+    P.nq = kp_cap; P.nt = kp_cap;
+    P.t_lo = min(s * rows_per, kp_cap);
+    P.t_hi = min((s + 1) * rows_per, kp_cap);
+    probs[i] = P;
+}
+
+static int orb_plan(aslam_orb *o)
+{
+    aslam_ctx *ctx = o->ctx;
+    std::vector<uint32_t> tabs;
+    build_orb_geometry(o->width, o->height, o->prm.nfeatures, o->prm.scale_factor, o->prm.nlevels,
+                       o->prm.edge_threshold, o->prm.fast_threshold, o->prm.blur_mode, o->g, tabs);
+    const OrbGeom &g = o->g;
+    const size_t B = (size_t)o->max_batch;
+    const size_t tiles = (size_t)(g.tiles_per_frame > 0 ? g.tiles_per_frame : 1);
+    OrbBuffers &b = o->b;
+    ASLAM_CUDA(cudaMalloc(&b.pyr, B * g.pyr_stride + 256));
+    ASLAM_CUDA(cudaMalloc(&b.blur, B * g.pyr_stride + 256));
+    ASLAM_CUDA(cudaMalloc(&b.cand, sizeof(uint32_t) * B * tiles * FT_CAP));
+    ASLAM_CUDA(cudaMalloc(&b.cand_cnt, sizeof(uint32_t) * B * tiles));
+    ASLAM_CUDA(cudaMalloc(&b.tile_base, sizeof(uint32_t) * B * tiles));
+    ASLAM_CUDA(cudaMalloc(&b.surv, sizeof(uint32_t) * B * tiles * FT_CAP));
+    ASLAM_CUDA(cudaMalloc(&b.hresp, sizeof(float) * B * tiles * FT_CAP));
+    ASLAM_CUDA(cudaMalloc(&b.sel_xy, sizeof(uint32_t) * B * g.kp_cap));
+    ASLAM_CUDA(cudaMalloc(&b.sel_resp, sizeof(float) * B * g.kp_cap));
+    ASLAM_CUDA(cudaMalloc(&b.sel_cnt, sizeof(int32_t) * B * ORB_MAX_LEVELS));
+    ASLAM_CUDA(cudaMalloc(&b.kps, sizeof(aslam_keypoint) * (B + 1) * g.kp_cap));
+    ASLAM_CUDA(cudaMalloc(&b.desc, (B + 1) * g.kp_cap * 32));
+    ASLAM_CUDA(cudaMalloc(&b.counts, sizeof(int32_t) * (B + 1)));
+    ASLAM_CUDA(cudaMalloc(&b.overflow, sizeof(int32_t) * (B + 1)));
+    ASLAM_CUDA(cudaMemsetAsync(b.counts, 0, sizeof(int32_t) * (B + 1), ctx->stream));
+    ASLAM_CUDA(cudaMemsetAsync(b.overflow, 0, sizeof(int32_t) * (B + 1), ctx->stream));
+    ASLAM_CUDA(cudaMemsetAsync(b.sel_cnt, 0, sizeof(int32_t) * B * ORB_MAX_LEVELS, ctx->stream));
+    ASLAM_CUDA(cudaMalloc(&o->d_tabs, sizeof(uint32_t) * (tabs.size() + 4)));
+    if (!tabs.empty())
+        ASLAM_CUDA(cudaMemcpyAsync(o->d_tabs, tabs.data(), sizeof(uint32_t) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    b.tabs = o->d_tabs;
+    b.pattern = o->d_pattern;
+    // tracking scratch
+    o->track_splits = choose_splits(ctx, g.kp_cap, g.kp_cap, o->max_batch);
+    ASLAM_CUDA(cudaMalloc(&o->d_matches, sizeof(aslam_match) * B * g.kp_cap));
+    ASLAM_CUDA(cudaMalloc(&o->d_match_counts, sizeof(int32_t) * B));
+    ASLAM_CUDA(cudaMalloc(&o->d_probs, sizeof(KnnProblem) * B * o->track_splits));
+    ASLAM_CUDA(cudaMalloc(&o->d_partial, sizeof(uint2) * B * o->track_splits * g.kp_cap));
+    ASLAM_CUDA(cudaMalloc(&o->d_tmp_kps, sizeof(aslam_keypoint) * g.kp_cap));
+    ASLAM_CUDA(cudaMalloc(&o->d_tmp_desc, (size_t)g.kp_cap * 32));
+    ASLAM_CUDA(cudaMallocHost(&o->h_counts, sizeof(int32_t) * (3 * B + 2)));
+    ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));   // tabs is a local
+    o->have_carry = false;
+    return ASLAM_OK;
+}
+
+extern "C" {
+
+void aslam_orb_default_params(aslam_orb_params *p)
+{
+    if (!p) return;
+    p->nfeatures = 1000; p->scale_factor = 1.2f; p->nlevels = 8; p->edge_threshold = 31;
+    p->first_level = 0; p->wta_k = 2; p->score_type = 0; p->patch_size = 31; p->fast_threshold = 20;
+    p->blur_mode = 2;
+}
+
+static int check_params(const aslam_orb_params *p, int width, int height, int max_batch)
+{
+    ASLAM_REQUIRE(p->nfeatures >= 0, "nfeatures must be >= 0");
+    ASLAM_REQUIRE(p->nlevels >= 1 && p->nlevels <= ORB_MAX_LEVELS, "nlevels must be 1..8");
+    ASLAM_REQUIRE(p->scale_factor > 1.0f && p->scale_factor <= 2.0f, "scale_factor must be in (1, 2]");
+    ASLAM_REQUIRE(p->edge_threshold >= 19 && p->edge_threshold <= 1024, "edge_threshold must be >= 19 (rBRIEF reach)");
+    ASLAM_REQUIRE(p->first_level == 0 && p->wta_k == 2 && p->score_type == 0 && p->patch_size == 31,
+                  "only first_level 0, WTA_K 2, HARRIS_SCORE, patch 31 are implemented (the reference's values)");
+    ASLAM_REQUIRE(p->fast_threshold >= 1 && p->fast_threshold <= 254, "fast_threshold must be 1..254");
+    ASLAM_REQUIRE(p->blur_mode >= 0 && p->blur_mode <= 2, "blur_mode must be 0..2");
+    ASLAM_REQUIRE(width >= 1 && height >= 1 && width <= 4095 && height <= 4095, "frame size must be 1..4095 per side");
+    ASLAM_REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch must be 1..4096");
+    return ASLAM_OK;
+}
+
+int aslam_orb_create(aslam_ctx *ctx, const aslam_orb_params *p, int width, int height, int max_batch, aslam_orb **out)
+{
+    ASLAM_REQUIRE(ctx && p && out, "NULL argument");
+    *out = nullptr;
+    int rc = check_params(p, width, height, max_batch);
+    if (rc) return rc;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    aslam_orb *o = new aslam_orb();
+    o->ctx = ctx; o->prm = *p; o->width = width; o->height = height; o->max_batch = max_batch;
+    uint32_t packed[256];
+    for (int i = 0; i < 256; ++i)
+        packed[i] = (uint32_t)(uint8_t)k_brief_pattern[i][0] | ((uint32_t)(uint8_t)k_brief_pattern[i][1] << 8) |
+                    ((uint32_t)(uint8_t)k_brief_pattern[i][2] << 16) | ((uint32_t)(uint8_t)k_brief_pattern[i][3] << 24);
+    cudaError_t e = cudaMalloc(&o->d_pattern, sizeof(packed));
+    if (e == cudaSuccess) e = cudaMemcpy(o->d_pattern, packed, sizeof(packed), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete o; return fail(ASLAM_E_CUDA, "pattern upload -> %s", cudaGetErrorString(e)); }
+    rc = orb_plan(o);
+    if (rc) { orb_free_buffers(o); cudaFree(o->d_pattern); delete o; return rc; }
+    *out = o;
+    return ASLAM_OK;
+}
+
+void aslam_orb_destroy(aslam_orb *o)
+{
+    if (!o) return;
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
+    orb_free_buffers(o);
+    cudaFree(o->d_pattern);
+    cudaFree(o->d_boxes);
+    delete o;
+}
+
+int aslam_orb_set_max_features(aslam_orb *o, int nfeatures)
+{
+    ASLAM_REQUIRE(o, "orb is NULL");
+    ASLAM_REQUIRE(nfeatures >= 0, "nfeatures must be >= 0");
+    if (o->pending) return fail(ASLAM_E_STATE, "set_max_features with an extract pending");
+    ASLAM_CUDA(cudaSetDevice(o->ctx->device));
+    ASLAM_CUDA(cudaStreamSynchronize(o->ctx->stream));
+    // OrbCudaExtractor.cpp:212-216 re-creates the detector with only nfeatures set: defaults elsewhere.
+    const int blur_mode = o->prm.blur_mode;
+    aslam_orb_default_params(&o->prm);
+    o->prm.nfeatures = nfeatures;
+    o->prm.blur_mode = blur_mode;
+    orb_free_buffers(o);
+    return orb_plan(o);
+}
+
+int aslam_orb_get_max_features(const aslam_orb *o) { return o ? o->prm.nfeatures : 0; }
+int aslam_orb_capacity(const aslam_orb *o) { return o ? o->g.kp_cap : 0; }
+
+int aslam_orb_level_size(const aslam_orb *o, int level, int *w, int *h)
+{
+    ASLAM_REQUIRE(o && w && h, "NULL argument");
+    ASLAM_REQUIRE(level >= 0 && level < o->g.nlevels, "level out of range");
+    *w = o->g.lv[level].w; *h = o->g.lv[level].h;
+    return ASLAM_OK;
+}
+
+}  // extern "C"
+
+// Enqueue the whole extraction of n frames whose level-0 pixels (and masks) are already in place.
+static int orb_enqueue(aslam_orb *o, int n, bool with_mask)
+{
+    aslam_ctx *ctx = o->ctx;
+    const OrbGeom &g = o->g;
+    OrbBuffers b = o->b;
+    if (!with_mask) b.mask = nullptr;
+    int rc;
+    ASLAM_CUDA(cudaMemsetAsync(o->b.overflow + 1, 0, sizeof(int32_t) * n, ctx->stream));
+    for (int l = 1; l < g.nbuilt; ++l) {
+        if ((rc = launch_resize_level(ctx, g, b, l, n, false))) return rc;
+        if (with_mask && (rc = launch_resize_level(ctx, g, b, l, n, true))) return rc;
+    }
+    if ((rc = launch_fast(ctx, g, b, n))) return rc;
+    if ((rc = launch_blur(ctx, g, b, n))) return rc;
+    if ((rc = launch_select(ctx, g, b, n))) return rc;
+    if ((rc = launch_describe(ctx, g, b, n))) return rc;
+    return ASLAM_OK;
+}
+
+static int orb_upload(aslam_orb *o, uint8_t *dst_base, const uint8_t *src, int n, size_t frame_stride,
+                      int row_stride, cudaMemcpyKind kind)
+{
+    const OrbGeom &g = o->g;
+    const LevelGeom &L0 = g.lv[0];
+    if (g.nbuilt == 0) return ASLAM_OK;
+    // level 0 of frame i sits at dst_base + i*pyr_stride (off 0); one 2-D copy per frame keeps
+    // the caller's row stride and ours independent.  A single 3-D-shaped copy is possible when
+    // both strides are uniform, which cudaMemcpy2DAsync expresses when rows are contiguous.
+    if ((size_t)row_stride == (size_t)L0.pitch && frame_stride == (size_t)L0.pitch * L0.h && g.pyr_stride == frame_stride) {
+        ASLAM_CUDA(cudaMemcpyAsync(dst_base, src, frame_stride * n, kind, o->ctx->stream));
+        return ASLAM_OK;
+    }
+    if ((size_t)row_stride == (size_t)L0.pitch && frame_stride >= (size_t)L0.pitch * L0.h) {
+        // whole frames as "rows" of a 2-D copy
+        ASLAM_CUDA(cudaMemcpy2DAsync(dst_base, g.pyr_stride, src, frame_stride, (size_t)L0.pitch * L0.h, n, kind, o->ctx->stream));
+        return ASLAM_OK;
+    }
+    for (int i = 0; i < n; ++i)
+        ASLAM_CUDA(cudaMemcpy2DAsync(dst_base + (size_t)i * g.pyr_stride, L0.pitch, src + (size_t)i * frame_stride,
+                                     row_stride, L0.w, L0.h, kind, o->ctx->stream));
+    return ASLAM_OK;
+}
+
+static int orb_prepare_mask(aslam_orb *o)
+{
+    if (!o->b.mask) ASLAM_CUDA(cudaMalloc(&o->b.mask, (size_t)o->max_batch * o->g.pyr_stride + 256));
+    return ASLAM_OK;
+}
+
+static int orb_extract_common(aslam_orb *o, const uint8_t *images, int n, size_t frame_stride, int row_stride,
+                              const uint8_t *masks, cudaMemcpyKind kind)
+{
+    ASLAM_REQUIRE(o && images, "NULL argument");
+    ASLAM_REQUIRE(n >= 1 && n <= o->max_batch, "n must be 1..max_batch");
+    ASLAM_REQUIRE(row_stride >= o->width, "row_stride smaller than width");
+    ASLAM_REQUIRE(n == 1 || frame_stride >= (size_t)row_stride * (o->height - 1) + o->width, "frame_stride too small");
+    if (o->pending) return fail(ASLAM_E_STATE, "an extract is already pending on this handle; call sync first");
+    ASLAM_CUDA(cudaSetDevice(o->ctx->device));
+    int rc;
+    if ((rc = orb_upload(o, o->b.pyr, images, n, frame_stride, row_stride, kind))) return rc;
+    if (masks) {
+        if ((rc = orb_prepare_mask(o))) return rc;
+        if ((rc = orb_upload(o, o->b.mask, masks, n, (size_t)o->width * o->height, o->width, kind))) return rc;
+    }
+    if ((rc = orb_enqueue(o, n, masks != nullptr))) return rc;
+    o->pending = n;
+    o->pending_track = false;
+    return ASLAM_OK;
+}
+
+extern "C" {
+
+int aslam_orb_extract_async(aslam_orb *o, const uint8_t *image, int width, int height, int row_stride,
+                            const uint8_t *mask, const aslam_box *boxes, int nboxes)
+{
+    ASLAM_REQUIRE(o, "orb is NULL");
+    ASLAM_REQUIRE(width == o->width && height == o->height, "frame size differs from the handle's");
+    ASLAM_REQUIRE(nboxes >= 0 && (nboxes == 0 || boxes), "bad boxes");
+    int rc = orb_extract_common(o, image, 1, 0, row_stride, mask, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    if (nboxes > 0) {
+        aslam_ctx *ctx = o->ctx;
+        if (nboxes > o->boxes_cap) {
+            if (o->d_boxes) ASLAM_CUDA(cudaFree(o->d_boxes));
+            o->d_boxes = nullptr;
+            ASLAM_CUDA(cudaMalloc(&o->d_boxes, sizeof(aslam_box) * (size_t)(nboxes + 64)));
+            o->boxes_cap = nboxes + 64;
+        }
+        ASLAM_CUDA(cudaMemcpyAsync(o->d_boxes, boxes, sizeof(aslam_box) * (size_t)nboxes, cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_box_filter(ctx, o->g, o->b, 1, o->d_boxes, nboxes, o->d_tmp_kps, o->d_tmp_desc);
+    }
+    return rc;
+}
+
+int aslam_orb_extract_batch_async(aslam_orb *o, const uint8_t *images, int n, size_t frame_stride, int row_stride,
+                                  const uint8_t *masks)
+{
+    return orb_extract_common(o, images, n, frame_stride, row_stride, masks, cudaMemcpyHostToDevice);
+}
+
+int aslam_orb_extract_batch_device(aslam_orb *o, const uint8_t *d_images, int n, size_t frame_stride, int row_stride,
+                                   const uint8_t *d_masks)
+{
+    return orb_extract_common(o, d_images, n, frame_stride, row_stride, d_masks, cudaMemcpyDeviceToDevice);
+}
+
+int aslam_orb_device_results(aslam_orb *o, const aslam_keypoint **d_kps, const uint8_t **d_desc, const int32_t **d_counts)
+{
+    ASLAM_REQUIRE(o, "orb is NULL");
+    if (d_kps) *d_kps = o->b.kps + o->g.kp_cap;
+    if (d_desc) *d_desc = o->b.desc + (size_t)o->g.kp_cap * 32;
+    if (d_counts) *d_counts = o->b.counts + 1;
+    o->pending = 0;     // the caller reads in stream order on the device
+    return ASLAM_OK;
+}
+
+static int orb_collect(aslam_orb *o, aslam_keypoint *kps, uint8_t *desc, int32_t *counts,
+                       aslam_match *matches, int32_t *match_counts)
+{
+    ASLAM_REQUIRE(o, "orb is NULL");
+    if (!o->pending) return fail(ASLAM_E_STATE, "sync without a pending extract");
+    aslam_ctx *ctx = o->ctx;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    const int n = o->pending;
+    const size_t cap = (size_t)o->g.kp_cap;
+    const size_t B = (size_t)o->max_batch;
+    int32_t *h_cnt = o->h_counts, *h_ovf = o->h_counts + (B + 1), *h_mc = o->h_counts + 2 * (B + 1);
+    ASLAM_CUDA(cudaMemcpyAsync(h_cnt, o->b.counts + 1, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ASLAM_CUDA(cudaMemcpyAsync(h_ovf, o->b.overflow + 1, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kps) ASLAM_CUDA(cudaMemcpyAsync(kps, o->b.kps + cap, sizeof(aslam_keypoint) * cap * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) ASLAM_CUDA(cudaMemcpyAsync(desc, o->b.desc + cap * 32, cap * 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o->pending_track) {
+        if (match_counts) ASLAM_CUDA(cudaMemcpyAsync(h_mc, o->d_match_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (matches) ASLAM_CUDA(cudaMemcpyAsync(matches, o->d_matches, sizeof(aslam_match) * cap * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    o->pending = 0;
+    int ovf = 0;
+    for (int i = 0; i < n; ++i) {
+        if (counts) counts[i] = h_cnt[i];
+        if (o->pending_track && match_counts) match_counts[i] = h_mc[i];
+        ovf |= h_ovf[i];
+    }
+    if (ovf) return fail(ASLAM_E_OVERFLOW, "a pyramid level had more tied keypoints than its %d spare rows; output clipped", SEL_TIE_ROOM);
+    return ASLAM_OK;
+}
+
+int aslam_orb_sync(aslam_orb *o, aslam_keypoint *kps, uint8_t *desc, int32_t *counts)
+{
+    return orb_collect(o, kps, desc, counts, nullptr, nullptr);
+}
+
+int aslam_orb_track_batch_async(aslam_orb *o, const uint8_t *images, int n, size_t frame_stride, int row_stride,
+                                float ratio, int images_on_device)
+{
+    ASLAM_REQUIRE(o, "orb is NULL");
+    int rc = orb_extract_common(o, images, n, frame_stride, row_stride, nullptr,
+                                images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    aslam_ctx *ctx = o->ctx;
+    const OrbGeom &g = o->g;
+    const int cap = g.kp_cap, splits = o->track_splits;
+    if (!o->have_carry) ASLAM_CUDA(cudaMemsetAsync(o->b.counts, 0, sizeof(int32_t), ctx->stream));
+    const int rows_per = (cap + splits - 1) / splits;
+    {
+    ProfScope ps(ctx, PK_MISC);
+    fill_track_problems_kernel<<<(n * splits + 127) / 128, 128, 0, ctx->stream>>>(o->d_probs, o->b.desc, o->b.counts,
+                                                                                  n, splits, cap, rows_per);
+    }
+    ASLAM_LAUNCH_CHECK();
+    if ((rc = launch_knn2_partial(ctx, o->d_probs, n * splits, cap, o->d_partial, cap))) return rc;
+    RatioTest rt; rt.ratio = (double)ratio; rt.as_double = 0; rt.disabled = ratio < 0;
+    if ((rc = launch_knn2_finish_matches(ctx, o->d_probs, o->d_partial, n, splits, cap, rt, o->d_matches, cap,
+                                         o->d_match_counts, nullptr, nullptr))) return rc;
+    // carry the last frame of this batch into slot 0 for the next call
+    ASLAM_CUDA(cudaMemcpyAsync(o->b.desc, o->b.desc + (size_t)n * cap * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    ASLAM_CUDA(cudaMemcpyAsync(o->b.kps, o->b.kps + (size_t)n * cap, sizeof(aslam_keypoint) * cap, cudaMemcpyDeviceToDevice, ctx->stream));
+    ASLAM_CUDA(cudaMemcpyAsync(o->b.counts, o->b.counts + n, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    o->have_carry = true;
+    o->pending_track = true;
+    return ASLAM_OK;
+}
+
+int aslam_orb_track_sync(aslam_orb *o, aslam_keypoint *kps, uint8_t *desc, int32_t *counts,
+                         aslam_match *matches, int32_t *match_counts)
+{
+    return orb_collect(o, kps, desc, counts, matches, match_counts);
+}
+
+int aslam_orb_read_level(aslam_orb *o, int frame, int level, int blurred, uint8_t *out)
+{
+    ASLAM_REQUIRE(o && out, "NULL argument");
+    ASLAM_REQUIRE(frame >= 0 && frame < o->max_batch, "frame out of range");
+    ASLAM_REQUIRE(level >= 0 && level < o->g.nbuilt, "level not built (it cannot hold keypoints)");
+    const LevelGeom &L = o->g.lv[level];
+    ASLAM_CUDA(cudaSetDevice(o->ctx->device));
+    ASLAM_CUDA(cudaStreamSynchronize(o->ctx->stream));
+    const uint8_t *src = (blurred ? o->b.blur : o->b.pyr) + (size_t)frame * o->g.pyr_stride + L.off;
+    ASLAM_CUDA(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ASLAM_OK;
+}
+
+int aslam_orb_read_corners(aslam_orb *o, int frame, int level, uint32_t *out, int cap, int *n)
+{
+    ASLAM_REQUIRE(o && n && (out || cap == 0), "NULL argument");
+    ASLAM_REQUIRE(frame >= 0 && frame < o->max_batch, "frame out of range");
+    ASLAM_REQUIRE(level >= 0 && level < o->g.nlevels, "level out of range");
+    *n = 0;
+    const LevelGeom &L = o->g.lv[level];
+    const int ntiles = level < o->g.nbuilt ? L.tiles_x * L.tiles_y : 0;
+    if (ntiles == 0) return ASLAM_OK;
+    ASLAM_CUDA(cudaSetDevice(o->ctx->device));
+    ASLAM_CUDA(cudaStreamSynchronize(o->ctx->stream));
+    std::vector<uint32_t> cnt((size_t)ntiles), tile((size_t)FT_CAP);
+    const size_t tile0 = (size_t)frame * o->g.tiles_per_frame + L.tile_off;
+    ASLAM_CUDA(cudaMemcpy(cnt.data(), o->b.cand_cnt + tile0, sizeof(uint32_t) * ntiles, cudaMemcpyDeviceToHost));
+    int total = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int c = (int)cnt[t];
+        if (c > FT_CAP) return fail(ASLAM_E_STATE, "tile %d reports %d corners", t, c);
+        if (c) ASLAM_CUDA(cudaMemcpy(tile.data(), o->b.cand + (tile0 + t) * FT_CAP, sizeof(uint32_t) * c, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c; ++i) {
+            if (total < cap) out[total] = tile[i];
+            ++total;
+        }
+    }
+    *n = total;
+    return ASLAM_OK;
+}
+
+}  // extern "C"

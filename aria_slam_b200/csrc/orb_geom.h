@@ -1,0 +1,47 @@
+// Level geometry of the ORB pyramid and the per-frame memory layout in HBM.
+// Arithmetic follows cv::ORB_Impl (OpenCV features2d/orb.cpp) as the reference's CPU path
+// reaches it (src/legacy/Frame.cpp:47); see SURVEY.md Appendix A1/A2.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace aslam {
+
+constexpr int ORB_MAX_LEVELS = 8;
+// FAST work tile: 62x30 output pixels from a 64x32 score block and a 70x38 pixel block.
+constexpr int FT_OUT_W = 62, FT_OUT_H = 30;
+constexpr int FT_SCORE_W = 64, FT_SCORE_H = 32;
+constexpr int FT_PIX_W = 70, FT_PIX_H = 38;
+// No two 3x3-strict maxima are 8-neighbours, so a 62x30 tile holds at most 31*15 = 465 corners.
+constexpr int FT_CAP = 512;
+constexpr int SEL_TIE_ROOM = 64;   // extra output rows per level for tied Harris responses
+
+struct LevelGeom {
+    int w, h, pitch;         // pitch: bytes per row, multiple of 16
+    unsigned int off;        // byte offset of the level inside a frame's pyramid block
+    int tiles_x, tiles_y;    // FAST tiles covering [edge, w-edge) x [edge, h-edge)
+    int tile_off;            // first tile index of this level within the frame
+    int quota;               // N_l
+    int sel_off, sel_cap;    // rows of this level in the per-frame selection buffer
+    int xtab_off, ytab_off;  // resize tables (level l-1 -> l), in uint32 entries
+    int row_fused_end;       // blur: row-pass columns below this use fused multiply-add
+    int col_fused_end;
+    float sf;                // scale of the level
+};
+
+struct OrbGeom {
+    int nlevels;             // as requested (quotas are spread over all of them)
+    int nbuilt;              // levels 0..nbuilt-1 exist in memory (those that can hold keypoints, chained)
+    int width, height, edge, fast_thr;
+    int tiles_per_frame;
+    int kp_cap;              // keypoint rows per frame in the output buffers
+    unsigned int pyr_stride; // bytes per frame of pyramid (and of blurred pyramid, and of mask pyramid)
+    LevelGeom lv[ORB_MAX_LEVELS];
+};
+
+// Fills g and the resize tables (entry = ofs | c1 << 16; c0 = 256 - c1 applies to p[ofs]).
+void build_orb_geometry(int width, int height, int nfeatures, float scale_factor, int nlevels,
+                        int edge, int fast_thr, int blur_mode, OrbGeom &g, std::vector<uint32_t> &tables);
+
+}  // namespace aslam

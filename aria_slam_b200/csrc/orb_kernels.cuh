@@ -1,0 +1,41 @@
+// Device kernels of the ORB extractor (sm_100a).  One batch = `nframes` frames of one size; every
+// kernel is launched once per batch (the resize once per level) with blockIdx.z / .y = frame.
+//
+// Per-frame HBM layout (OrbGeom): pyramid levels packed back to back, 16-B aligned rows; the
+// blurred pyramid and the optional mask pyramid use the same layout.
+#pragma once
+#include "common.cuh"
+#include "orb_geom.h"
+
+namespace aslam {
+
+struct OrbBuffers {
+    uint8_t *pyr;          // [B][pyr_stride]
+    uint8_t *blur;         // [B][pyr_stride]
+    uint8_t *mask;         // [B][pyr_stride] or NULL
+    const uint32_t *tabs;  // resize tables
+    uint32_t *cand;        // [B][tiles_per_frame][FT_CAP]  score<<24 | y<<12 | x
+    uint32_t *cand_cnt;    // [B][tiles_per_frame]
+    uint32_t *tile_base;   // [B][tiles_per_frame]  scratch of the selection kernel
+    uint32_t *surv;        // [B][tiles_per_frame][FT_CAP] (only the head of each level's range is used)
+    float *hresp;          // same shape as surv
+    uint32_t *sel_xy;      // [B][kp_cap]  y<<12 | x, level ranges at LevelGeom::sel_off
+    float *sel_resp;       // [B][kp_cap]
+    int32_t *sel_cnt;      // [B][ORB_MAX_LEVELS]
+    aslam_keypoint *kps;   // [B+1][kp_cap]   slot 0 = carry of the previous batch (tracking)
+    uint8_t *desc;         // [B+1][kp_cap][32]
+    int32_t *counts;       // [B+1]
+    int32_t *overflow;     // [B+1]
+    const uint32_t *pattern;   // 256 x (x0,y0,x1,y1) packed as int8x4
+};
+
+int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask);
+int launch_fast(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);
+int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);
+int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);
+int launch_describe(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);
+// SlamPipeline::filterDynamicKeypoints: drop keypoints inside boxes of dynamic classes, keeping order.
+int launch_box_filter(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int frame_slot,
+                      const aslam_box *d_boxes, int nboxes, aslam_keypoint *tmp_kps, uint8_t *tmp_desc);
+
+}  // namespace aslam

@@ -1,0 +1,242 @@
+/* aslam_b200.h -- C ABI of the B200 (sm_100a) ORB frontend: extraction, Hamming kNN matching and the
+ * loop-closure descriptor query of robertteleng/aria-slam.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only; caller owns every host buffer,
+ * the library owns all device memory; no exception crosses it.  Every entry point returns an
+ * aslam_status (0 = ok) and aslam_last_error() gives the message for the calling thread.
+ *
+ * Each group cites the reference interface it stands in for (paths relative to the reference
+ * repository).  The C++ adapters in aria_slam_b200/adapters/ bind these to the reference's own
+ * abstract classes (include/interfaces/IFeatureExtractor.hpp, IMatcher.hpp, ILoopDetector.hpp);
+ * INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Threading contract (same as the reference adapters, OrbCudaExtractor.hpp:48): one handle,
+ * one CUDA stream, one caller thread at a time.
+ */
+#ifndef ASLAM_B200_H
+#define ASLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASLAM_API __attribute__((visibility("default")))
+
+typedef enum {
+    ASLAM_OK = 0,
+    ASLAM_E_INVALID = 1,     /* bad argument */
+    ASLAM_E_CUDA = 2,        /* a CUDA runtime call failed; message carries the CUDA error */
+    ASLAM_E_NOMEM = 3,
+    ASLAM_E_STATE = 4,       /* call order violated (e.g. sync without a pending extract) */
+    ASLAM_E_OVERFLOW = 5,    /* results were produced but a capacity clipped them (see call) */
+    ASLAM_E_NODEVICE = 6     /* no CUDA device: there is no CPU fallback on this path */
+} aslam_status;
+
+typedef struct aslam_ctx aslam_ctx;
+typedef struct aslam_orb aslam_orb;
+typedef struct aslam_loopdb aslam_loopdb;
+
+/* aria::core::KeyPoint, include/core/Types.hpp:9-15 (24 bytes, same field order) */
+typedef struct {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+} aslam_keypoint;
+
+/* aria::core::Match, include/core/Types.hpp:97-101 */
+typedef struct {
+    int32_t query_idx;
+    int32_t train_idx;
+    float distance;
+} aslam_match;
+
+/* aria::core::Detection, include/core/Types.hpp:104-112 */
+typedef struct {
+    float x1, y1, x2, y2;
+    float confidence;
+    int32_t class_id;
+} aslam_box;
+
+/* The argument list of cv::ORB::create as the reference calls it
+ * (src/adapters/gpu/OrbCudaExtractor.cpp:35-45, src/euroc_eval.cpp:88).  Only the values the
+ * reference uses are implemented: first_level 0, wta_k 2, HARRIS score, patch 31. */
+typedef struct {
+    int32_t nfeatures;       /* 1000 / 2000 / 4000 */
+    float scale_factor;      /* 1.2f */
+    int32_t nlevels;         /* 8 (max 8) */
+    int32_t edge_threshold;  /* 31 */
+    int32_t first_level;     /* 0 */
+    int32_t wta_k;           /* 2 */
+    int32_t score_type;      /* 0 = HARRIS_SCORE */
+    int32_t patch_size;      /* 31 */
+    int32_t fast_threshold;  /* 20 */
+    int32_t blur_mode;       /* 2 = cv2-wheel hybrid FMA split, 1 = always fused, 0 = never */
+} aslam_orb_params;
+
+/* ------------------------------------------------------------------ context
+ * Stands in for the adapter constructors' device/stream handling
+ * (OrbCudaExtractor.cpp:21-33, CudaMatcher.cpp:7-19; FactoryConfig::cuda_device,
+ * include/factory/PipelineFactory.hpp:21).  stream = a cudaStream_t to borrow, or NULL to
+ * create (and later destroy) a private one. */
+ASLAM_API int aslam_ctx_create(int device, void *stream, aslam_ctx **out);
+ASLAM_API void aslam_ctx_destroy(aslam_ctx *ctx);
+ASLAM_API int aslam_ctx_sync(aslam_ctx *ctx);
+ASLAM_API void *aslam_ctx_stream(aslam_ctx *ctx);
+ASLAM_API int aslam_ctx_sm_count(aslam_ctx *ctx);
+ASLAM_API const char *aslam_last_error(void);
+ASLAM_API const char *aslam_version(void);
+/* number of this library's kernels launched by the calling process so far */
+ASLAM_API uint64_t aslam_kernel_launches(void);
+/* Optional per-kernel timing: when enabled, every launch on the context is bracketed by a CUDA
+ * event pair on its stream.  aslam_prof_read waits for the stream and returns the accumulated
+ * device time and launch count of one kernel kind (names via aslam_prof_name, 0..count-1). */
+ASLAM_API int aslam_prof_enable(aslam_ctx *ctx, int on);
+ASLAM_API int aslam_prof_count(void);
+ASLAM_API const char *aslam_prof_name(int kind);
+ASLAM_API int aslam_prof_read(aslam_ctx *ctx, int kind, double *total_ms, int64_t *launches, int reset);
+/* pinned host memory for callers that want truly asynchronous H2D/D2H */
+ASLAM_API int aslam_host_alloc(size_t bytes, void **out);
+ASLAM_API int aslam_host_free(void *p);
+
+/* ------------------------------------------------------------------ ORB extraction
+ * Replaces OrbCudaExtractor::extract / extractAsync / sync / setMaxFeatures / getMaxFeatures
+ * (src/adapters/gpu/OrbCudaExtractor.cpp:64-128,136-171,176-210,212-218) and the legacy
+ * Frame constructors (src/legacy/Frame.cpp:6-49).  Results follow the reference's CPU path,
+ * cv::ORB::detectAndCompute.
+ *
+ * A handle is built for one frame size and up to max_batch frames per call. */
+ASLAM_API void aslam_orb_default_params(aslam_orb_params *p);
+ASLAM_API int aslam_orb_create(aslam_ctx *ctx, const aslam_orb_params *p, int width, int height,
+                               int max_batch, aslam_orb **out);
+ASLAM_API void aslam_orb_destroy(aslam_orb *orb);
+/* setMaxFeatures: like the reference (OrbCudaExtractor.cpp:212-216) every other parameter
+ * returns to its default.  Must not be called with an extract pending. */
+ASLAM_API int aslam_orb_set_max_features(aslam_orb *orb, int nfeatures);
+ASLAM_API int aslam_orb_get_max_features(const aslam_orb *orb);
+/* Rows the caller must provide per frame in aslam_orb_sync's kps/desc buffers.  It is
+ * nfeatures plus head-room for response ties, which cv::ORB keeps (KeyPointsFilter::retainBest). */
+ASLAM_API int aslam_orb_capacity(const aslam_orb *orb);
+
+/* Host-buffer path.  image: grayscale, row_stride bytes per row (IFeatureExtractor.hpp:14 is
+ * the tightly packed case row_stride == width).  mask: NULL or width*height bytes, 0 = reject
+ * (cv::ORB's mask argument).  boxes: NULL or detections whose dynamic classes
+ * (src/main.cpp:29-41) remove keypoints inside them after selection
+ * (SlamPipeline::filterDynamicKeypoints, include/pipeline/SlamPipeline.hpp:96-99, using
+ * Detection::contains, include/core/Types.hpp:109-111).
+ * The pixel buffers must stay valid until aslam_orb_sync returns. */
+ASLAM_API int aslam_orb_extract_async(aslam_orb *orb, const uint8_t *image, int width, int height,
+                                      int row_stride, const uint8_t *mask,
+                                      const aslam_box *boxes, int nboxes);
+/* n frames, frame i at images + i*frame_stride.  masks: NULL or n masks, width*height each. */
+ASLAM_API int aslam_orb_extract_batch_async(aslam_orb *orb, const uint8_t *images, int n,
+                                            size_t frame_stride, int row_stride,
+                                            const uint8_t *masks);
+/* Waits, then copies out: kps[n][capacity], desc[n][capacity][32], counts[n].
+ * ASLAM_E_OVERFLOW: a frame had more tied keypoints than capacity; the first capacity (in
+ * level, y, x order) were returned. */
+ASLAM_API int aslam_orb_sync(aslam_orb *orb, aslam_keypoint *kps, uint8_t *desc, int32_t *counts);
+
+/* Device-resident path (inputs already in HBM; results stay there). */
+ASLAM_API int aslam_orb_extract_batch_device(aslam_orb *orb, const uint8_t *d_images, int n,
+                                             size_t frame_stride, int row_stride,
+                                             const uint8_t *d_masks);
+ASLAM_API int aslam_orb_device_results(aslam_orb *orb, const aslam_keypoint **d_kps,
+                                       const uint8_t **d_desc, const int32_t **d_counts);
+
+/* Extract n frames and match frame i (query) against frame i-1 (train) in the same stream;
+ * frame 0 is matched against the last frame of the previous call on this handle (none on the
+ * first call).  One call = the per-frame body of SlamPipeline::processFrame's
+ * extract -> match (docs H12:595-601 of the reference) for a whole batch.
+ * ratio as in IMatcher::match (include/interfaces/IMatcher.hpp:19-24). */
+ASLAM_API int aslam_orb_track_batch_async(aslam_orb *orb, const uint8_t *images, int n,
+                                          size_t frame_stride, int row_stride, float ratio,
+                                          int images_on_device);
+/* As aslam_orb_sync plus matches[n][capacity], match_counts[n].  Any pointer may be NULL to
+ * skip that copy. */
+ASLAM_API int aslam_orb_track_sync(aslam_orb *orb, aslam_keypoint *kps, uint8_t *desc,
+                                   int32_t *counts, aslam_match *matches, int32_t *match_counts);
+
+/* Stage read-back for the parity tests (all after a sync).  level images are W_l x H_l,
+ * tightly packed into out. */
+ASLAM_API int aslam_orb_level_size(const aslam_orb *orb, int level, int *w, int *h);
+ASLAM_API int aslam_orb_read_level(aslam_orb *orb, int frame, int level, int blurred, uint8_t *out);
+/* FAST candidates after NMS/border/mask of one level as packed (score<<24 | y<<12 | x);
+ * returns how many through *n (cap entries written at most). */
+ASLAM_API int aslam_orb_read_corners(aslam_orb *orb, int frame, int level, uint32_t *out, int cap, int *n);
+
+/* ------------------------------------------------------------------ Hamming kNN (k = 2)
+ * Replaces CudaMatcher::match (src/adapters/gpu/CudaMatcher.cpp:28-68) and the inlined twins
+ * src/main.cpp:158-175, src/euroc_eval.cpp:167-175.  Descriptors are rows of 32 bytes.
+ * Results follow cv::BFMatcher(NORM_HAMMING)::knnMatch(k=2): ascending (distance, train index).
+ *
+ * aslam_match_knn2: ratio test d0 < ratio*d1 evaluated in float exactly as CudaMatcher.cpp:60;
+ * out receives at most nq matches in query order; *nout their number.  nt < 2 or nq == 0
+ * yields *nout = 0 (the reference emits a match only when both neighbours exist). */
+ASLAM_API int aslam_match_knn2(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                               float ratio, aslam_match *out, int *nout);
+/* Raw neighbours: idx[nq][2], dist[nq][2]; -1 where fewer than two train rows exist. */
+ASLAM_API int aslam_knn2_raw(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                             int32_t *idx, int32_t *dist);
+/* One query set against several train sets in one launch: IMatcher::matchMultiple
+ * (include/interfaces/IMatcher.hpp:27-37).  t = concatenated train rows, t_start[nsets+1]
+ * row offsets; out[nsets][nq], nout[nsets]. */
+ASLAM_API int aslam_match_multi(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t,
+                                const int32_t *t_start, int nsets, float ratio,
+                                aslam_match *out, int32_t *nout);
+/* Device-resident single problem (used by bench `value` and by callers chaining extract ->
+ * match in HBM): d_q/d_t device rows; d_out[nq], d_nout device. */
+ASLAM_API int aslam_match_knn2_device(aslam_ctx *ctx, const uint8_t *d_q, int nq,
+                                      const uint8_t *d_t, int nt, float ratio,
+                                      aslam_match *d_out, int32_t *d_nout);
+
+/* ------------------------------------------------------------------ loop-closure database
+ * Replaces the descriptor side of LoopClosureDetector (src/legacy/LoopClosure.cpp): the
+ * keyframe store addKeyFrame (:24-31, FIFO cap 500) and findCandidates' per-keyframe
+ * knnMatch + 0.7 ratio count (:72-114), as one resident [rows,32] array in HBM
+ * (the design of docs/milestones/H14_GPU_LOOPCLOSURE_AUDIT.md:41-78 in the reference).
+ * A database may be one shard of a larger one: global row = row_base + local row. */
+ASLAM_API int aslam_loopdb_create(aslam_ctx *ctx, int64_t capacity_rows, int max_keyframes,
+                                  aslam_loopdb **out);
+ASLAM_API void aslam_loopdb_destroy(aslam_loopdb *db);
+/* Append one keyframe's descriptors (host rows).  Evicts oldest keyframes while more than
+ * max_keyframes are stored (LoopClosure.cpp:27-30). */
+ASLAM_API int aslam_loopdb_add(aslam_loopdb *db, const uint8_t *desc, int n, uint64_t keyframe_id);
+ASLAM_API int aslam_loopdb_add_device(aslam_loopdb *db, const uint8_t *d_desc, int n, uint64_t keyframe_id);
+ASLAM_API int aslam_loopdb_clear(aslam_loopdb *db);
+ASLAM_API int aslam_loopdb_num_keyframes(const aslam_loopdb *db);
+ASLAM_API int64_t aslam_loopdb_num_rows(const aslam_loopdb *db);
+ASLAM_API int aslam_loopdb_set_row_base(aslam_loopdb *db, int64_t row_base);
+/* ids[k], rows[k] of the stored keyframes, oldest first. */
+ASLAM_API int aslam_loopdb_keyframes(const aslam_loopdb *db, uint64_t *ids, int32_t *rows);
+/* Per stored keyframe: how many of the nq queries pass d0 < ratio*d1 (double arithmetic as in
+ * LoopClosure.cpp:92) against that keyframe's rows.  good[num_keyframes]. */
+ASLAM_API int aslam_loopdb_query_segmented(aslam_loopdb *db, const uint8_t *q, int nq, double ratio,
+                                           int32_t *good);
+/* Flat query: per query the two smallest (distance, global row) over the whole shard as
+ * packed keys (distance << 40 | global row); empty slots are UINT64_MAX.  d_q, d_top2 are
+ * device pointers (top2[nq][2]); asynchronous on the context's stream. */
+ASLAM_API int aslam_loopdb_query_global_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
+                                               uint64_t *d_top2);
+/* Host-buffer form of the flat query (copies in and out, synchronous). */
+ASLAM_API int aslam_loopdb_query_global(aslam_loopdb *db, const uint8_t *q, int nq, uint64_t *top2);
+/* Merge step after the all-gather of shard results: d_parts[nparts][nq][2] packed keys ->
+ * d_out[nq][2], the two smallest per query.  Total order, so any shard count gives the
+ * single-GPU answer.  Asynchronous on the context's stream. */
+ASLAM_API int aslam_loop_merge_top2_device(aslam_ctx *ctx, const uint64_t *d_parts, int nparts,
+                                           int nq, uint64_t *d_out);
+
+/* ------------------------------------------------------------------ pipe micro-benchmarks
+ * Measured integer-pipe ceilings used as roofline denominators for the matching kernel
+ * (SURVEY.md 8d asks for the POPC rate to be measured, not assumed).  which: 0 = POPC,
+ * 1 = LOP3, 2 = IADD3, 3 = VIMNMX3.U16x2.  Returns giga warp-lane operations per second. */
+ASLAM_API int aslam_microbench(aslam_ctx *ctx, int which, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASLAM_B200_H */

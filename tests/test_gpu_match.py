@@ -1,0 +1,192 @@
+"""GPU parity of Hamming kNN / ratio matching / loop database against the CPU oracle
+(bit-exact: distances, indices, ratio survivors).  All calls go through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_desc(n, seed, entropy=256):
+    rs = np.random.RandomState(seed)
+    d = rs.randint(0, 256, (n, 32), dtype=np.uint8)
+    if entropy < 256:           # low-entropy descriptors: few distinct bytes -> mass distance ties
+        d = (d % entropy).astype(np.uint8)
+    return d
+
+
+@pytest.mark.parametrize("nq,nt,seed", [(1000, 1000, 1), (2000, 2000, 2), (513, 129, 3), (1, 2, 4), (7, 4097, 5),
+                                        (4000, 4000, 6), (300, 1, 7), (64, 128, 8)])
+def test_knn2_raw_matches_oracle(ctx, oracle, nq, nt, seed):
+    from aria_slam_b200.frontend import B200Matcher
+    q, t = _rand_desc(nq, seed), _rand_desc(nt, seed + 100)
+    idx, dist = B200Matcher(ctx).knn2(q, t)
+    ridx, rdist = oracle.knn2(q, t)
+    assert (idx == ridx).all() and (dist == rdist).all()
+
+
+def test_knn2_ties_go_to_lowest_index(ctx, oracle):
+    from aria_slam_b200.frontend import B200Matcher
+    t = _rand_desc(900, 11, entropy=2)           # bytes in {0,1}: distances collide constantly
+    t[100:130] = t[5]                            # exact duplicates of row 5
+    q = np.concatenate([t[5:6], t[700:800], _rand_desc(50, 12, entropy=2)])
+    idx, dist = B200Matcher(ctx).knn2(q, t)
+    ridx, rdist = oracle.knn2(q, t)
+    assert (idx == ridx).all() and (dist == rdist).all()
+    assert idx[0, 0] == 5 and idx[0, 1] == 100 and dist[0, 0] == 0 and dist[0, 1] == 0
+
+
+@pytest.mark.parametrize("ratio,num,den", [(0.75, 3, 4), (0.7, None, None), (0.9, None, None), (1.0, 1, 1)])
+def test_match_ratio_survivors(ctx, oracle, ratio, num, den):
+    from aria_slam_b200.frontend import B200Matcher, Frame
+    t = _rand_desc(1500, 21)
+    q = t[::2].copy()
+    rs = np.random.RandomState(22)
+    for i in range(len(q)):                      # 0..60 flipped bits -> a spread of d0/d1 ratios
+        bits = rs.choice(256, rs.randint(0, 61), replace=False)
+        np.bitwise_xor.at(q[i], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    m = []
+    B200Matcher(ctx).match(Frame(descriptors=q.reshape(-1), keypoints=np.zeros(len(q))),
+                           Frame(descriptors=t.reshape(-1), keypoints=np.zeros(len(t))), m, ratio)
+    idx, dist = oracle.knn2(q, t)
+    # CudaMatcher.cpp:60 in float arithmetic
+    ok = dist[:, 0].astype(np.float32) < np.float32(ratio) * dist[:, 1].astype(np.float32)
+    ref = [(i, idx[i, 0], float(dist[i, 0])) for i in np.nonzero(ok)[0]]
+    got = [(int(x["query_idx"]), int(x["train_idx"]), float(x["distance"])) for x in m]
+    assert got == ref
+    if num:
+        assert len(got) == len(oracle.ratio_matches(idx, dist, num, den))
+
+
+def test_match_appends_and_empty_sides(ctx):
+    from aria_slam_b200.frontend import B200Matcher, Frame
+    mt = B200Matcher(ctx)
+    q = Frame(descriptors=_rand_desc(10, 31).reshape(-1))
+    sentinel = ["keep"]
+    mt.match(q, Frame(), sentinel)                    # CudaMatcher.cpp:35-37: untouched
+    mt.match(Frame(), q, sentinel)
+    assert sentinel == ["keep"]
+    one = Frame(descriptors=_rand_desc(1, 32).reshape(-1))
+    mt.match(q, one, sentinel, 0.99)                  # nt < 2: knn.size() >= 2 never holds
+    assert sentinel == ["keep"]
+    mt.match(q, q, sentinel, 0.99)                    # appends, never clears (:65)
+    assert sentinel[0] == "keep" and len(sentinel) == 11
+    before = len(sentinel)
+    mt.match(q, q, sentinel, 0.0)                     # implementation semantics of 0.0: nothing passes
+    assert len(sentinel) == before
+
+
+def test_match_multiple_equals_looped_match(ctx):
+    from aria_slam_b200.frontend import B200Matcher, Frame
+    mt = B200Matcher(ctx)
+    q = Frame(descriptors=_rand_desc(700, 41).reshape(-1))
+    cands = [Frame(descriptors=_rand_desc(n, 42 + i).reshape(-1)) for i, n in enumerate([500, 0, 1, 2, 1300])]
+    cands[0].descriptors[:32 * 50] = q.descriptors[:32 * 50]
+    allm = []
+    mt.matchMultiple(q, cands, allm, 0.8)
+    assert len(allm) == len(cands)
+    for c, got in zip(cands, allm):
+        ref = []
+        mt.match(q, c, ref, 0.8)
+        assert [tuple(x) for x in got] == [tuple(x) for x in ref]
+    assert len(allm[0]) >= 50 and allm[1] == [] and allm[2] == []
+
+
+def _make_db(nkf, per, seed):
+    rs = np.random.RandomState(seed)
+    sizes = [per if i % 7 else max(2, per // 3) for i in range(nkf)]
+    sizes[3] = 1                                           # a keyframe with a single descriptor
+    return [rs.randint(0, 256, (n, 32), dtype=np.uint8) for n in sizes]
+
+
+def test_loopdb_segmented_counts(ctx, oracle):
+    from aria_slam_b200.frontend import LoopDB
+    kfs = _make_db(40, 300, 51)
+    db = LoopDB(ctx, sum(len(k) for k in kfs) + 10, 500)
+    for i, k in enumerate(kfs):
+        db.add(k, i)
+    flat = np.concatenate(kfs)
+    q = flat[np.random.RandomState(52).randint(0, len(flat), 400)].copy()
+    q[::3, 5] ^= 0x3c
+    good = db.query_segmented(q, 0.7)
+    start = np.concatenate([[0], np.cumsum([len(k) for k in kfs])]).astype(np.int32)
+    ref = oracle.loop_segment_counts(q, flat, start, 7, 10)
+    assert (good == ref).all()
+    # LoopClosure.cpp:92 uses the double literal 0.7: same survivors as 10*d0 < 7*d1
+    idx, dist = oracle.knn2(q, kfs[5])
+    assert ref[5] == int(((dist[:, 0].astype(np.float64)) < 0.7 * dist[:, 1].astype(np.float64)).sum())
+    db.close()
+
+
+def test_loopdb_fifo_eviction_and_slide(ctx, oracle):
+    from aria_slam_b200.frontend import LoopDB
+    kfs = _make_db(30, 100, 61)
+    db = LoopDB(ctx, 1200, 8)                   # small capacity: forces eviction and the slide-back
+    for i, k in enumerate(kfs):
+        db.add(k, 1000 + i)
+    ids, rows = db.keyframes()
+    assert list(ids) == [1000 + i for i in range(22, 30)]         # LoopClosure.cpp:27-30
+    assert list(rows) == [len(k) for k in kfs[22:]]
+    q = np.concatenate([kfs[25][:20], kfs[10][:20]])
+    good = db.query_segmented(q, 0.7)
+    live = np.concatenate(kfs[22:])
+    start = np.concatenate([[0], np.cumsum([len(k) for k in kfs[22:]])]).astype(np.int32)
+    assert (good == oracle.loop_segment_counts(q, live, start, 7, 10)).all()
+    db.close()
+
+
+def test_loopdb_global_top2_and_sharded_merge(ctx, oracle):
+    """Shards of one database queried separately and merged == the unsharded query == the oracle."""
+    import torch
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import LoopDB, unpack_top2
+    from aria_slam_b200._lib import lib, check, ptr
+    db_rows = synth.descriptor_db(60_000, 5)
+    q, _ = synth.loop_queries(db_rows, 500, 6)
+    ridx, rdist = oracle.knn2(q, db_rows)
+    whole = LoopDB(ctx, len(db_rows), 10)
+    whole.add(db_rows, 0)
+    rows, dist = whole.query_global(q)
+    assert (rows == ridx).all() and (dist == rdist).all()
+    whole.close()
+    for nshard in (2, 3, 8):
+        bounds = np.linspace(0, len(db_rows), nshard + 1).astype(np.int64)
+        parts = torch.empty((nshard, len(q), 2), dtype=torch.int64, device="cuda")
+        dq = torch.from_numpy(q).cuda()
+        torch.cuda.synchronize()
+        shards = []
+        for s in range(nshard):
+            sh = LoopDB(ctx, int(bounds[s + 1] - bounds[s]) + 1, 10)
+            sh.add(db_rows[bounds[s]:bounds[s + 1]], s)
+            sh.set_row_base(int(bounds[s]))
+            sh.query_global_device(dq, len(q), parts[s])
+            shards.append(sh)
+        out = torch.empty((len(q), 2), dtype=torch.int64, device="cuda")
+        check(lib().aslam_loop_merge_top2_device(ctx.h, ptr(parts), nshard, len(q), ptr(out)))
+        ctx.sync()
+        mrows, mdist = unpack_top2(out.cpu().numpy().view(np.uint64))
+        assert (mrows == ridx).all() and (mdist == rdist).all()
+        for sh in shards:
+            sh.close()
+
+
+def test_loop_detector_candidates_follow_reference_ranking(ctx, oracle):
+    from aria_slam_b200.frontend import B200LoopDetector, KeyFrame, Frame
+    rs = np.random.RandomState(71)
+    det = B200LoopDetector(ctx, min_frames_between=5, min_score=0.3, min_matches=10, capacity_rows=40 * 400)
+    kfs = []
+    for i in range(30):
+        d = rs.randint(0, 256, (300, 32), dtype=np.uint8)
+        kfs.append(d)
+        det.addKeyFrame(KeyFrame(id=i, frame=Frame(descriptors=d.reshape(-1), keypoints=np.zeros(300))))
+    qd = np.concatenate([kfs[4][:150], kfs[9][:60], kfs[28][:90]])      # 28 is inside the gap
+    query = KeyFrame(id=31, frame=Frame(descriptors=qd.reshape(-1), keypoints=np.zeros(len(qd))))
+    cands = det.findCandidates(query)
+    flat = np.concatenate(kfs)
+    start = (np.arange(31) * 300).astype(np.int32)
+    good = oracle.loop_segment_counts(qd, flat, start, 7, 10)
+    ref = oracle.loop_candidates(good, len(qd), list(range(30)), 31, 5)
+    assert [c[0] for c in cands] == [c[0] for c in ref] == [4, 9]
+    assert all(abs(a[1] - b[1]) == 0 for a, b in zip(cands, ref))
+    hit = det.detect(query)
+    assert hit is not None and hit.match_id == 4 and hit.query_id == 31 and len(hit.matches) >= 150
+    assert det.getLoopCount() == 1

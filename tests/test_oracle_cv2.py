@@ -1,0 +1,129 @@
+"""Pins the CPU oracle (oracle/orb_oracle.c) against the live cv2 wheel -- the same OpenCV code the
+reference's CPU path calls (Frame.cpp:47, LoopClosure.cpp:21,87).  Runs without a GPU."""
+import numpy as np
+import pytest
+
+from conftest import kp_keys
+
+cv2 = pytest.importorskip("cv2")
+
+
+def test_level_geometry_and_quotas(oracle):
+    Wl, Hl, sf = oracle.level_geometry(752, 480)
+    assert list(Wl) == [752, 627, 522, 435, 363, 302, 252, 210] and list(Hl) == [480, 400, 333, 278, 231, 193, 161, 134]
+    assert list(oracle.level_quotas(1000)) == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert list(oracle.level_quotas(2000)) == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert list(oracle.level_quotas(4000)) == [869, 724, 603, 503, 419, 349, 291, 242]
+    assert abs(sf[3] - 1.728) < 1e-5
+
+
+@pytest.mark.parametrize("w,h", [(752, 480), (640, 480), (333, 257)])
+def test_resize_chain_equals_cv2_linear_exact(oracle, w, h):
+    from aria_slam_b200 import synth
+    img = synth.frame(w, h, 3)
+    prev = img
+    for l, lev in enumerate(oracle.pyramid(img)[1:], 1):
+        ref = cv2.resize(prev, (lev.shape[1], lev.shape[0]), interpolation=cv2.INTER_LINEAR_EXACT)
+        assert (ref == lev).all(), "level %d" % l
+        prev = ref
+
+
+def test_fast_equals_cv2_fast_detector(oracle):
+    from aria_slam_b200 import synth
+    for seed, (w, h) in enumerate([(752, 480), (200, 150)]):
+        img = synth.frame(w, h, seed + 1)
+        cs = oracle.fast_nms(oracle.fast_score_map(img, 20))
+        kp = cv2.FastFeatureDetector_create(20, True).detect(img)
+        a = set((int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in kp)
+        b = set(zip(cs["x"].tolist(), cs["y"].tolist(), cs["score"].tolist()))
+        assert a == b and len(a) > 100
+
+
+def test_blur_matches_cv2_sepfilter(oracle):
+    """The hybrid fused/unfused split (orb_oracle.c A8) reproduces this cv2 build exactly."""
+    g = cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel()
+    assert np.allclose(g[:4], [0.07015932, 0.13107488, 0.19071282, 0.21610594], atol=1e-8)
+    bad = 0
+    for seed, w in enumerate([401, 752, 627, 100, 37, 522]):
+        img = np.random.RandomState(seed).randint(0, 256, (200, w)).astype(np.uint8)
+        ref = cv2.sepFilter2D(img, cv2.CV_8U, g, g, borderType=cv2.BORDER_REFLECT_101)
+        bad += int((oracle.blur7(img) != ref).sum())
+    assert bad == 0
+
+
+def test_fast_atan2_equals_cv2(oracle):
+    rs = np.random.RandomState(0)
+    ys, xs = rs.randint(-200000, 200000, 3000), rs.randint(-200000, 200000, 3000)
+    for y, x in list(zip(ys, xs)) + [(0, 5), (5, 0), (-5, 0), (0, -5), (3, 3), (-3, 3)]:
+        assert oracle.fast_atan2(y, x) == np.float32(cv2.fastAtan2(float(y), float(x)))
+
+
+def _same(ka, da, kb, db):
+    a, b = {k: i for i, k in enumerate(kp_keys(ka))}, {k: i for i, k in enumerate(kp_keys(kb))}
+    assert set(a) == set(b)
+    ia, ib = [a[k] for k in sorted(a)], [b[k] for k in sorted(a)]
+    assert (ka["response"][ia] == kb["response"][ib]).all()
+    assert (ka["angle"][ia] == kb["angle"][ib]).all()
+    assert (ka["size"][ia] == kb["size"][ib]).all()
+    return float((da[ia] == db[ib]).all(1).mean())
+
+
+@pytest.mark.parametrize("w,h,n,seed", [(752, 480, 1000, 1), (752, 480, 2000, 2), (640, 480, 1000, 4000), (320, 240, 500, 11)])
+def test_whole_orb_equals_cv2(oracle, w, h, n, seed):
+    from aria_slam_b200 import synth
+    img = synth.frame(w, h, seed)
+    ko, do = oracle.orb(img, n)
+    kc, dc = oracle.cv2_orb(img, n)
+    assert 0.9 * n <= len(kc) <= n
+    assert _same(ko, do, kc, dc) >= 0.999
+
+
+def test_whole_orb_with_mask_equals_cv2(oracle):
+    from aria_slam_b200 import synth
+    img = synth.frame(700, 500, 3000)
+    mask, _ = synth.mask_and_boxes(700, 500, 3000)
+    ko, do = oracle.orb(img, 1500, mask=mask)
+    kc, dc = oracle.cv2_orb(img, 1500, mask=mask)
+    assert _same(ko, do, kc, dc) >= 0.999
+
+
+def test_degenerate_frames(oracle):
+    from aria_slam_b200 import synth
+    for img in (np.full((480, 752), 128, np.uint8), synth.frame(60, 60, 1), synth.frame(300, 50, 1)):
+        ko, _ = oracle.orb(img, 1000)
+        kc, _ = oracle.cv2_orb(img, 1000)
+        assert len(ko) == 0 and len(kc) == 0
+
+
+def test_knn2_equals_bfmatcher_including_ties(oracle):
+    rs = np.random.RandomState(5)
+    t = (rs.randint(0, 256, (600, 32)) % 2).astype(np.uint8)        # low entropy: ties everywhere
+    t[50:60] = t[7]
+    q = np.concatenate([t[7:8], t[100:300], (rs.randint(0, 256, (100, 32)) % 2).astype(np.uint8)])
+    for qq, tt in ((q, t), (q, t[:1]), (q[:3], t[:2])):
+        idx, dist = oracle.knn2(qq, tt)
+        cidx, cdist = oracle.cv2_knn2(qq, tt)
+        assert (idx == cidx).all() and (dist == cdist).all()
+    assert oracle.knn2(q, t)[0][0].tolist() == [7, 50]
+
+
+def test_ratio_tests_reduce_to_integers(oracle):
+    """CudaMatcher.cpp:60 (float 0.75f) == 4*d0 < 3*d1; LoopClosure.cpp:92 (double 0.7) == 10*d0 < 7*d1."""
+    d0, d1 = np.meshgrid(np.arange(257), np.arange(257), indexing="ij")
+    f = d0.astype(np.float32) < np.float32(0.75) * d1.astype(np.float32)
+    assert (f == (4 * d0 < 3 * d1)).all()
+    d = d0.astype(np.float32).astype(np.float64) < 0.7 * d1.astype(np.float32).astype(np.float64)
+    assert (d == (10 * d0 < 7 * d1)).all()
+
+
+def test_merge_top2_is_shard_invariant(oracle):
+    rs = np.random.RandomState(9)
+    t = rs.randint(0, 256, (3000, 32), dtype=np.uint8); q = t[rs.randint(0, 3000, 100)].copy(); q[:, 3] ^= 5
+    ridx, rdist = oracle.knn2(q, t)
+    for cuts in ([0, 1500, 3000], [0, 1, 2, 1000, 3000]):
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            i, d = oracle.knn2(q, t[a:b])
+            parts.append((np.where(i >= 0, i + a, -1), d))
+        midx, mdist = oracle.merge_top2(parts)
+        assert (midx == ridx).all() and (mdist == rdist).all()

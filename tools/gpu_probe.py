@@ -1,0 +1,32 @@
+"""First-contact probe on the B200 box: integer-pipe micro-benchmarks + a timing of each stage."""
+import json, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from aria_slam_b200._lib import Context
+from aria_slam_b200.frontend import OrbBatchTracker
+from aria_slam_b200 import synth
+
+ctx = Context(0)
+out = {"sm_count": ctx.sm_count}
+for which, name in enumerate(["popc", "lop3", "iadd3", "vimnmx3_u16x2"]):
+    out["gops_" + name] = ctx.microbench(which)
+frames = synth.frame_stream(32, 752, 480, 1000)
+B = 256
+batch = np.ascontiguousarray(np.concatenate([frames] * (B // 32)))
+import torch
+d = torch.from_numpy(batch).cuda()
+tr = OrbBatchTracker(752, 480, 2000, B, ctx)
+ctx.prof_enable(True)
+for it in range(3):
+    tr.track_async(d, 0.75, on_device=True); tr.device_results()
+ctx.sync(); ctx.prof_read(reset=True)
+t0 = time.perf_counter()
+K = 5
+for it in range(K):
+    tr.track_async(d, 0.75, on_device=True); tr.device_results()
+ctx.sync()
+dt = (time.perf_counter() - t0) / K
+out["ms_per_batch256"] = dt * 1e3
+out["frames_per_s_device"] = B / dt
+out["stages_ms_per_batch"] = {k: (v[0] / K, v[1] / K) for k, v in ctx.prof_read().items()}
+print(json.dumps(out, indent=1))
