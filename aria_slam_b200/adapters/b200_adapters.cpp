@@ -1,0 +1,193 @@
+#include "b200_adapters.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+namespace aria::adapters::b200 {
+
+static void check(int rc, bool allow_overflow = false)
+{
+    if (rc == ASLAM_OK || (allow_overflow && rc == ASLAM_E_OVERFLOW)) return;
+    throw std::runtime_error(std::string("aslam_b200: ") + aslam_last_error());
+}
+
+Context::Context(int cuda_device, void* cuda_stream) { check(aslam_ctx_create(cuda_device, cuda_stream, &ctx_)); }
+Context::~Context() { aslam_ctx_destroy(ctx_); }
+
+// ---------------------------------------------------------------- extractor
+OrbB200Extractor::OrbB200Extractor(std::shared_ptr<Context> ctx, int max_features)
+    : ctx_(std::move(ctx)), max_features_(max_features) {}
+
+OrbB200Extractor::~OrbB200Extractor() { aslam_orb_destroy(orb_); }
+
+void OrbB200Extractor::ensure(int width, int height)
+{
+    if (orb_ && width == width_ && height == height_) return;
+    aslam_orb_destroy(orb_);
+    orb_ = nullptr;
+    aslam_orb_params p;
+    aslam_orb_default_params(&p);          // == cv::ORB::create(n,1.2f,8,31,0,2,HARRIS,31,20), OrbCudaExtractor.cpp:35-45
+    p.nfeatures = max_features_;
+    check(aslam_orb_create(ctx_->get(), &p, width, height, 1, &orb_));
+    width_ = width; height_ = height;
+    const size_t cap = (size_t)aslam_orb_capacity(orb_);
+    kp_buf_.resize(cap);
+    desc_buf_.resize(cap * 32);
+}
+
+void OrbB200Extractor::setDynamicBoxes(const std::vector<core::Detection>& detections)
+{
+    boxes_.clear();
+    for (const auto& d : detections) boxes_.push_back({d.x1, d.y1, d.x2, d.y2, d.confidence, d.class_id});
+}
+
+void OrbB200Extractor::extractAsync(const uint8_t* image_data, int width, int height, core::Frame& frame)
+{
+    ensure(width, height);
+    // image_data: grayscale, row-major, tightly packed (IFeatureExtractor.hpp:14); it and `frame`
+    // must outlive sync(), as upstream (OrbCudaExtractor.cpp:143).
+    check(aslam_orb_extract_async(orb_, image_data, width, height, width, nullptr,
+                                  boxes_.empty() ? nullptr : boxes_.data(), (int)boxes_.size()));
+    pending_frame_ = &frame;
+}
+
+void OrbB200Extractor::sync()
+{
+    if (!pending_frame_) return;
+    core::Frame& frame = *pending_frame_;
+    pending_frame_ = nullptr;
+    int32_t n = 0;
+    check(aslam_orb_sync(orb_, kp_buf_.data(), desc_buf_.data(), &n), true);
+    // fills width/height/keypoints/descriptors only, like OrbCudaExtractor.cpp:109-127
+    frame.width = width_;
+    frame.height = height_;
+    frame.keypoints.clear();
+    frame.keypoints.reserve((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const aslam_keypoint& k = kp_buf_[(size_t)i];
+        core::KeyPoint kp;
+        kp.x = k.x; kp.y = k.y; kp.size = k.size; kp.angle = k.angle; kp.response = k.response; kp.octave = k.octave;
+        frame.keypoints.push_back(kp);
+    }
+    frame.descriptors.assign(desc_buf_.begin(), desc_buf_.begin() + (size_t)n * 32);
+}
+
+void OrbB200Extractor::extract(const uint8_t* image_data, int width, int height, core::Frame& frame)
+{
+    extractAsync(image_data, width, height, frame);
+    sync();
+}
+
+void OrbB200Extractor::setMaxFeatures(int n)
+{
+    max_features_ = n;
+    if (orb_) check(aslam_orb_set_max_features(orb_, n));     // OrbCudaExtractor.cpp:212-216
+    if (orb_) {
+        const size_t cap = (size_t)aslam_orb_capacity(orb_);
+        kp_buf_.resize(cap);
+        desc_buf_.resize(cap * 32);
+    }
+}
+
+// ---------------------------------------------------------------- matcher
+void B200Matcher::match(const core::Frame& query, const core::Frame& train, std::vector<core::Match>& matches,
+                        float ratio_threshold)
+{
+    if (query.descriptors.empty() || train.descriptors.empty()) return;       // CudaMatcher.cpp:35-37
+    const int nq = (int)(query.descriptors.size() / 32), nt = (int)(train.descriptors.size() / 32);
+    buf_.resize((size_t)nq);
+    int n = 0;
+    check(aslam_match_knn2(ctx_->get(), query.descriptors.data(), nq, train.descriptors.data(), nt,
+                           ratio_threshold, buf_.data(), &n));
+    for (int i = 0; i < n; ++i) {                                              // append, never clear (:65)
+        core::Match m;
+        m.query_idx = buf_[(size_t)i].query_idx; m.train_idx = buf_[(size_t)i].train_idx; m.distance = buf_[(size_t)i].distance;
+        matches.push_back(m);
+    }
+}
+
+void B200Matcher::matchMultiple(const core::Frame& query, const std::vector<core::Frame>& candidates,
+                                std::vector<std::vector<core::Match>>& all_matches, float ratio_threshold)
+{
+    all_matches.resize(candidates.size());                                     // IMatcher.hpp:33
+    if (query.descriptors.empty() || candidates.empty()) return;
+    const int nq = (int)(query.descriptors.size() / 32), nsets = (int)candidates.size();
+    std::vector<int32_t> start((size_t)nsets + 1, 0), nout((size_t)nsets, 0);
+    for (int s = 0; s < nsets; ++s) start[(size_t)s + 1] = start[(size_t)s] + (int32_t)(candidates[(size_t)s].descriptors.size() / 32);
+    std::vector<uint8_t> rows((size_t)start[(size_t)nsets] * 32);
+    for (int s = 0; s < nsets; ++s)
+        if (!candidates[(size_t)s].descriptors.empty())
+            std::memcpy(rows.data() + (size_t)start[(size_t)s] * 32, candidates[(size_t)s].descriptors.data(), candidates[(size_t)s].descriptors.size());
+    std::vector<aslam_match> out((size_t)nsets * nq);
+    check(aslam_match_multi(ctx_->get(), query.descriptors.data(), nq, rows.data(), start.data(), nsets,
+                            ratio_threshold, out.data(), nout.data()));
+    for (int s = 0; s < nsets; ++s)
+        for (int i = 0; i < nout[(size_t)s]; ++i) {
+            const aslam_match& a = out[(size_t)s * nq + i];
+            core::Match m;
+            m.query_idx = a.query_idx; m.train_idx = a.train_idx; m.distance = a.distance;
+            all_matches[(size_t)s].push_back(m);
+        }
+}
+
+// ---------------------------------------------------------------- loop detector
+B200LoopDetector::B200LoopDetector(std::shared_ptr<Context> ctx, int min_frames_between, double min_score,
+                                   int min_matches, int max_keyframes, int64_t capacity_rows)
+    : ctx_(ctx), matcher_(ctx), min_frames_between_(min_frames_between), min_matches_(min_matches),
+      max_keyframes_(max_keyframes), min_score_(min_score)
+{
+    check(aslam_loopdb_create(ctx_->get(), capacity_rows, max_keyframes, &db_));
+}
+
+B200LoopDetector::~B200LoopDetector() { aslam_loopdb_destroy(db_); }
+
+void B200LoopDetector::addKeyFrame(const core::KeyFrame& kf)
+{
+    const auto& d = kf.frame.descriptors;
+    check(aslam_loopdb_add(db_, d.data(), (int)(d.size() / 32), kf.id));
+    store_.emplace_back(kf.id, d);
+    while ((int)store_.size() > max_keyframes_) store_.pop_front();            // LoopClosure.cpp:27-30
+}
+
+std::vector<std::pair<int, double>> B200LoopDetector::findCandidates(const core::KeyFrame& query)
+{
+    std::vector<std::pair<int, double>> cands;
+    const auto& qd = query.frame.descriptors;
+    if (qd.empty()) return cands;                                              // LoopClosure.cpp:75
+    const int nkf = aslam_loopdb_num_keyframes(db_);
+    std::vector<int32_t> good((size_t)std::max(nkf, 1), 0), rows((size_t)std::max(nkf, 1), 0);
+    std::vector<uint64_t> ids((size_t)std::max(nkf, 1), 0);
+    check(aslam_loopdb_query_segmented(db_, qd.data(), (int)(qd.size() / 32), 0.7, good.data()));
+    check(aslam_loopdb_keyframes(db_, ids.data(), rows.data()));
+    for (int i = 0; i < nkf; ++i) {
+        if ((int64_t)query.id - (int64_t)ids[(size_t)i] < min_frames_between_) continue;   // :81
+        if (rows[(size_t)i] == 0) continue;                                                // :83
+        const double score = (double)good[(size_t)i] / std::max(1, (int)query.frame.keypoints.size());   // :98
+        if (score > 0.1) cands.push_back({i, score});
+    }
+    std::stable_sort(cands.begin(), cands.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+    if (cands.size() > 5) cands.resize(5);
+    return cands;
+}
+
+std::optional<core::LoopCandidate> B200LoopDetector::detect(const core::KeyFrame& query)
+{
+    if ((int)store_.size() < min_frames_between_) return std::nullopt;        // LoopClosure.cpp:34-36
+    for (const auto& [idx, score] : findCandidates(query)) {
+        if (score < min_score_) continue;
+        core::Frame kf;
+        kf.descriptors = store_[(size_t)idx].second;
+        kf.keypoints.resize(kf.descriptors.size() / 32);
+        std::vector<core::Match> m;
+        matcher_.match(query.frame, kf, m, 0.7f);       // verifyGeometry's re-match (:120-128); RANSAC itself is host code upstream
+        if ((int)m.size() < min_matches_) continue;
+        core::LoopCandidate c;
+        c.query_id = query.id; c.match_id = store_[(size_t)idx].first; c.score = score; c.matches = std::move(m);
+        ++loops_;
+        return c;
+    }
+    return std::nullopt;
+}
+
+}  // namespace aria::adapters::b200

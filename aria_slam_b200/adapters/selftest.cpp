@@ -1,0 +1,79 @@
+// Exercises the C++ adapters through the reference's interface types on a GPU box.
+//   adapter_selftest <in.raw> <width> <height> <nfeatures> <out.bin>
+// in.raw holds two frames back to back.  out.bin: for each frame [int32 n][n x KeyPoint 24 B][n x 32 B],
+// then [int32 m][m x Match 12 B] for match(frame1, frame0, 0.75f), then the loop detector's verdict.
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+#include "b200_adapters.hpp"
+
+using namespace aria;
+
+static void put(FILE* f, const void* p, size_t n) { if (fwrite(p, 1, n, f) != n) throw std::runtime_error("write failed"); }
+
+int main(int argc, char** argv)
+{
+    if (argc != 6) { fprintf(stderr, "usage: %s in.raw w h nfeatures out.bin\n", argv[0]); return 2; }
+    const int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]);
+    try {
+        std::vector<uint8_t> px((size_t)2 * w * h);
+        FILE* in = fopen(argv[1], "rb");
+        if (!in || fread(px.data(), 1, px.size(), in) != px.size()) throw std::runtime_error("cannot read input frames");
+        fclose(in);
+        auto ctx = std::make_shared<adapters::b200::Context>(0);
+        std::unique_ptr<interfaces::IFeatureExtractor> extractor = std::make_unique<adapters::b200::OrbB200Extractor>(ctx, 500);
+        std::unique_ptr<interfaces::IMatcher> matcher = std::make_unique<adapters::b200::B200Matcher>(ctx);
+        extractor->setMaxFeatures(nf);
+        if (extractor->getMaxFeatures() != nf) throw std::runtime_error("getMaxFeatures");
+        core::Frame f0, f1;
+        f0.id = 7; f0.timestamp = 1.5;
+        extractor->extract(px.data(), w, h, f0);
+        extractor->extractAsync(px.data() + (size_t)w * h, w, h, f1);
+        extractor->sync();
+        if (f0.id != 7 || f0.timestamp != 1.5) throw std::runtime_error("extract touched id/timestamp");
+        FILE* out = fopen(argv[5], "wb");
+        for (const core::Frame* f : {&f0, &f1}) {
+            int32_t n = (int32_t)f->keypoints.size();
+            put(out, &n, 4);
+            put(out, f->keypoints.data(), (size_t)n * sizeof(core::KeyPoint));
+            put(out, f->descriptors.data(), (size_t)n * 32);
+        }
+        std::vector<core::Match> m;
+        m.push_back({-1, -1, -1.f});                       // must survive: match() appends
+        matcher->match(f1, f0, m, 0.75f);
+        if (m[0].query_idx != -1) throw std::runtime_error("match cleared the vector");
+        int32_t nm = (int32_t)m.size() - 1;
+        put(out, &nm, 4);
+        put(out, m.data() + 1, (size_t)nm * sizeof(core::Match));
+        std::vector<std::vector<core::Match>> all;
+        matcher->matchMultiple(f1, {f0, core::Frame(), f1}, all, 0.75f);
+        if (all.size() != 3 || all[0].size() != (size_t)nm || !all[1].empty()) throw std::runtime_error("matchMultiple disagrees with match");
+        // loop detector: 12 keyframes, number 3 is frame 0; the query (frame 1) must find it
+        std::unique_ptr<interfaces::ILoopDetector> loop = std::make_unique<adapters::b200::B200LoopDetector>(ctx, 5, 0.2, 20, 50, 50 * 4096);
+        for (int i = 0; i < 12; ++i) {
+            core::KeyFrame kf;
+            kf.id = (uint64_t)i;
+            if (i == 3) kf.frame = f0;
+            else {
+                kf.frame.descriptors.resize(f0.descriptors.size());
+                uint32_t s = 12345u + (uint32_t)i;
+                for (auto& b : kf.frame.descriptors) { s = s * 1664525u + 1013904223u; b = (uint8_t)(s >> 24); }
+                kf.frame.keypoints.resize(f0.keypoints.size());
+            }
+            loop->addKeyFrame(kf);
+        }
+        core::KeyFrame q;
+        q.id = 20; q.frame = f1;
+        auto hit = loop->detect(q);
+        int32_t verdict[3] = {hit ? 1 : 0, hit ? (int32_t)hit->match_id : -1, hit ? (int32_t)hit->matches.size() : 0};
+        put(out, verdict, sizeof(verdict));
+        if (loop->getLoopCount() != (hit ? 1 : 0)) throw std::runtime_error("getLoopCount");
+        fclose(out);
+        printf("selftest ok: %zu + %zu keypoints, %d matches, loop %d -> kf %d\n", f0.keypoints.size(), f1.keypoints.size(), nm, verdict[0], verdict[1]);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "selftest FAILED: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,69 @@
+"""The C++ host side: the adapters implement the reference's own abstract classes and behave like
+its adapters.  CPU part: they compile against the reference's real headers (when the reference tree
+is present).  GPU part: the self-test binary runs the whole path through the interface types and
+its output is checked against the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AD = os.path.join(ROOT, "aria_slam_b200", "adapters")
+REF_INC = "/root/reference/include"
+
+
+def test_adapters_compile_against_reference_headers():
+    if not os.path.exists(os.path.join(REF_INC, "interfaces", "IFeatureExtractor.hpp")):
+        pytest.skip("reference tree not present on this machine")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DARIA_UPSTREAM_HEADERS", "-I" + REF_INC,
+                        "-I" + os.path.join(ROOT, "tests", "eigen_stub"),
+                        os.path.join(AD, "b200_adapters.cpp"), os.path.join(AD, "selftest.cpp")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_adapter_library_is_built_and_links_the_c_abi():
+    so = os.path.join(ROOT, "aria_slam_b200", "libaslam_adapters.so")
+    assert os.path.exists(so) and os.path.exists(os.path.join(AD, "adapter_selftest"))
+    out = subprocess.run(["nm", "-D", "--undefined-only", so], stdout=subprocess.PIPE, text=True).stdout
+    for sym in ("aslam_orb_extract_async", "aslam_orb_sync", "aslam_match_knn2", "aslam_loopdb_query_segmented"):
+        assert sym in out
+
+
+@pytest.mark.gpu
+def test_adapter_selftest_matches_oracle(tmp_path, oracle):
+    from aria_slam_b200 import synth
+    from oracle.oracle import KP_DTYPE
+    w, h, n = 640, 480, 1000
+    a = synth.frame(w, h, 77)
+    b = synth.shifted(a, seed=78)
+    raw = tmp_path / "in.raw"
+    raw.write_bytes(a.tobytes() + b.tobytes())
+    out = tmp_path / "out.bin"
+    r = subprocess.run([os.path.join(AD, "adapter_selftest"), str(raw), str(w), str(h), str(n), str(out)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    buf = out.read_bytes()
+    pos, frames = 0, []
+    for _ in range(2):
+        (k,) = struct.unpack_from("<i", buf, pos); pos += 4
+        kps = np.frombuffer(buf, KP_DTYPE, k, pos); pos += 24 * k
+        desc = np.frombuffer(buf, np.uint8, 32 * k, pos).reshape(k, 32); pos += 32 * k
+        frames.append((kps, desc))
+    (m,) = struct.unpack_from("<i", buf, pos); pos += 4
+    matches = np.frombuffer(buf, np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), m, pos); pos += 12 * m
+    verdict = struct.unpack_from("<3i", buf, pos)
+    for img, (kps, desc) in zip((a, b), frames):
+        ko, do = oracle.orb(img, n)
+        key = lambda k: sorted(zip(k["octave"].tolist(), k["x"].tolist(), k["y"].tolist()))
+        assert key(kps) == key(ko)
+        og, oo = np.lexsort((kps["x"], kps["y"], kps["octave"])), np.lexsort((ko["x"], ko["y"], ko["octave"]))
+        assert (desc[og] == do[oo]).all(1).mean() >= 0.99
+        assert (kps["angle"][og] == ko["angle"][oo]).all() and (kps["response"][og] == ko["response"][oo]).all()
+    idx, dist = oracle.knn2(frames[1][1], frames[0][1])
+    ref = oracle.ratio_matches(idx, dist, 3, 4)
+    got = np.stack([matches["q"], matches["t"], matches["d"].astype(np.int32)], 1)
+    assert got.shape == ref.shape and (got == ref).all()
+    assert verdict[0] == 1 and verdict[1] == 3 and verdict[2] >= 20

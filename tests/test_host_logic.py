@@ -1,0 +1,65 @@
+"""Host-side logic that needs no GPU: shard planning, key packing, and the N>1 exchange step over
+gloo with world_size 2 (local scans and the merge are done by the oracle here -- it is the checker)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_shards_covers_everything_contiguously():
+    from aria_slam_b200.sharded import plan_shards, keyframe_starts
+    for n, w in [(500, 8), (500, 1), (7, 8), (63, 4), (0, 2)]:
+        p = plan_shards(n, w)
+        assert len(p) == w and p[0][0] == 0 and p[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(p[:-1], p[1:]))
+        sizes = [hi - lo for lo, hi in p]
+        assert max(sizes) - min(sizes) <= 1
+    s = keyframe_starts(1_000_000, 2000)
+    assert len(s) == 501 and s[-1] == 1_000_000 and s[1] == 2000
+    assert list(keyframe_starts(4100, 2000)) == [0, 2000, 4000, 4100]
+
+
+def test_pack_unpack_roundtrip_and_order():
+    from aria_slam_b200.sharded import pack_top2
+    from aria_slam_b200.frontend import unpack_top2
+    rows = np.array([[5, 7], [123456789, -1], [-1, -1]], np.int64)
+    dist = np.array([[0, 256], [17, -1], [-1, -1]], np.int64)
+    k = pack_top2(rows, dist)
+    r, d = unpack_top2(k)
+    assert (r == rows).all() and (d == dist).all()
+    # unsigned order of keys == lexicographic (distance, row); empty sorts last
+    assert k[0, 0] < k[0, 1] < k[2, 0] and pack_top2([[9]], [[3]])[0, 0] < pack_top2([[2]], [[4]])[0, 0]
+
+
+def _gloo_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from aria_slam_b200 import synth
+    from aria_slam_b200.sharded import plan_shards, keyframe_starts, pack_top2, all_gather_top2
+    from aria_slam_b200.frontend import unpack_top2
+    from oracle import oracle as O
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    db = synth.descriptor_db(6100, 5)
+    q, _ = synth.loop_queries(db, 64, 6)
+    starts = keyframe_starts(len(db), 500)
+    lo, hi = plan_shards(len(starts) - 1, world)[rank]
+    r0, r1 = int(starts[lo]), int(starts[hi])
+    idx, d = O.knn2(q, db[r0:r1])
+    local = torch.from_numpy(pack_top2(np.where(idx >= 0, idx.astype(np.int64) + r0, -1), d).view(np.int64))
+    parts = all_gather_top2(local, world).numpy().view(np.uint64)
+    merged = O.merge_top2([unpack_top2(parts[p]) for p in range(world)])
+    ridx, rdist = O.knn2(q, db)
+    ok = (merged[0] == ridx).all() and (merged[1] == rdist).all()
+    open(os.path.join(tmp, "ok%d" % rank), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
