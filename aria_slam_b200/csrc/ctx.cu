@@ -1,4 +1,6 @@
 // Context, error state, pinned-memory helpers and the integer-pipe micro-benchmarks.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace aslam {
@@ -162,35 +164,51 @@ int aslam_host_free(void *p)
 // ------------------------------------------------------------------ pipe micro-benchmarks
 // Eight independent dependency chains per thread so the measured rate is the pipe's, not the
 // latency's.  The result is written so the compiler cannot drop the loop.
+__device__ __forceinline__ uint32_t hmax2_bits(uint32_t a, uint32_t b)
+{
+    __half2 x = *reinterpret_cast<__half2 *>(&a), y = *reinterpret_cast<__half2 *>(&b);
+    __half2 r = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+
 template <int WHICH>
 __global__ void __launch_bounds__(256) pipe_bench_kernel(uint32_t *out, int iters, uint32_t seed)
 {
-    uint32_t a[8];
+    uint32_t a[8], h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
-    uint32_t b = seed ^ 0x5bd1e995u, c = seed + 77u;
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
+        h[i] = 0x64006400u | ((a[i] >> 3) & 0x00ff00ffu);     // two halves in [1024, 1279]
+    }
+    uint32_t b = seed ^ 0x5bd1e995u;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (WHICH == 0) a[i] = __popc(a[i]) + b;                 // POPC (+1 IADD to keep a live chain)
-                else if (WHICH == 1) a[i] = (a[i] & b) ^ c ^ a[(i + 1) & 7];   // LOP3
-                else if (WHICH == 2) a[i] = a[i] + b + c;                // IADD3
-                else a[i] = __vimax3_u16x2(a[i], b, a[(i + 3) & 7]);     // VIMNMX3.U16x2
+                else if (WHICH == 1) a[i] = (a[i] & b) ^ a[(i + 1) & 7];       // LOP3
+                else if (WHICH == 2) a[i] = a[i] + b + a[(i + 5) & 7];   // IADD3
+                else if (WHICH == 3) a[i] = __vimax3_u16x2(a[i], b, a[(i + 3) & 7]);     // VIMNMX3.U16x2
+                else if (WHICH == 4) h[i] = hmax2_bits(h[i], h[(i + 3) & 7]);          // HMNMX2
+                else if (WHICH == 5) {                                   // both, independent chains
+                    a[i] = __vimax3_u16x2(a[i], b, a[(i + 3) & 7]);
+                    h[i] = hmax2_bits(h[i], h[(i + 3) & 7]);
+                } else if (WHICH == 6) a[i] = a[i] * b + a[(i + 3) & 7]; // IMAD
+                else a[i] = __byte_perm(a[i], a[(i + 3) & 7], b);        // PRMT
             }
         }
     }
     uint32_t s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s ^= a[i];
+    for (int i = 0; i < 8; ++i) s ^= a[i] ^ h[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 extern "C" int aslam_microbench(aslam_ctx *ctx, int which, double *gops)
 {
     ASLAM_REQUIRE(ctx && gops, "NULL argument");
-    ASLAM_REQUIRE(which >= 0 && which <= 3, "which must be 0..3");
+    ASLAM_REQUIRE(which >= 0 && which <= 7, "which must be 0..7");
     ASLAM_CUDA(cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
     uint32_t *d = nullptr;
@@ -205,7 +223,11 @@ extern "C" int aslam_microbench(aslam_ctx *ctx, int which, double *gops)
         case 0: pipe_bench_kernel<0><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
         case 1: pipe_bench_kernel<1><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
         case 2: pipe_bench_kernel<2><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
-        default: pipe_bench_kernel<3><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 3: pipe_bench_kernel<3><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 4: pipe_bench_kernel<4><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 5: pipe_bench_kernel<5><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 6: pipe_bench_kernel<6><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        default: pipe_bench_kernel<7><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
         }
         ASLAM_LAUNCH_CHECK();
         ASLAM_CUDA(cudaEventRecord(e1, ctx->stream));
@@ -214,7 +236,7 @@ extern "C" int aslam_microbench(aslam_ctx *ctx, int which, double *gops)
         ASLAM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best) best = ms;
     }
-    double ops = (double)blocks * threads * (double)iters * 32.0;
+    double ops = (double)blocks * threads * (double)iters * 32.0 * (which == 5 ? 2.0 : 1.0);
     *gops = ops / (best * 1e-3) * 1e-9;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

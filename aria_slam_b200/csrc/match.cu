@@ -5,31 +5,70 @@
 // (src/adapters/gpu/CudaMatcher.cpp:56, src/main.cpp:159, src/euroc_eval.cpp:168) and the CPU
 // cv::BFMatcher::knnMatch of src/legacy/LoopClosure.cpp:87; results follow the CPU matcher:
 // ascending (distance, train index).
+#include <cstdlib>
+
 #include "match.cuh"
 
 namespace aslam {
 
 constexpr int KNN_TILE = 128;   // train rows per shared-memory stage (4 KB)
 
-__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4 a, const uint4 b)
+// popcount(q ^ t) over 256 bits.  POPC issues at 16 lanes/clk/SM (measured 4.39 Tpopc/s), LOP3 and
+// IADD3 at 64: carry-save adders (2 LOP3 each) compress three equal-weight words into a sum and a
+// carry word and so trade one quarter-rate POPC for two full-rate logic ops.
+//   CSA 0: 8 POPC            CSA 2: 6 POPC + 2 adders        CSA 3: 5 POPC + 3 adders
+//   CSA 4: 4 POPC + 4 adders (ones, ones, twos, fours)
+//   CSA 5: as CSA 3, but the adder sums come from precomputed word parities: with Qa = q0^q1^q2 kept
+//          per query and Ta = t0^t1^t2 computed once per train row, s0 = Qa^Ta needs no x2, and the
+//          carry maj(x0,x1,x2) = f(x0,x1,s0) is still one LOP3 -- 11 logic ops per pair instead of 14.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
 {
-#if ASLAM_KNN_CSA
-    // Carry-save compression of six of the eight XOR words (two full adders = 4 LOP3) trades two
-    // quarter-rate POPCs for four full-rate logic ops: sum = popc(s0)+popc(s1)+popc(x6)+popc(x7)
-    // + 2*(popc(c0)+popc(c1)).
-    uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
-    uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
-    uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 ^ x1));
-    uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 ^ x4));
-    uint32_t ones = __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7);
-    uint32_t twos = __popc(c0) + __popc(c1);
-    return ones + 2u * twos;
-#else
-    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
-           __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
-#endif
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
 }
 
+template <int CSA>
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4 a, const uint4 b)
+{
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    if (CSA == 0)
+        return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+    uint32_t s0, c0, s1, c1;
+    csa(x0, x1, x2, s0, c0);
+    csa(x3, x4, x5, s1, c1);
+    if (CSA == 2)
+        return __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2u * (__popc(c0) + __popc(c1));
+    uint32_t s2, c2;
+    csa(s0, s1, x6, s2, c2);
+    if (CSA == 3)
+        return __popc(s2) + __popc(x7) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
+    uint32_t s3, c3;
+    csa(c0, c1, c2, s3, c3);
+    return __popc(s2) + __popc(x7) + 2u * __popc(s3) + 4u * __popc(c3);
+}
+
+// carry of a full adder given two inputs and the SUM of all three: x2 = s ^ x0 ^ x1
+__device__ __forceinline__ uint32_t carry_from_sum(uint32_t x0, uint32_t x1, uint32_t s)
+{
+    uint32_t r;      // one LOP3: (x0 & x1) | ((s ^ x0 ^ x1) & (x0 ^ x1))
+    asm("lop3.b32 %0, %1, %2, %3, 0xd4;" : "=r"(r) : "r"(x0), "r"(x1), "r"(s));
+    return r;
+}
+
+struct QueryParity { uint32_t a, b, c; };      // q0^q1^q2, q3^q4^q5, q0^..^q6
+
+__device__ __forceinline__ uint32_t hamming256_parity(const uint32_t (&q)[8], const QueryParity qp, const uint4 a, const uint4 b,
+                                                     uint32_t ta, uint32_t tb, uint32_t tc)
+{
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, s0 = qp.a ^ ta, c0 = carry_from_sum(x0, x1, s0);
+    const uint32_t x3 = q[3] ^ a.w, x4 = q[4] ^ b.x, s1 = qp.b ^ tb, c1 = carry_from_sum(x3, x4, s1);
+    const uint32_t s2 = qp.c ^ tc, c2 = carry_from_sum(s0, s1, s2);
+    const uint32_t x7 = q[7] ^ b.w;
+    return __popc(s2) + __popc(x7) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
+}
+
+template <int CSA>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride)
 {
@@ -57,6 +96,13 @@ knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ pa
         qd[j][4] = hi.x; qd[j][5] = hi.y; qd[j][6] = hi.z; qd[j][7] = hi.w;
         b1[j] = KEY_EMPTY; b2[j] = KEY_EMPTY;
     }
+    QueryParity qp[KNN_RQ];
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        qp[j].a = qd[j][0] ^ qd[j][1] ^ qd[j][2];
+        qp[j].b = qd[j][3] ^ qd[j][4] ^ qd[j][5];
+        qp[j].c = qp[j].a ^ qp[j].b ^ qd[j][6];
+    }
 
     const uint4 *trows = reinterpret_cast<const uint4 *>(P.t);
     // stage 0
@@ -83,17 +129,18 @@ knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ pa
 #pragma unroll 4
         for (int r = 0; r < rows; ++r) {
             const uint4 a = tb[2 * r], b = tb[2 * r + 1];
+            const uint32_t ta = a.x ^ a.y ^ a.z, tbp = a.w ^ b.x ^ b.y, tc = ta ^ tbp ^ b.z;
 #pragma unroll
             for (int j = 0; j < KNN_RQ; ++j) {
-                const uint32_t d = hamming256(qd[j], a, b);
+                const uint32_t d = CSA == 5 ? hamming256_parity(qd[j], qp[j], a, b, ta, tbp, tc)
+                                            : hamming256<CSA>(qd[j], a, b);
                 const uint32_t key = (d << KEY_IDX_BITS) + keybase;
                 b2[j] = min(b2[j], max(b1[j], key));
                 b1[j] = min(b1[j], key);
             }
             ++keybase;
         }
-        // the other buffer is rewritten next iteration only after everyone passed this barrier
-        // in the following loop trip; with two buffers one barrier per stage suffices.
+        // two buffers: the barrier of the next trip orders this trip's reads before the rewrite
     }
 #pragma unroll
     for (int j = 0; j < KNN_RQ; ++j) {
@@ -269,8 +316,15 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
 {
     if (nprobs <= 0 || max_nq <= 0) return ASLAM_OK;
     dim3 grid((max_nq + KNN_QBLOCK - 1) / KNN_QBLOCK, nprobs);
+    static const int csa = [] { const char *e = getenv("ASLAM_KNN_CSA"); return e ? atoi(e) : ASLAM_KNN_CSA; }();
     ProfScope ps(ctx, PK_KNN_PARTIAL);
-    knn2_partial_kernel<<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride);
+    switch (csa) {
+    case 0: knn2_partial_kernel<0><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    case 3: knn2_partial_kernel<3><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    case 4: knn2_partial_kernel<4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    case 5: knn2_partial_kernel<5><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    default: knn2_partial_kernel<2><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    }
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

@@ -21,7 +21,7 @@ struct aslam_orb {
     OrbGeom g{};
     OrbBuffers b{};
     uint32_t *d_tabs = nullptr;
-    uint32_t *d_pattern = nullptr;
+    float4 *d_pattern = nullptr;
     // tracking
     aslam_match *d_matches = nullptr;      // [B][kp_cap]
     int32_t *d_match_counts = nullptr;     // [B]
@@ -149,10 +149,10 @@ int aslam_orb_create(aslam_ctx *ctx, const aslam_orb_params *p, int width, int h
     ASLAM_CUDA(cudaSetDevice(ctx->device));
     aslam_orb *o = new aslam_orb();
     o->ctx = ctx; o->prm = *p; o->width = width; o->height = height; o->max_batch = max_batch;
-    uint32_t packed[256];
-    for (int i = 0; i < 256; ++i)
-        packed[i] = (uint32_t)(uint8_t)k_brief_pattern[i][0] | ((uint32_t)(uint8_t)k_brief_pattern[i][1] << 8) |
-                    ((uint32_t)(uint8_t)k_brief_pattern[i][2] << 16) | ((uint32_t)(uint8_t)k_brief_pattern[i][3] << 24);
+    float4 packed[256];
+    for (int i = 0; i < 256; ++i)      // transposed: entry j*32 + lane = comparison 8*lane + j (coalesced per j)
+        packed[(i & 7) * 32 + (i >> 3)] = make_float4((float)k_brief_pattern[i][0], (float)k_brief_pattern[i][1],
+                                (float)k_brief_pattern[i][2], (float)k_brief_pattern[i][3]);
     cudaError_t e = cudaMalloc(&o->d_pattern, sizeof(packed));
     if (e == cudaSuccess) e = cudaMemcpy(o->d_pattern, packed, sizeof(packed), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { delete o; return fail(ASLAM_E_CUDA, "pattern upload -> %s", cudaGetErrorString(e)); }

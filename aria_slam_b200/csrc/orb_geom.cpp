@@ -1,6 +1,7 @@
 // Host-side geometry: level sizes, per-level quotas, exact-bilinear coefficient tables.
 #include "orb_geom.h"
 
+#include <algorithm>
 #include <cmath>
 
 namespace aslam {
@@ -9,17 +10,54 @@ static inline int cv_round(float v) { return (int)lrintf(v); }   // cvRound: hal
 
 // cv::resize INTER_LINEAR_EXACT, 8-bit: source coordinate in double, weight in 8.8 fixed point
 // rounded half to even (OpenCV imgproc/resize.cpp, interpolationLinear::getCoeffs).
-static void resize_table(int src, int dst, uint32_t *tab)
+// Normalised so that the weight of p[ofs+1] is c1 in [0,255] and that of p[ofs] is 256-c1:
+// a weight of 256 on the right tap becomes (ofs+1, 0); clamped edges are one sample at weight 256.
+static void resize_coeff(int src, int dst, int i, int &ofs, int &c1)
 {
     const double scale = 1.0 / ((double)dst / (double)src);
+    const double f = scale * ((double)i + 0.5) - 0.5;
+    const int i0 = (int)std::floor(f);
+    if (i0 < 0) { ofs = 0; c1 = 0; }
+    else if (i0 >= src - 1) { ofs = src - 1; c1 = 0; }
+    else {
+        ofs = i0;
+        c1 = (int)lrint((f - (double)i0) * 256.0);
+        if (c1 == 256) { ofs = i0 + 1; c1 = 0; }
+    }
+}
+
+// Row table: entry y = ofs | wy1 << 16 with taps (ofs, ofs+1) both inside the image.
+static void resize_row_table(int src, int dst, uint32_t *tab)
+{
     for (int i = 0; i < dst; ++i) {
-        const double f = scale * ((double)i + 0.5) - 0.5;
-        const int i0 = (int)std::floor(f);
-        uint32_t ofs, c1;
-        if (i0 < 0) { ofs = 0; c1 = 0; }                                  // clamp left: p[0] * 256
-        else if (i0 >= src - 1) { ofs = (uint32_t)(src - 2); c1 = 256; }  // clamp right: p[src-1] * 256
-        else { ofs = (uint32_t)i0; c1 = (uint32_t)lrint((f - (double)i0) * 256.0); }
-        tab[i] = ofs | (c1 << 16);
+        int ofs, c1;
+        resize_coeff(src, dst, i, ofs, c1);
+        if (ofs >= src - 1) { ofs = src - 2; c1 = 256; }      // keep ofs+1 a real row; same value
+        tab[i] = (uint32_t)ofs | ((uint32_t)c1 << 16);
+    }
+}
+
+// Column table: 8 words per group of 4 output columns (see resize_kernel):
+//   [0] aligned source word of the window, [1] funnel shift in bits, [2] PRMT selectors of outputs 0,1,
+//   [3] selectors of outputs 2,3, [4..7] weight words (255-c1) | c1 << 8 | 1 << 16.
+// Outputs past the level width repeat the last real column (their bytes land in row padding).
+static void resize_col_table(int src, int dst, uint32_t *tab)
+{
+    for (int g = 0; g * 4 < dst; ++g) {
+        int ofs[4], c1[4];
+        for (int i = 0; i < 4; ++i) resize_coeff(src, dst, std::min(g * 4 + i, dst - 1), ofs[i], c1[i]);
+        const int o0 = ofs[0];
+        uint32_t *t = tab + 8 * g;
+        t[0] = (uint32_t)(o0 >> 2);
+        t[1] = (uint32_t)(o0 & 3) * 8u;
+        uint32_t sel[4];
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t k = (uint32_t)(ofs[i] - o0);           // 0..4, so k+1 <= 5 < 8
+            sel[i] = k | ((k + 1) << 4) | (k << 8) | (k << 12);
+            t[4 + i] = (uint32_t)(255 - c1[i]) | ((uint32_t)c1[i] << 8) | (1u << 16);
+        }
+        t[2] = sel[0] | (sel[1] << 16);
+        t[3] = sel[2] | (sel[3] << 16);
     }
 }
 
@@ -41,7 +79,7 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
     g.lv[nlevels - 1].quota = nfeatures - sum > 0 ? nfeatures - sum : 0;
 
     unsigned int off = 0;
-    int tile_off = 0, sel_off = 0;
+    int tile_off = 0, sel_off = 0, blur_off = 0;
     g.nbuilt = 0;
     tables.clear();
     for (int l = 0; l < nlevels; ++l) {
@@ -50,11 +88,14 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
         L.w = cv_round((float)width / L.sf);
         L.h = cv_round((float)height / L.sf);
         L.pitch = (L.w + 15) / 16 * 16;
-        const int rw = L.w - 2 * edge, rh = L.h - 2 * edge;
-        const bool active = rw > 0 && rh > 0 && L.quota > 0 && L.w >= 8 && L.h >= 8;
+        // FAST score blocks start at the even column (edge-1)&~1; their interior columns are outputs
+        const int rw = L.w - edge - 1 - ((edge - 1) & ~1), rh = L.h - 2 * edge;
+        const bool active = L.w - 2 * edge > 0 && rh > 0 && L.quota > 0 && L.w >= 8 && L.h >= 8;
         L.tiles_x = active ? (rw + FT_OUT_W - 1) / FT_OUT_W : 0;
         L.tiles_y = active ? (rh + FT_OUT_H - 1) / FT_OUT_H : 0;
         L.tile_off = tile_off;
+        L.blur_tile_off = blur_off;
+        if (active) blur_off += ((L.w + 127) / 128) * ((L.h + 31) / 32);
         tile_off += L.tiles_x * L.tiles_y;
         L.sel_off = sel_off;
         L.sel_cap = L.quota + SEL_TIE_ROOM;
@@ -71,15 +112,16 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
         if (l > 0) {
             const LevelGeom &P = g.lv[l - 1];
             L.xtab_off = (int)tables.size();
-            tables.resize(tables.size() + (size_t)(L.w + 3) / 4 * 4, 0);
-            resize_table(P.w, L.w, tables.data() + L.xtab_off);
+            tables.resize(tables.size() + (size_t)(L.w + 3) / 4 * 8, 0);
+            resize_col_table(P.w, L.w, tables.data() + L.xtab_off);
             L.ytab_off = (int)tables.size();
             tables.resize(tables.size() + (size_t)(L.h + 3) / 4 * 4, 0);
-            resize_table(P.h, L.h, tables.data() + L.ytab_off);
+            resize_row_table(P.h, L.h, tables.data() + L.ytab_off);
         }
     }
     g.pyr_stride = off ? off : 256;
     g.tiles_per_frame = tile_off;
+    g.blur_tiles_per_frame = blur_off;
     g.kp_cap = (sel_off + 63) / 64 * 64;
 }
 

@@ -22,6 +22,7 @@ struct LevelGeom {
     unsigned int off;        // byte offset of the level inside a frame's pyramid block
     int tiles_x, tiles_y;    // FAST tiles covering [edge, w-edge) x [edge, h-edge)
     int tile_off;            // first tile index of this level within the frame
+    int blur_tile_off;       // first 128x32 blur tile of this level within the frame
     int quota;               // N_l
     int sel_off, sel_cap;    // rows of this level in the per-frame selection buffer
     int xtab_off, ytab_off;  // resize tables (level l-1 -> l), in uint32 entries
@@ -35,6 +36,7 @@ struct OrbGeom {
     int nbuilt;              // levels 0..nbuilt-1 exist in memory (those that can hold keypoints, chained)
     int width, height, edge, fast_thr;
     int tiles_per_frame;
+    int blur_tiles_per_frame;
     int kp_cap;              // keypoint rows per frame in the output buffers
     unsigned int pyr_stride; // bytes per frame of pyramid (and of blurred pyramid, and of mask pyramid)
     LevelGeom lv[ORB_MAX_LEVELS];

@@ -12,42 +12,73 @@
 namespace aslam {
 
 // ------------------------------------------------------------------ exact bilinear resize (A2)
-// One thread = 4 consecutive output pixels of one row (one 32-bit store).  The two source rows
-// and the per-column (offset, weight) table entries come through L1; the table is 16-B loaded.
-__global__ void __launch_bounds__(256)
+// One thread = 4 consecutive output columns x RS_ROWS output rows, marching down.  Per source row
+// the 4 horizontal interpolations are done once and reused by the next output row (scale 1.2:
+// consecutive output rows share a source row most of the time):
+//   3 aligned 32-bit loads cover the <= 6-byte window of the 4 outputs, a funnel shift aligns it,
+//   and each 8.8 value is ONE PRMT + ONE DP4A:  (a, b, a, .) . (255-c1, c1, 1, 0) = a*(256-c1) + b*c1.
+// Vertical: v = hA*256 + (hB-hA)*wy1 + 2^15, byte 2 of v is the pixel (>>16); 3 PRMTs pack 4 pixels.
+// Column tables (window word, shift, 4 selectors, 4 weight words) are built on the host with the
+// double arithmetic OpenCV uses and depend only on the level sizes.
+constexpr int RS_ROWS = 16;
+
+struct HRow { uint32_t h[4]; };
+
+__device__ __forceinline__ HRow resize_hrow(const uint8_t *__restrict__ row, const uint4 t0, const uint4 t1)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row) + t0.x;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const uint32_t lo = __funnelshift_r(w0, w1, t0.y), hi = __funnelshift_r(w1, w2, t0.y);
+    HRow r;
+    r.h[0] = __dp4a(__byte_perm(lo, hi, t0.z & 0xffffu), t1.x, 0u);
+    r.h[1] = __dp4a(__byte_perm(lo, hi, t0.z >> 16), t1.y, 0u);
+    r.h[2] = __dp4a(__byte_perm(lo, hi, t0.w & 0xffffu), t1.z, 0u);
+    r.h[3] = __dp4a(__byte_perm(lo, hi, t0.w >> 16), t1.w, 0u);
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
 resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
               LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs, int thresh)
 {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x4 >= D.w || y >= D.h) return;
+    const int cg = blockIdx.x * 32 + threadIdx.x;
+    const int y_begin = (blockIdx.y * 4 + threadIdx.y) * RS_ROWS;
+    if (cg * 4 >= D.w || y_begin >= D.h) return;
+    const int y_end = min(y_begin + RS_ROWS, D.h);
     const uint8_t *src = srcb + (size_t)blockIdx.z * stride + S.off;
-    uint8_t *dst = dstb + (size_t)blockIdx.z * stride + D.off;
-    const uint32_t yt = __ldg(tabs + D.ytab_off + y);
-    const uint8_t *r0 = src + (size_t)(yt & 0xffffu) * S.pitch;
-    const uint8_t *r1 = r0 + S.pitch;
-    const uint32_t wy1 = yt >> 16, wy0 = 256u - wy1;
-    const uint4 xt4 = __ldg(reinterpret_cast<const uint4 *>(tabs + D.xtab_off + x4));
-    const uint32_t xt[4] = {xt4.x, xt4.y, xt4.z, xt4.w};
-    uint32_t out = 0;
+    uint8_t *dst = dstb + (size_t)blockIdx.z * stride + D.off + cg * 4;
+    const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
+    const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
+    const uint32_t *yt = tabs + D.ytab_off;
+
+    int rb = -1;          // source row whose horizontal pass sits in hb
+    HRow ha, hb;
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; ++y) {
+        const uint32_t e = __ldg(yt + y);
+        const int r0 = (int)(e & 0xffffu);
+        const int wy1 = (int)(e >> 16);
+        if (r0 == rb) ha = hb;
+        else ha = resize_hrow(src + (size_t)r0 * S.pitch, t0, t1);
+        hb = resize_hrow(src + (size_t)(r0 + 1) * S.pitch, t0, t1);
+        rb = r0 + 1;
+        uint32_t v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (x4 + i < D.w) {
-            const uint32_t o = xt[i] & 0xffffu, wx1 = xt[i] >> 16, wx0 = 256u - wx1;
-            const uint32_t h0 = __ldg(r0 + o) * wx0 + __ldg(r0 + o + 1) * wx1;   // 8.8
-            const uint32_t h1 = __ldg(r1 + o) * wx0 + __ldg(r1 + o + 1) * wx1;
-            uint32_t v = (h0 * wy0 + h1 * wy1 + 32768u) >> 16;                   // 16.16 -> u8
-            if (thresh && v <= 254u) v = 0;   // mask levels: threshold(254, THRESH_TOZERO)
-            out |= v << (8 * i);
+        for (int i = 0; i < 4; ++i) {
+            const int d = (int)hb.h[i] - (int)ha.h[i];
+            v[i] = (uint32_t)(d * wy1 + (int)(ha.h[i] * 256u + 32768u));      // 16.16, byte 2 = rounded pixel
+            if (thresh && (v[i] >> 16) <= 254u) v[i] = 0;                     // mask levels: threshold(254, TOZERO)
         }
+        const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062);
+        *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = __byte_perm(p01, p23, 0x5410);
     }
-    *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch + x4) = out;
 }
 
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask)
 {
     const LevelGeom &D = g.lv[level], &S = g.lv[level - 1];
-    dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, nframes), block(32, 8);
+    const int cgs = (D.w + 3) / 4, chunks = (D.h + RS_ROWS - 1) / RS_ROWS;
+    dim3 grid((cgs + 31) / 32, (chunks + 3) / 4, nframes), block(32, 4);
     uint8_t *base = is_mask ? b.mask : b.pyr;
     ProfScope ps(ctx, PK_RESIZE);
     resize_kernel<<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, is_mask ? 1 : 0);
@@ -81,21 +112,27 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int &total
 }
 
 // ------------------------------------------------------------------ FAST-9/16 + NMS (A3, A4 filters)
-// One CTA = one 62x30 output tile.  Pixels are staged in shared memory twice as u16 (one copy
-// shifted by a pixel) so that any horizontally adjacent pixel pair is one aligned 32-bit word:
-// the ring test then runs on u16x2 lanes with the 3-input min/max instructions (VIMNMX3.U16x2),
+// One CTA = one tile of 62x30 output pixels = a 64x32 block of scores = a (64+6)x(32+6) block of
+// pixels.  Pixels are staged in shared memory twice as u16 -- copy A at even alignment, copy Bc
+// shifted by one pixel -- so that ANY horizontally adjacent pixel pair is one aligned 32-bit word.
+// The ring test then runs on u16x2 lanes with the 3-input min/max instruction (VIMNMX3.U16x2):
 // two pixels per thread per instruction.
 //
 // With d_k = v - ring_k:  A = max_arcs min_k d_k = v - min_arcs max_k ring_k, and
 // B = max_arcs min_k(-d_k) = max_arcs min_k ring_k - v, so only min/max of raw ring values over
 // the sixteen 9-arcs are needed.  Corner iff max(A,B) > t; score = max(A,B) - 1.
-constexpr int FA_PITCH = 72;
+//
+// Score block origin: sx0 = ((edge-1) & ~1) + 62*tx (even, so a pair never straddles a word),
+// sy0 = edge-1 + 30*ty; outputs are its interior columns 1..62 / rows 1..30.
+constexpr int FA_PITCH = 80;      // u16 per staged row (76 used), 160 B
+constexpr int FA_WORDS = 19;      // aligned 32-bit global words per staged row
 
 template <int DX, int DY>
-__device__ __forceinline__ uint32_t ring_pair(const uint16_t (*A)[FA_PITCH], const uint16_t (*Bc)[FA_PITCH], int r, int p)
+__device__ __forceinline__ uint32_t ring_pair(const uint16_t (*A)[FA_PITCH], const uint16_t (*Bc)[FA_PITCH], int r, int gp)
 {
-    if (DX & 1) return reinterpret_cast<const uint32_t *>(A[r + 3 + DY])[(3 + DX) / 2 + p];
-    return reinterpret_cast<const uint32_t *>(Bc[r + 3 + DY])[(2 + DX) / 2 + p];
+    // gp = g0/2 + p where g0 = staged column of score column 0
+    if ((DX & 1) == 0) return reinterpret_cast<const uint32_t *>(A[r + 3 + DY])[gp + DX / 2];
+    return reinterpret_cast<const uint32_t *>(Bc[r + 3 + DY])[gp + (DX - 1) / 2];
 }
 
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
@@ -106,8 +143,8 @@ fast_kernel(OrbGeom g, OrbBuffers b)
 {
     __shared__ __align__(16) uint16_t A[FT_PIX_H][FA_PITCH];
     __shared__ __align__(16) uint16_t Bc[FT_PIX_H][FA_PITCH];
-    __shared__ __align__(16) uint8_t S[FT_SCORE_H][FT_SCORE_W];
-    __shared__ int warp_sums[8];
+    __shared__ uint32_t S[FT_SCORE_H][FT_SCORE_W / 2];      // two u16 scores per word
+    __shared__ int warp_tot[8];
 
     const int tile = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
     int l = 0;
@@ -117,33 +154,44 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     const LevelGeom L = g.lv[l];
     const int tl = tile - L.tile_off;
     const int ty = tl / L.tiles_x, tx = tl - ty * L.tiles_x;
-    const int ox = g.edge + tx * FT_OUT_W, oy = g.edge + ty * FT_OUT_H;   // first output pixel
-    const int px0 = ox - 4, py0 = oy - 4;
+    const int sx0 = ((g.edge - 1) & ~1) + tx * FT_OUT_W, sy0 = g.edge - 1 + ty * FT_OUT_H;
+    const int gx0 = (sx0 - 3) & ~3;          // first staged column (aligned), staged row 0 is y = sy0-3
+    const int g0 = sx0 - gx0;                // 4 or 6
     const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
 
-    for (int i = tid; i < FT_PIX_H * FT_PIX_W; i += 256) {
-        const int r = i / FT_PIX_W, c = i - r * FT_PIX_W;
-        const int x = min(px0 + c, L.w - 1), y = min(py0 + r, L.h - 1);
-        const uint16_t v = __ldg(img + (size_t)y * L.pitch + x);
-        A[r][c] = v;
-        if (c >= 1) Bc[r][c - 1] = v;
+    // stage 38 rows x 19 words; each word becomes four u16 in A, and (shifted by one pixel) in Bc
+    for (int i = tid; i < FT_PIX_H * FA_WORDS; i += 256) {
+        const int r = i / FA_WORDS, j = i - r * FA_WORDS;
+        const int y = min(sy0 - 3 + r, L.h - 1);
+        const int x = min(gx0 + 4 * j, L.pitch - 4);
+        const uint8_t *row = img + (size_t)y * L.pitch;
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+        const uint32_t nx = __ldg(row + min(x + 4, L.pitch - 1));
+        uint2 a, c;
+        a.x = __byte_perm(w, 0, 0x4140); a.y = __byte_perm(w, 0, 0x4342);
+        c.x = __byte_perm(w, 0, 0x4241); c.y = __byte_perm(w, nx, 0x7473);
+        *reinterpret_cast<uint2 *>(&A[r][4 * j]) = a;
+        *reinterpret_cast<uint2 *>(&Bc[r][4 * j]) = c;       // Bc[i] = pixel i+1
     }
     __syncthreads();
 
     const int warp = tid >> 5, p = tid & 31;
-    const int thr = g.fast_thr;
+    const int gp = g0 / 2 + p;
+    // cv::FAST evaluates pixels [3, w-3) x [3, h-3) only; x >= 3 and y >= 3 always hold here (edge >= 19)
+    const int px_x = sx0 + 2 * p;
+    const int thr0 = px_x < L.w - 3 ? g.fast_thr : 0x7fffffff, thr1 = px_x + 1 < L.w - 3 ? g.fast_thr : 0x7fffffff;
 #pragma unroll 1
     for (int r = warp; r < FT_SCORE_H; r += 8) {
         uint32_t v[16];
-        v[0] = ring_pair<0, 3>(A, Bc, r, p);    v[1] = ring_pair<1, 3>(A, Bc, r, p);
-        v[2] = ring_pair<2, 2>(A, Bc, r, p);    v[3] = ring_pair<3, 1>(A, Bc, r, p);
-        v[4] = ring_pair<3, 0>(A, Bc, r, p);    v[5] = ring_pair<3, -1>(A, Bc, r, p);
-        v[6] = ring_pair<2, -2>(A, Bc, r, p);   v[7] = ring_pair<1, -3>(A, Bc, r, p);
-        v[8] = ring_pair<0, -3>(A, Bc, r, p);   v[9] = ring_pair<-1, -3>(A, Bc, r, p);
-        v[10] = ring_pair<-2, -2>(A, Bc, r, p); v[11] = ring_pair<-3, -1>(A, Bc, r, p);
-        v[12] = ring_pair<-3, 0>(A, Bc, r, p);  v[13] = ring_pair<-3, 1>(A, Bc, r, p);
-        v[14] = ring_pair<-2, 2>(A, Bc, r, p);  v[15] = ring_pair<-1, 3>(A, Bc, r, p);
-        const uint32_t c = ring_pair<0, 0>(A, Bc, r, p);
+        v[0] = ring_pair<0, 3>(A, Bc, r, gp);    v[1] = ring_pair<1, 3>(A, Bc, r, gp);
+        v[2] = ring_pair<2, 2>(A, Bc, r, gp);    v[3] = ring_pair<3, 1>(A, Bc, r, gp);
+        v[4] = ring_pair<3, 0>(A, Bc, r, gp);    v[5] = ring_pair<3, -1>(A, Bc, r, gp);
+        v[6] = ring_pair<2, -2>(A, Bc, r, gp);   v[7] = ring_pair<1, -3>(A, Bc, r, gp);
+        v[8] = ring_pair<0, -3>(A, Bc, r, gp);   v[9] = ring_pair<-1, -3>(A, Bc, r, gp);
+        v[10] = ring_pair<-2, -2>(A, Bc, r, gp); v[11] = ring_pair<-3, -1>(A, Bc, r, gp);
+        v[12] = ring_pair<-3, 0>(A, Bc, r, gp);  v[13] = ring_pair<-3, 1>(A, Bc, r, gp);
+        v[14] = ring_pair<-2, 2>(A, Bc, r, gp);  v[15] = ring_pair<-1, 3>(A, Bc, r, gp);
+        const uint32_t c = ring_pair<0, 0>(A, Bc, r, gp);
 
         uint32_t hi3[16], lo3[16];
 #pragma unroll
@@ -169,44 +217,62 @@ fast_kernel(OrbGeom g, OrbBuffers b)
         const int c0 = (int)(c & 0xffffu), c1 = (int)(c >> 16);
         const int s0 = max(c0 - (int)(mn & 0xffffu), (int)(mx & 0xffffu) - c0);
         const int s1 = max(c1 - (int)(mn >> 16), (int)(mx >> 16) - c1);
-        // cv::FAST evaluates pixels [3, w-3) x [3, h-3) only
-        const int x = ox - 1 + 2 * p, y = oy - 1 + r;
-        const bool yin = y >= 3 && y < L.h - 3;
-        const uint32_t o0 = (s0 > thr && yin && x >= 3 && x < L.w - 3) ? (uint32_t)(s0 - 1) : 0u;
-        const uint32_t o1 = (s1 > thr && yin && x + 1 >= 3 && x + 1 < L.w - 3) ? (uint32_t)(s1 - 1) : 0u;
-        reinterpret_cast<uint16_t *>(S[r])[p] = (uint16_t)(o0 | (o1 << 8));
+        const bool yin = sy0 + r < L.h - 3;
+        const uint32_t o0 = (s0 > thr0 && yin) ? (uint32_t)(s0 - 1) : 0u;
+        const uint32_t o1 = (s1 > thr1 && yin) ? (uint32_t)(s1 - 1) : 0u;
+        S[r][p] = o0 | (o1 << 16);
     }
     __syncthreads();
 
-    // 3x3 strict non-max suppression + border/mask filter; 8 consecutive columns per thread.
+    // 3x3 strict non-max suppression in the same pair layout.  Warp w owns rows 1+4w .. 4+4w, so the
+    // emitted order is row-major; positions come from ballots (no atomics, deterministic).
+    // For a column x: C3 = max of the three rows (centre row included), V = max of rows above/below.
+    // neighbours(x) = max(V[x], C3[x-1], C3[x+1]); columns x-1 / x+1 of a pair come from the lanes beside it.
+    const uint8_t *mrow = b.mask ? b.mask + (size_t)frame * g.pyr_stride + L.off : nullptr;
     uint32_t found[4];
-    int nfound = 0;
-    if (tid < 240) {
-        const int row = 1 + tid / 8, cbase = (tid & 7) * 8;
-        const uint8_t *mrow = b.mask ? b.mask + (size_t)frame * g.pyr_stride + L.off : nullptr;
-        const int y = oy - 1 + row;
+    int off[4];
+    int local = 0;
+    const bool col0_ok = p >= 1 && px_x >= g.edge && px_x < L.w - g.edge;
+    const bool col1_ok = p <= 30 && px_x + 1 >= g.edge && px_x + 1 < L.w - g.edge;
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-            const int col = cbase + cc;
-            if (col < 1 || col > FT_OUT_W) continue;
-            const int s = S[row][col];
-            if (s == 0) continue;
-            const bool is_max = s > S[row - 1][col - 1] && s > S[row - 1][col] && s > S[row - 1][col + 1] &&
-                                s > S[row][col - 1] && s > S[row][col + 1] &&
-                                s > S[row + 1][col - 1] && s > S[row + 1][col] && s > S[row + 1][col + 1];
-            const int x = ox - 1 + col;
-            if (!is_max || x >= L.w - g.edge || y >= L.h - g.edge) continue;
-            if (mrow && __ldg(mrow + (size_t)y * L.pitch + x) == 0) continue;
-            if (nfound < 4) found[nfound] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
-            ++nfound;
+    for (int k = 0; k < 4; ++k) {
+        const int r = 1 + 4 * warp + k;
+        uint32_t e = 0;
+        if (r <= FT_OUT_H) {
+            const uint32_t up = S[r - 1][p], cur = S[r][p], dn = S[r + 1][p];
+            const uint32_t V = __vmaxu2(up, dn), C3 = max3(up, cur, dn);
+            const uint32_t Lw = __shfl_up_sync(0xffffffffu, C3, 1), Rw = __shfl_down_sync(0xffffffffu, C3, 1);
+            const uint32_t nb = max3(V, __byte_perm(Lw, C3, 0x5432), __byte_perm(C3, Rw, 0x5432));
+            const int s0 = (int)(cur & 0xffffu), s1 = (int)(cur >> 16);
+            const int y = sy0 + r;
+            const bool yok = y < L.h - g.edge;
+            const int x0 = px_x;
+            // adjacent pixels are never both strict maxima, so a pair yields at most one corner
+            if (s0 > (int)(nb & 0xffffu) && col0_ok && yok &&
+                !(mrow && __ldg(mrow + (size_t)y * L.pitch + x0) == 0))
+                e = ((uint32_t)s0 << 24) | ((uint32_t)y << 12) | (uint32_t)x0;
+            else if (s1 > (int)(nb >> 16) && col1_ok && yok &&
+                     !(mrow && __ldg(mrow + (size_t)y * L.pitch + x0 + 1) == 0))
+                e = ((uint32_t)s1 << 24) | ((uint32_t)y << 12) | (uint32_t)(x0 + 1);
         }
+        const uint32_t bal = __ballot_sync(0xffffffffu, e != 0);
+        found[k] = e;
+        off[k] = local + __popc(bal & ((1u << p) - 1u));
+        local += __popc(bal);
     }
-    int total;
-    const int pos = block_excl_scan<256>(nfound, warp_sums, total);
+    if (p == 0) warp_tot[warp] = local;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = warp_tot[i];
+        if (i < warp) base += t;
+        total += t;
+    }
     uint32_t *out = b.cand + ((size_t)frame * g.tiles_per_frame + tile) * FT_CAP;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (i < nfound) out[pos + i] = found[i];
+    for (int k = 0; k < 4; ++k)
+        if (found[k]) out[base + off[k]] = found[k];
     if (tid == 0) b.cand_cnt[(size_t)frame * g.tiles_per_frame + tile] = (uint32_t)total;
 }
 
@@ -234,71 +300,135 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return min(max(i, 0), n - 1);
 }
 
-constexpr int BL_W = 128, BL_H = 16;
+// v3: one launch covers every level (tile table in LevelGeom::blur_tile_off).  Row pass: a thread
+// reads the 16 aligned bytes around its 8 outputs straight from global memory (L1-resident; no u8
+// staging buffer), converts them with the exponent trick (u8 -> f32 without the conversion unit) and
+// writes 8 row results as float into shared memory.  Column pass: 4x4 register blocks, 4 pixels per
+// 32-bit store.  Rounding to nearest even is the 1.5*2^23 trick (exact for 0 <= s < 2^22).
+constexpr int BL_W = 128, BL_H = 32;
+
+__device__ __forceinline__ float u8_to_f32(uint32_t word, int k)
+{
+    // 0x4B000000 | byte  ==  8388608.0f + byte
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
+}
+
+template <bool FUSED>
+__device__ __forceinline__ float acc(float k, float v, float s)
+{
+    return FUSED ? __fmaf_rn(k, v, s) : __fadd_rn(s, __fmul_rn(k, v));
+}
+
+template <bool FUSED>
+__device__ __forceinline__ void blur_row8(const float (&v)[14], float *__restrict__ out, const BlurTaps &T)
+{
+    // v[k] = pixel x-3+k; output i uses v[i .. i+6], taps left to right
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float s = __fmul_rn(T.k[0], v[i]);
+        s = acc<FUSED>(T.k[1], v[i + 1], s);
+        s = acc<FUSED>(T.k[2], v[i + 2], s);
+        s = acc<FUSED>(T.k[3], v[i + 3], s);
+        s = acc<FUSED>(T.k[2], v[i + 4], s);
+        s = acc<FUSED>(T.k[1], v[i + 5], s);
+        s = acc<FUSED>(T.k[0], v[i + 6], s);
+        r[i] = s;
+    }
+    *reinterpret_cast<float4 *>(out) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4 *>(out + 4) = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+template <bool FUSED>
+__device__ __forceinline__ uint32_t blur_col4(const float4 *w, int j, const BlurTaps &T)
+{
+    // w[0..9] = rows r..r+9 of one 4-column group; output row j uses w[j .. j+6], centre w[j+3]
+    const float *a0 = reinterpret_cast<const float *>(&w[j]), *a1 = reinterpret_cast<const float *>(&w[j + 1]);
+    const float *a2 = reinterpret_cast<const float *>(&w[j + 2]), *a3 = reinterpret_cast<const float *>(&w[j + 3]);
+    const float *a4 = reinterpret_cast<const float *>(&w[j + 4]), *a5 = reinterpret_cast<const float *>(&w[j + 5]);
+    const float *a6 = reinterpret_cast<const float *>(&w[j + 6]);
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float s = __fmul_rn(T.k[3], a3[i]);
+        s = acc<FUSED>(T.k[2], __fadd_rn(a4[i], a2[i]), s);
+        s = acc<FUSED>(T.k[1], __fadd_rn(a5[i], a1[i]), s);
+        s = acc<FUSED>(T.k[0], __fadd_rn(a6[i], a0[i]), s);
+        // cvRound + saturate: s is a convex combination of [0,255] values up to float rounding
+        const int v = __float_as_int(__fadd_rn(s, 12582912.0f)) - 0x4B400000;
+        out |= (uint32_t)min(max(v, 0), 255) << (8 * i);
+    }
+    return out;
+}
 
 __global__ void __launch_bounds__(256)
-blur_kernel(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, unsigned int stride, LevelGeom L, BlurTaps T)
+blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
 {
-    __shared__ uint8_t P[BL_H + 6][BL_W + 8];
-    __shared__ float R[BL_H + 6][BL_W];
-    const int x0 = blockIdx.x * BL_W, y0 = blockIdx.y * BL_H, tid = threadIdx.x;
-    const uint8_t *img = pyr + (size_t)blockIdx.z * stride + L.off;
-    uint8_t *dst = blur + (size_t)blockIdx.z * stride + L.off;
+    __shared__ __align__(16) float R[BL_H + 6][BL_W];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ORB_MAX_LEVELS; ++i)
+        if (i < g.nbuilt && tile >= g.lv[i].blur_tile_off) l = i;
+    const LevelGeom L = g.lv[l];
+    const int tl = tile - L.blur_tile_off;
+    const int btx = (L.w + BL_W - 1) / BL_W;
+    const int ty = tl / btx, tx = tl - ty * btx;
+    const int x0 = tx * BL_W, y0 = ty * BL_H;
+    const uint8_t *img = b.pyr + (size_t)blockIdx.y * g.pyr_stride + L.off;
+    uint8_t *dst = b.blur + (size_t)blockIdx.y * g.pyr_stride + L.off;
 
-    for (int i = tid; i < (BL_H + 6) * (BL_W + 6); i += 256) {
-        const int r = i / (BL_W + 6), c = i - r * (BL_W + 6);
-        const int x = reflect101(x0 - 3 + c, L.w), y = reflect101(y0 - 3 + r, L.h);
-        P[r][c] = __ldg(img + (size_t)y * L.pitch + x);
-    }
-    __syncthreads();
-    for (int i = tid; i < (BL_H + 6) * BL_W; i += 256) {
-        const int r = i / BL_W, c = i - r * BL_W;
-        const bool fused = x0 + c < L.row_fused_end;
-        float s = __fmul_rn(T.k[0], (float)P[r][c]);
+    // row pass: 38 rows x 16 groups of 8 outputs
+    for (int i = tid; i < (BL_H + 6) * (BL_W / 8); i += 256) {
+        const int r = i / (BL_W / 8), c8 = (i - r * (BL_W / 8)) * 8;
+        const int x = x0 + c8;
+        if (x >= L.w) continue;
+        const uint8_t *row = img + (size_t)reflect101(y0 - 3 + r, L.h) * L.pitch;
+        float v[14];
+        if (x >= 4 && x + 12 <= L.w) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x - 4);
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+            v[0] = u8_to_f32(w0, 1); v[1] = u8_to_f32(w0, 2); v[2] = u8_to_f32(w0, 3);
+            v[3] = u8_to_f32(w1, 0); v[4] = u8_to_f32(w1, 1); v[5] = u8_to_f32(w1, 2); v[6] = u8_to_f32(w1, 3);
+            v[7] = u8_to_f32(w2, 0); v[8] = u8_to_f32(w2, 1); v[9] = u8_to_f32(w2, 2); v[10] = u8_to_f32(w2, 3);
+            v[11] = u8_to_f32(w3, 0); v[12] = u8_to_f32(w3, 1); v[13] = u8_to_f32(w3, 2);
+        } else {
 #pragma unroll
-        for (int k = 1; k < 7; ++k) {
-            const float kk = T.k[k < 4 ? k : 6 - k], pv = (float)P[r][c + k];
-            s = fused ? __fmaf_rn(kk, pv, s) : __fadd_rn(s, __fmul_rn(kk, pv));
+            for (int k = 0; k < 14; ++k) v[k] = (float)__ldg(row + reflect101(x - 3 + k, L.w));
         }
-        R[r][c] = s;
+        if (x < L.row_fused_end) blur_row8<true>(v, &R[r][c8], T);
+        else blur_row8<false>(v, &R[r][c8], T);
     }
     __syncthreads();
-    for (int t = tid; t < BL_H * BL_W / 4; t += 256) {
-        const int r = t / (BL_W / 4), c4 = (t - r * (BL_W / 4)) * 4;
-        const int y = y0 + r;
-        if (y >= L.h || x0 + c4 >= L.w) continue;
-        uint32_t out = 0;
+    // column pass: 32 groups of 4 columns x 8 runs of 4 rows = 256 register blocks
+    {
+        const int c4 = (tid & 31) * 4, r0 = (tid >> 5) * 4;
+        if (x0 + c4 < L.w && y0 + r0 < L.h) {
+            float4 w[10];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = c4 + i;
-            const bool fused = x0 + c < L.col_fused_end;
-            float s = __fmul_rn(T.k[3], R[r + 3][c]);
+            for (int k = 0; k < 10; ++k) w[k] = *reinterpret_cast<const float4 *>(&R[r0 + k][c4]);
+            const bool fused = x0 + c4 < L.col_fused_end;
 #pragma unroll
-            for (int k = 1; k <= 3; ++k) {
-                const float pr = __fadd_rn(R[r + 3 + k][c], R[r + 3 - k][c]);
-                s = fused ? __fmaf_rn(T.k[3 - k], pr, s) : __fadd_rn(s, __fmul_rn(T.k[3 - k], pr));
+            for (int j = 0; j < 4; ++j) {
+                if (y0 + r0 + j >= L.h) break;
+                const uint32_t out = fused ? blur_col4<true>(w, j, T) : blur_col4<false>(w, j, T);
+                *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r0 + j) * L.pitch + x0 + c4) = out;
             }
-            const int v = min(max(__float2int_rn(s), 0), 255);
-            out |= (uint32_t)v << (8 * i);
         }
-        *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.pitch + x0 + c4) = out;
     }
 }
 
 int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
 {
+    if (g.blur_tiles_per_frame == 0) return ASLAM_OK;
     BlurTaps T;
     double t[7], sum = 0;
     for (int i = 0; i < 7; ++i) { const double x = i - 3; t[i] = exp(-0.125 * x * x); sum += t[i]; }
     for (int i = 0; i < 4; ++i) T.k[i] = (float)(t[i] / sum);
-    for (int l = 0; l < g.nbuilt; ++l) {
-        const LevelGeom &L = g.lv[l];
-        if (L.tiles_x == 0) continue;   // no keypoints possible on this level
-        dim3 grid((L.w + BL_W - 1) / BL_W, (L.h + BL_H - 1) / BL_H, nframes);
-        ProfScope ps(ctx, PK_BLUR);
-        blur_kernel<<<grid, 256, 0, ctx->stream>>>(b.pyr, b.blur, g.pyr_stride, L, T);
-        ASLAM_LAUNCH_CHECK();
-    }
+    dim3 grid(g.blur_tiles_per_frame, nframes);
+    ProfScope ps(ctx, PK_BLUR);
+    blur_kernel<<<grid, 256, 0, ctx->stream>>>(g, b, T);
+    ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
 
@@ -537,11 +667,14 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 __device__ const int8_t c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
+constexpr int DP_ROWS = 39, DP_WORDS = 12;      // blurred patch: +-19 rows, 48-byte rows (aligned start)
+
 __global__ void __launch_bounds__(256)
 describe_kernel(OrbGeom g, OrbBuffers b)
 {
-    const int frame = blockIdx.y, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);     // keypoint index within the frame
+    __shared__ uint32_t patch_s[8][DP_ROWS * DP_WORDS];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * 8 + warp;     // keypoint index within the frame
     const int32_t *sc = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS;
     int l = -1, first = 0, total = 0;
 #pragma unroll
@@ -562,22 +695,38 @@ describe_kernel(OrbGeom g, OrbBuffers b)
     const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
     const uint8_t *blr = b.blur + (size_t)frame * g.pyr_stride + L.off;
 
-    // ICAngles: m10 = sum u*I, m01 = sum v*I over |u| <= umax[|v|]
+    // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
+    const float kx = __fmul_rn((float)x, L.sf), ky = __fmul_rn((float)y, L.sf);
+    const float inv = __fdiv_rn(1.f, L.sf);
+    const int xi = __float2int_rn(__fmul_rn(kx, inv)), yi = __float2int_rn(__fmul_rn(ky, inv));
+
+    // Stage the 39-row blurred patch with aligned 32-bit loads (15 per lane, coalesced per row); the
+    // loads are in flight while the orientation is computed.  Every sample of the rotated pattern lies
+    // within +-19 px of the centre (pattern radius < 18.4).
+    const int ax = (xi - 19) & ~3;
+    uint32_t pw[15];
+#pragma unroll
+    for (int it = 0; it < 15; ++it) {
+        const int idx = min(lane + 32 * it, DP_ROWS * DP_WORDS - 1);
+        const int r = idx / DP_WORDS, w = idx - r * DP_WORDS;
+        pw[it] = __ldg(reinterpret_cast<const uint32_t *>(blr + (size_t)(yi - 19 + r) * L.pitch + min(ax + 4 * w, L.pitch - 4)));
+    }
+
+    // ICAngles: m10 = sum u*I, m01 = sum v*I over |u| <= umax[|v|].  Lane = column u; the disc is
+    // symmetric, so column u spans rows |v| <= umax[|u|]: m10 = u * (column sum), m01 = sum v*I.
     const int u = lane - 15;
-    int m10 = 0, m01 = 0;
+    int colsum = 0, m01 = 0;
     if (lane < 31) {
+        const int vmax = c_umax[u < 0 ? -u : u];
         const uint8_t *c = img + (size_t)y * L.pitch + x + u;
-        const int au = u < 0 ? -u : u;
 #pragma unroll 1
-        for (int v = -15; v <= 15; ++v) {
-            const int av = v < 0 ? -v : v;
-            if (au <= c_umax[av]) {
-                const int val = __ldg(c + (ptrdiff_t)v * L.pitch);
-                m10 += u * val;
-                m01 += v * val;
-            }
+        for (int v = -vmax; v <= vmax; ++v) {
+            const int val = __ldg(c + (ptrdiff_t)v * L.pitch);
+            colsum += val;
+            m01 += v * val;
         }
     }
+    int m10 = u * colsum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -585,25 +734,30 @@ describe_kernel(OrbGeom g, OrbBuffers b)
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
-    const float kx = __fmul_rn((float)x, L.sf), ky = __fmul_rn((float)y, L.sf);
-    const float inv = __fdiv_rn(1.f, L.sf);
-    const int xi = __float2int_rn(__fmul_rn(kx, inv)), yi = __float2int_rn(__fmul_rn(ky, inv));
+    uint32_t *ps = patch_s[warp];
+#pragma unroll
+    for (int it = 0; it < 15; ++it)
+        if (lane + 32 * it < DP_ROWS * DP_WORDS) ps[lane + 32 * it] = pw[it];
+    __syncwarp();
+
     const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
-    const uint8_t *center = blr + (size_t)yi * L.pitch + xi;
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    const float ca = (float)cd, sa = (float)sd;
+    // cvRound by the 1.5*2^23 trick: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v) for |v| < 2^22.
+    // The constant is folded into the patch offset: byte = (iy+19)*48 + (xi-ax) + ix.
+    const uint8_t *pb = reinterpret_cast<const uint8_t *>(ps);
+    const uint32_t fold = (uint32_t)(19 * DP_WORDS * 4 + (xi - ax)) - 0x4B400000u * (uint32_t)(DP_WORDS * 4 + 1);
     uint32_t byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const uint32_t pk = __ldg(b.pattern + lane * 8 + j);
-        const float x0 = (float)(int8_t)(pk & 0xff), y0 = (float)(int8_t)((pk >> 8) & 0xff);
-        const float x1 = (float)(int8_t)((pk >> 16) & 0xff), y1 = (float)(int8_t)(pk >> 24);
-        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
-        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
-        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
-        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
-        const int t0 = __ldg(center + (ptrdiff_t)iy0 * L.pitch + ix0);
-        const int t1 = __ldg(center + (ptrdiff_t)iy1 * L.pitch + ix1);
+        const float4 pt = __ldg(b.pattern + j * 32 + lane);      // (x0, y0, x1, y1) of comparison 8*lane + j
+        const uint32_t X0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, ca), __fmul_rn(pt.y, sa)), 12582912.0f));
+        const uint32_t Y0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, sa), __fmul_rn(pt.y, ca)), 12582912.0f));
+        const uint32_t X1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, ca), __fmul_rn(pt.w, sa)), 12582912.0f));
+        const uint32_t Y1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, sa), __fmul_rn(pt.w, ca)), 12582912.0f));
+        const int t0 = pb[Y0 * (uint32_t)(DP_WORDS * 4) + X0 + fold];
+        const int t1 = pb[Y1 * (uint32_t)(DP_WORDS * 4) + X1 + fold];
         byte |= (uint32_t)(t0 < t1) << j;
     }
     b.desc[(fslot * g.kp_cap + slot) * 32 + lane] = (uint8_t)byte;

@@ -233,7 +233,8 @@ ASLAM_API int aslam_loop_merge_top2_device(aslam_ctx *ctx, const uint64_t *d_par
 /* ------------------------------------------------------------------ pipe micro-benchmarks
  * Measured integer-pipe ceilings used as roofline denominators for the matching kernel
  * (SURVEY.md 8d asks for the POPC rate to be measured, not assumed).  which: 0 = POPC,
- * 1 = LOP3, 2 = IADD3, 3 = VIMNMX3.U16x2.  Returns giga warp-lane operations per second. */
+ * 1 = LOP3, 2 = IADD3, 3 = VIMNMX3.U16x2, 4 = HMNMX2, 5 = VIMNMX3.U16x2 + HMNMX2 interleaved,
+ * 6 = IMAD, 7 = PRMT.  Returns giga warp-lane operations per second. */
 ASLAM_API int aslam_microbench(aslam_ctx *ctx, int which, double *gops);
 
 #ifdef __cplusplus

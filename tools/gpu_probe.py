@@ -8,7 +8,7 @@ from aria_slam_b200 import synth
 
 ctx = Context(0)
 out = {"sm_count": ctx.sm_count}
-for which, name in enumerate(["popc", "lop3", "iadd3", "vimnmx3_u16x2"]):
+for which, name in enumerate(["popc", "lop3", "iadd3", "vimnmx3_u16x2", "hmnmx2", "vimnmx3+hmnmx2", "imad", "prmt"]):
     out["gops_" + name] = ctx.microbench(which)
 frames = synth.frame_stream(32, 752, 480, 1000)
 B = 256
