@@ -79,7 +79,7 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
     g.lv[nlevels - 1].quota = nfeatures - sum > 0 ? nfeatures - sum : 0;
 
     unsigned int off = 0;
-    int tile_off = 0, sel_off = 0, blur_off = 0;
+    int tile_off = 0, sel_off = 0, blur_off = 0, desc_off = 0;
     g.nbuilt = 0;
     tables.clear();
     for (int l = 0; l < nlevels; ++l) {
@@ -95,11 +95,15 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
         L.tiles_y = active ? (rh + FT_OUT_H - 1) / FT_OUT_H : 0;
         L.tile_off = tile_off;
         L.blur_tile_off = blur_off;
-        if (active) blur_off += ((L.w + 127) / 128) * ((L.h + 31) / 32);
+        if (active) blur_off += ((L.w + 127) / 128) * ((L.h + 57) / 58);      // 128x58 blur tiles
         tile_off += L.tiles_x * L.tiles_y;
         L.sel_off = sel_off;
         L.sel_cap = L.quota + SEL_TIE_ROOM;
         sel_off += L.sel_cap;
+        L.desc_block_off = desc_off;
+        if (active) desc_off += (L.sel_cap + 7) / 8;
+        L.inv_sf = 1.f / L.sf;
+        L.kp_size = 31.f * L.sf;
         L.row_fused_end = blur_mode == 0 ? 0 : blur_mode == 1 ? L.w : (L.w & ~31);
         L.col_fused_end = blur_mode == 0 ? 0 : blur_mode == 1 ? L.w : (L.w & ~3);
         if (active) g.nbuilt = l + 1;
@@ -122,6 +126,7 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
     g.pyr_stride = off ? off : 256;
     g.tiles_per_frame = tile_off;
     g.blur_tiles_per_frame = blur_off;
+    g.desc_blocks_per_frame = desc_off;
     g.kp_cap = (sel_off + 63) / 64 * 64;
 }
 

@@ -22,13 +22,16 @@ struct LevelGeom {
     unsigned int off;        // byte offset of the level inside a frame's pyramid block
     int tiles_x, tiles_y;    // FAST tiles covering [edge, w-edge) x [edge, h-edge)
     int tile_off;            // first tile index of this level within the frame
-    int blur_tile_off;       // first 128x32 blur tile of this level within the frame
+    int blur_tile_off;       // first 128x58 blur tile of this level within the frame
     int quota;               // N_l
     int sel_off, sel_cap;    // rows of this level in the per-frame selection buffer
+    int desc_block_off;      // first describe CTA (8 keypoints each) of this level within the frame
     int xtab_off, ytab_off;  // resize tables (level l-1 -> l), in uint32 entries
     int row_fused_end;       // blur: row-pass columns below this use fused multiply-add
     int col_fused_end;
     float sf;                // scale of the level
+    float inv_sf;            // 1.f / sf (float division, as computeOrbDescriptors does)
+    float kp_size;           // 31.f * sf
 };
 
 struct OrbGeom {
@@ -37,6 +40,7 @@ struct OrbGeom {
     int width, height, edge, fast_thr;
     int tiles_per_frame;
     int blur_tiles_per_frame;
+    int desc_blocks_per_frame;
     int kp_cap;              // keypoint rows per frame in the output buffers
     unsigned int pyr_stride; // bytes per frame of pyramid (and of blurred pyramid, and of mask pyramid)
     LevelGeom lv[ORB_MAX_LEVELS];

@@ -12,22 +12,16 @@
 namespace aslam {
 
 // ------------------------------------------------------------------ exact bilinear resize (A2)
-// One thread = 4 consecutive output columns x RS_ROWS output rows, marching down.  Per source row
-// the 4 horizontal interpolations are done once and reused by the next output row (scale 1.2:
-// consecutive output rows share a source row most of the time):
+// Per source row and group of 4 output columns:
 //   3 aligned 32-bit loads cover the <= 6-byte window of the 4 outputs, a funnel shift aligns it,
 //   and each 8.8 value is ONE PRMT + ONE DP4A:  (a, b, a, .) . (255-c1, c1, 1, 0) = a*(256-c1) + b*c1.
 // Vertical: v = hA*256 + (hB-hA)*wy1 + 2^15, byte 2 of v is the pixel (>>16); 3 PRMTs pack 4 pixels.
 // Column tables (window word, shift, 4 selectors, 4 weight words) are built on the host with the
 // double arithmetic OpenCV uses and depend only on the level sizes.
-constexpr int RS_ROWS = 16;
-
 struct HRow { uint32_t h[4]; };
 
-__device__ __forceinline__ HRow resize_hrow(const uint8_t *__restrict__ row, const uint4 t0, const uint4 t1)
+__device__ __forceinline__ HRow resize_hrow(uint32_t w0, uint32_t w1, uint32_t w2, const uint4 t0, const uint4 t1)
 {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(row) + t0.x;
-    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
     const uint32_t lo = __funnelshift_r(w0, w1, t0.y), hi = __funnelshift_r(w1, w2, t0.y);
     HRow r;
     r.h[0] = __dp4a(__byte_perm(lo, hi, t0.z & 0xffffu), t1.x, 0u);
@@ -37,48 +31,43 @@ __device__ __forceinline__ HRow resize_hrow(const uint8_t *__restrict__ row, con
     return r;
 }
 
-__global__ void __launch_bounds__(128)
+// One thread = 4 consecutive output pixels of one row: six independent 32-bit loads issued up front
+// (no serial march down the image: the kernel is latency-, not instruction-limited), source-row reuse
+// between neighbouring output rows is left to L1.
+__global__ void __launch_bounds__(256)
 resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
               LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs, int thresh)
 {
     const int cg = blockIdx.x * 32 + threadIdx.x;
-    const int y_begin = (blockIdx.y * 4 + threadIdx.y) * RS_ROWS;
-    if (cg * 4 >= D.w || y_begin >= D.h) return;
-    const int y_end = min(y_begin + RS_ROWS, D.h);
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (cg * 4 >= D.w || y >= D.h) return;
     const uint8_t *src = srcb + (size_t)blockIdx.z * stride + S.off;
-    uint8_t *dst = dstb + (size_t)blockIdx.z * stride + D.off + cg * 4;
+    uint8_t *dst = dstb + (size_t)blockIdx.z * stride + D.off;
     const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
     const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
-    const uint32_t *yt = tabs + D.ytab_off;
-
-    int rb = -1;          // source row whose horizontal pass sits in hb
-    HRow ha, hb;
-#pragma unroll 1
-    for (int y = y_begin; y < y_end; ++y) {
-        const uint32_t e = __ldg(yt + y);
-        const int r0 = (int)(e & 0xffffu);
-        const int wy1 = (int)(e >> 16);
-        if (r0 == rb) ha = hb;
-        else ha = resize_hrow(src + (size_t)r0 * S.pitch, t0, t1);
-        hb = resize_hrow(src + (size_t)(r0 + 1) * S.pitch, t0, t1);
-        rb = r0 + 1;
-        uint32_t v[4];
+    const uint32_t e = __ldg(tabs + D.ytab_off + y);
+    const int wy1 = (int)(e >> 16);
+    const uint32_t *ra = reinterpret_cast<const uint32_t *>(src + (size_t)(e & 0xffffu) * S.pitch) + t0.x;
+    const uint32_t *rb = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(ra) + S.pitch);
+    const uint32_t a0 = __ldg(ra), a1 = __ldg(ra + 1), a2 = __ldg(ra + 2);
+    const uint32_t b0 = __ldg(rb), b1 = __ldg(rb + 1), b2 = __ldg(rb + 2);
+    const HRow ha = resize_hrow(a0, a1, a2, t0, t1), hb = resize_hrow(b0, b1, b2, t0, t1);
+    uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int d = (int)hb.h[i] - (int)ha.h[i];
-            v[i] = (uint32_t)(d * wy1 + (int)(ha.h[i] * 256u + 32768u));      // 16.16, byte 2 = rounded pixel
-            if (thresh && (v[i] >> 16) <= 254u) v[i] = 0;                     // mask levels: threshold(254, TOZERO)
-        }
-        const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062);
-        *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = __byte_perm(p01, p23, 0x5410);
+    for (int i = 0; i < 4; ++i) {
+        const int d = (int)hb.h[i] - (int)ha.h[i];
+        v[i] = (uint32_t)(d * wy1 + (int)(ha.h[i] * 256u + 32768u));      // 16.16, byte 2 = rounded pixel
+        if (thresh && (v[i] >> 16) <= 254u) v[i] = 0;                     // mask levels: threshold(254, TOZERO)
     }
+    const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062);
+    *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch + cg * 4) = __byte_perm(p01, p23, 0x5410);
 }
 
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask)
 {
     const LevelGeom &D = g.lv[level], &S = g.lv[level - 1];
-    const int cgs = (D.w + 3) / 4, chunks = (D.h + RS_ROWS - 1) / RS_ROWS;
-    dim3 grid((cgs + 31) / 32, (chunks + 3) / 4, nframes), block(32, 4);
+    const int cgs = (D.w + 3) / 4;
+    dim3 grid((cgs + 31) / 32, (D.h + 7) / 8, nframes), block(32, 8);
     uint8_t *base = is_mask ? b.mask : b.pyr;
     ProfScope ps(ctx, PK_RESIZE);
     resize_kernel<<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, is_mask ? 1 : 0);
@@ -177,9 +166,12 @@ fast_kernel(OrbGeom g, OrbBuffers b)
 
     const int warp = tid >> 5, p = tid & 31;
     const int gp = g0 / 2 + p;
-    // cv::FAST evaluates pixels [3, w-3) x [3, h-3) only; x >= 3 and y >= 3 always hold here (edge >= 19)
+    // cv::FAST evaluates pixels [3, w-3) x [3, h-3) only; x >= 3 and y >= 3 always hold here (edge >= 19).
+    // The score block holds s - t (>= 1 for corners, 0 otherwise): same order for the NMS, and the
+    // response max(A,B) - 1 is restored at emit time.  neg_thr: -t per valid u16 lane, -30000 otherwise.
     const int px_x = sx0 + 2 * p;
-    const int thr0 = px_x < L.w - 3 ? g.fast_thr : 0x7fffffff, thr1 = px_x + 1 < L.w - 3 ? g.fast_thr : 0x7fffffff;
+    const uint32_t neg_thr = ((uint32_t)(px_x < L.w - 3 ? -g.fast_thr : -30000) & 0xffffu) |
+                             ((uint32_t)(px_x + 1 < L.w - 3 ? -g.fast_thr : -30000) << 16);
 #pragma unroll 1
     for (int r = warp; r < FT_SCORE_H; r += 8) {
         uint32_t v[16];
@@ -214,13 +206,10 @@ fast_kernel(OrbGeom g, OrbBuffers b)
         mx = max3(mx, max3(arc_min[9], arc_min[10], arc_min[11]), max3(arc_min[12], arc_min[13], arc_min[14]));
         mx = __vmaxu2(mx, arc_min[15]);
 
-        const int c0 = (int)(c & 0xffffu), c1 = (int)(c >> 16);
-        const int s0 = max(c0 - (int)(mn & 0xffffu), (int)(mx & 0xffffu) - c0);
-        const int s1 = max(c1 - (int)(mn >> 16), (int)(mx >> 16) - c1);
-        const bool yin = sy0 + r < L.h - 3;
-        const uint32_t o0 = (s0 > thr0 && yin) ? (uint32_t)(s0 - 1) : 0u;
-        const uint32_t o1 = (s1 > thr1 && yin) ? (uint32_t)(s1 - 1) : 0u;
-        S[r][p] = o0 | (o1 << 16);
+        // per u16 lane: s = max(c - mn, mx - c); stored value = max(s - t, 0)
+        const uint32_t a = __vsub2(c, mn), bq = __vsub2(mx, c);
+        const uint32_t sc = __viaddmax_s16x2_relu(__vmaxs2(a, bq), neg_thr, 0u);
+        S[r][p] = sy0 + r < L.h - 3 ? sc : 0u;
     }
     __syncthreads();
 
@@ -232,8 +221,9 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     uint32_t found[4];
     int off[4];
     int local = 0;
-    const bool col0_ok = p >= 1 && px_x >= g.edge && px_x < L.w - g.edge;
-    const bool col1_ok = p <= 30 && px_x + 1 >= g.edge && px_x + 1 < L.w - g.edge;
+    const uint32_t col_ok = ((p >= 1 && px_x >= g.edge && px_x < L.w - g.edge) ? 0xffffu : 0u) |
+                            ((p <= 30 && px_x + 1 >= g.edge && px_x + 1 < L.w - g.edge) ? 0xffff0000u : 0u);
+    const uint32_t resp_bias = (uint32_t)(g.fast_thr - 1);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int r = 1 + 4 * warp + k;
@@ -243,17 +233,17 @@ fast_kernel(OrbGeom g, OrbBuffers b)
             const uint32_t V = __vmaxu2(up, dn), C3 = max3(up, cur, dn);
             const uint32_t Lw = __shfl_up_sync(0xffffffffu, C3, 1), Rw = __shfl_down_sync(0xffffffffu, C3, 1);
             const uint32_t nb = max3(V, __byte_perm(Lw, C3, 0x5432), __byte_perm(C3, Rw, 0x5432));
-            const int s0 = (int)(cur & 0xffffu), s1 = (int)(cur >> 16);
             const int y = sy0 + r;
-            const bool yok = y < L.h - g.edge;
-            const int x0 = px_x;
-            // adjacent pixels are never both strict maxima, so a pair yields at most one corner
-            if (s0 > (int)(nb & 0xffffu) && col0_ok && yok &&
-                !(mrow && __ldg(mrow + (size_t)y * L.pitch + x0) == 0))
-                e = ((uint32_t)s0 << 24) | ((uint32_t)y << 12) | (uint32_t)x0;
-            else if (s1 > (int)(nb >> 16) && col1_ok && yok &&
-                     !(mrow && __ldg(mrow + (size_t)y * L.pitch + x0 + 1) == 0))
-                e = ((uint32_t)s1 << 24) | ((uint32_t)y << 12) | (uint32_t)(x0 + 1);
+            // strict maximum per lane: cur - nb > 0; adjacent pixels are never both maxima
+            uint32_t d = __vimax_s16x2_relu(__vsub2(cur, nb), 0u) & col_ok;
+            if (y >= L.h - g.edge) d = 0;
+            if (d) {
+                const bool second = (d & 0xffffu) == 0;
+                const int x = px_x + (second ? 1 : 0);
+                const uint32_t sc = second ? cur >> 16 : cur & 0xffffu;
+                if (!(mrow && __ldg(mrow + (size_t)y * L.pitch + x) == 0))
+                    e = ((sc + resp_bias) << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+            }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, e != 0);
         found[k] = e;
@@ -300,71 +290,31 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return min(max(i, 0), n - 1);
 }
 
-// v3: one launch covers every level (tile table in LevelGeom::blur_tile_off).  Row pass: a thread
-// reads the 16 aligned bytes around its 8 outputs straight from global memory (L1-resident; no u8
-// staging buffer), converts them with the exponent trick (u8 -> f32 without the conversion unit) and
-// writes 8 row results as float into shared memory.  Column pass: 4x4 register blocks, 4 pixels per
-// 32-bit store.  Rounding to nearest even is the 1.5*2^23 trick (exact for 0 <= s < 2^22).
-constexpr int BL_W = 128, BL_H = 32;
+// v4: one launch covers every level (tile table in LevelGeom::blur_tile_off); a CTA produces a
+// 128x58 tile from 64 staged rows.
+//  * Row pass: a thread takes 8 outputs of TWO adjacent rows.  It reads the 16 aligned bytes around
+//    them straight from global memory (L1-resident), converts with the exponent trick (u8 -> f32
+//    without the conversion unit) and runs the 7 taps on packed f32x2 lanes (FFMA2: one lane per
+//    row), writing float row results to shared memory.
+//  * Column pass: 4 columns x 4 rows per thread, packed f32x2 over adjacent columns; rounding to
+//    nearest even by the 1.5*2^23 trick, whose low byte IS the pixel (no clamp: the taps sum to
+//    1 within float rounding and inputs are in [0,255]); one PRMT tree packs 4 pixels per store.
+//  * Columns at or beyond row_fused_end / col_fused_end (the build's scalar tail) take a scalar
+//    path with separately rounded products.  (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2,
+//    so packed arithmetic is used only where fusion is the wanted behaviour.)
+constexpr int BL_W = 128, BL_H = 58, BL_ROWS = BL_H + 6;
 
-__device__ __forceinline__ float u8_to_f32(uint32_t word, int k)
+__device__ __forceinline__ uint32_t u8_magic(uint32_t word, int k)
 {
-    // 0x4B000000 | byte  ==  8388608.0f + byte
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
+    return __byte_perm(word, 0x4B000000u, 0x7650 + k);      // bits of 8388608.0f + byte k
 }
 
-template <bool FUSED>
-__device__ __forceinline__ float acc(float k, float v, float s)
-{
-    return FUSED ? __fmaf_rn(k, v, s) : __fadd_rn(s, __fmul_rn(k, v));
-}
-
-template <bool FUSED>
-__device__ __forceinline__ void blur_row8(const float (&v)[14], float *__restrict__ out, const BlurTaps &T)
-{
-    // v[k] = pixel x-3+k; output i uses v[i .. i+6], taps left to right
-    float r[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float s = __fmul_rn(T.k[0], v[i]);
-        s = acc<FUSED>(T.k[1], v[i + 1], s);
-        s = acc<FUSED>(T.k[2], v[i + 2], s);
-        s = acc<FUSED>(T.k[3], v[i + 3], s);
-        s = acc<FUSED>(T.k[2], v[i + 4], s);
-        s = acc<FUSED>(T.k[1], v[i + 5], s);
-        s = acc<FUSED>(T.k[0], v[i + 6], s);
-        r[i] = s;
-    }
-    *reinterpret_cast<float4 *>(out) = make_float4(r[0], r[1], r[2], r[3]);
-    *reinterpret_cast<float4 *>(out + 4) = make_float4(r[4], r[5], r[6], r[7]);
-}
-
-template <bool FUSED>
-__device__ __forceinline__ uint32_t blur_col4(const float4 *w, int j, const BlurTaps &T)
-{
-    // w[0..9] = rows r..r+9 of one 4-column group; output row j uses w[j .. j+6], centre w[j+3]
-    const float *a0 = reinterpret_cast<const float *>(&w[j]), *a1 = reinterpret_cast<const float *>(&w[j + 1]);
-    const float *a2 = reinterpret_cast<const float *>(&w[j + 2]), *a3 = reinterpret_cast<const float *>(&w[j + 3]);
-    const float *a4 = reinterpret_cast<const float *>(&w[j + 4]), *a5 = reinterpret_cast<const float *>(&w[j + 5]);
-    const float *a6 = reinterpret_cast<const float *>(&w[j + 6]);
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float s = __fmul_rn(T.k[3], a3[i]);
-        s = acc<FUSED>(T.k[2], __fadd_rn(a4[i], a2[i]), s);
-        s = acc<FUSED>(T.k[1], __fadd_rn(a5[i], a1[i]), s);
-        s = acc<FUSED>(T.k[0], __fadd_rn(a6[i], a0[i]), s);
-        // cvRound + saturate: s is a convex combination of [0,255] values up to float rounding
-        const int v = __float_as_int(__fadd_rn(s, 12582912.0f)) - 0x4B400000;
-        out |= (uint32_t)min(max(v, 0), 255) << (8 * i);
-    }
-    return out;
-}
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
 __global__ void __launch_bounds__(256)
 blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
 {
-    __shared__ __align__(16) float R[BL_H + 6][BL_W];
+    __shared__ __align__(16) float R[BL_ROWS][BL_W];
     const int tile = blockIdx.x, tid = threadIdx.x;
     int l = 0;
 #pragma unroll
@@ -377,43 +327,110 @@ blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
     const int x0 = tx * BL_W, y0 = ty * BL_H;
     const uint8_t *img = b.pyr + (size_t)blockIdx.y * g.pyr_stride + L.off;
     uint8_t *dst = b.blur + (size_t)blockIdx.y * g.pyr_stride + L.off;
+    const float2 K0 = f2(T.k[0], T.k[0]), K1 = f2(T.k[1], T.k[1]), K2 = f2(T.k[2], T.k[2]), K3 = f2(T.k[3], T.k[3]);
 
-    // row pass: 38 rows x 16 groups of 8 outputs
-    for (int i = tid; i < (BL_H + 6) * (BL_W / 8); i += 256) {
-        const int r = i / (BL_W / 8), c8 = (i - r * (BL_W / 8)) * 8;
+    // ---- row pass: 32 row pairs x 16 groups of 8 outputs = 512 tasks, two per thread
+#pragma unroll 1
+    for (int i = tid; i < (BL_ROWS / 2) * (BL_W / 8); i += 256) {
+        const int rp = i / (BL_W / 8), c8 = (i - rp * (BL_W / 8)) * 8;
         const int x = x0 + c8;
         if (x >= L.w) continue;
-        const uint8_t *row = img + (size_t)reflect101(y0 - 3 + r, L.h) * L.pitch;
-        float v[14];
+        const uint8_t *rowa = img + (size_t)reflect101(y0 - 3 + 2 * rp, L.h) * L.pitch;
+        const uint8_t *rowb = img + (size_t)reflect101(y0 - 2 + 2 * rp, L.h) * L.pitch;
+        float2 v[14];       // .x = first row, .y = second row; v[k] = pixel x-3+k
         if (x >= 4 && x + 12 <= L.w) {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x - 4);
-            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
-            v[0] = u8_to_f32(w0, 1); v[1] = u8_to_f32(w0, 2); v[2] = u8_to_f32(w0, 3);
-            v[3] = u8_to_f32(w1, 0); v[4] = u8_to_f32(w1, 1); v[5] = u8_to_f32(w1, 2); v[6] = u8_to_f32(w1, 3);
-            v[7] = u8_to_f32(w2, 0); v[8] = u8_to_f32(w2, 1); v[9] = u8_to_f32(w2, 2); v[10] = u8_to_f32(w2, 3);
-            v[11] = u8_to_f32(w3, 0); v[12] = u8_to_f32(w3, 1); v[13] = u8_to_f32(w3, 2);
+            const uint4 wa = make_uint4(__ldg(reinterpret_cast<const uint32_t *>(rowa + x - 4)), __ldg(reinterpret_cast<const uint32_t *>(rowa + x)),
+                                        __ldg(reinterpret_cast<const uint32_t *>(rowa + x + 4)), __ldg(reinterpret_cast<const uint32_t *>(rowa + x + 8)));
+            const uint4 wb = make_uint4(__ldg(reinterpret_cast<const uint32_t *>(rowb + x - 4)), __ldg(reinterpret_cast<const uint32_t *>(rowb + x)),
+                                        __ldg(reinterpret_cast<const uint32_t *>(rowb + x + 4)), __ldg(reinterpret_cast<const uint32_t *>(rowb + x + 8)));
+            const uint32_t aw[4] = {wa.x, wa.y, wa.z, wa.w}, bw[4] = {wb.x, wb.y, wb.z, wb.w};
+            const float2 M = f2(-8388608.0f, -8388608.0f);
+#pragma unroll
+            for (int k = 0; k < 14; ++k) {
+                const int byte = k + 1;
+                v[k] = __fadd2_rn(f2(__uint_as_float(u8_magic(aw[byte >> 2], byte & 3)), __uint_as_float(u8_magic(bw[byte >> 2], byte & 3))), M);
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < 14; ++k) v[k] = (float)__ldg(row + reflect101(x - 3 + k, L.w));
+            for (int k = 0; k < 14; ++k) {
+                const int xx = reflect101(x - 3 + k, L.w);
+                v[k] = f2((float)__ldg(rowa + xx), (float)__ldg(rowb + xx));
+            }
         }
-        if (x < L.row_fused_end) blur_row8<true>(v, &R[r][c8], T);
-        else blur_row8<false>(v, &R[r][c8], T);
+        float2 r[8];
+        if (x < L.row_fused_end) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                float2 s = __fmul2_rn(K0, v[o]);
+                s = __ffma2_rn(K1, v[o + 1], s);
+                s = __ffma2_rn(K2, v[o + 2], s);
+                s = __ffma2_rn(K3, v[o + 3], s);
+                s = __ffma2_rn(K2, v[o + 4], s);
+                s = __ffma2_rn(K1, v[o + 5], s);
+                s = __ffma2_rn(K0, v[o + 6], s);
+                r[o] = s;
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                float sa = __fmul_rn(T.k[0], v[o].x), sb = __fmul_rn(T.k[0], v[o].y);
+#pragma unroll
+                for (int k = 1; k < 7; ++k) {
+                    const float kk = T.k[k < 4 ? k : 6 - k];
+                    sa = __fadd_rn(sa, __fmul_rn(kk, v[o + k].x));
+                    sb = __fadd_rn(sb, __fmul_rn(kk, v[o + k].y));
+                }
+                r[o] = f2(sa, sb);
+            }
+        }
+        *reinterpret_cast<float4 *>(&R[2 * rp][c8]) = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
+        *reinterpret_cast<float4 *>(&R[2 * rp][c8 + 4]) = make_float4(r[4].x, r[5].x, r[6].x, r[7].x);
+        *reinterpret_cast<float4 *>(&R[2 * rp + 1][c8]) = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
+        *reinterpret_cast<float4 *>(&R[2 * rp + 1][c8 + 4]) = make_float4(r[4].y, r[5].y, r[6].y, r[7].y);
     }
     __syncthreads();
-    // column pass: 32 groups of 4 columns x 8 runs of 4 rows = 256 register blocks
-    {
-        const int c4 = (tid & 31) * 4, r0 = (tid >> 5) * 4;
-        if (x0 + c4 < L.w && y0 + r0 < L.h) {
-            float4 w[10];
+
+    // ---- column pass: 32 groups of 4 columns x 15 runs of 4 rows (the last run has 2)
+#pragma unroll 1
+    for (int t = tid; t < 32 * ((BL_H + 3) / 4); t += 256) {
+        const int c4 = (t & 31) * 4, r0 = (t >> 5) * 4;
+        if (x0 + c4 >= L.w || y0 + r0 >= L.h) continue;
+        float4 w[10];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) w[k] = *reinterpret_cast<const float4 *>(&R[r0 + k][c4]);
-            const bool fused = x0 + c4 < L.col_fused_end;
+        for (int k = 0; k < 10; ++k) w[k] = *reinterpret_cast<const float4 *>(&R[min(r0 + k, BL_ROWS - 1)][c4]);
+        const bool fused = x0 + c4 < L.col_fused_end;
+        const float2 MG = f2(12582912.0f, 12582912.0f);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (y0 + r0 + j >= L.h) break;
-                const uint32_t out = fused ? blur_col4<true>(w, j, T) : blur_col4<false>(w, j, T);
-                *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r0 + j) * L.pitch + x0 + c4) = out;
+        for (int j = 0; j < 4; ++j) {
+            if (r0 + j >= BL_H || y0 + r0 + j >= L.h) break;
+            uint32_t b0, b1, b2, b3;         // float bit patterns whose low byte is the rounded pixel
+            if (fused) {
+                float2 sl = __fmul2_rn(K3, f2(w[j + 3].x, w[j + 3].y)), sh = __fmul2_rn(K3, f2(w[j + 3].z, w[j + 3].w));
+                sl = __ffma2_rn(K2, __fadd2_rn(f2(w[j + 4].x, w[j + 4].y), f2(w[j + 2].x, w[j + 2].y)), sl);
+                sh = __ffma2_rn(K2, __fadd2_rn(f2(w[j + 4].z, w[j + 4].w), f2(w[j + 2].z, w[j + 2].w)), sh);
+                sl = __ffma2_rn(K1, __fadd2_rn(f2(w[j + 5].x, w[j + 5].y), f2(w[j + 1].x, w[j + 1].y)), sl);
+                sh = __ffma2_rn(K1, __fadd2_rn(f2(w[j + 5].z, w[j + 5].w), f2(w[j + 1].z, w[j + 1].w)), sh);
+                sl = __ffma2_rn(K0, __fadd2_rn(f2(w[j + 6].x, w[j + 6].y), f2(w[j].x, w[j].y)), sl);
+                sh = __ffma2_rn(K0, __fadd2_rn(f2(w[j + 6].z, w[j + 6].w), f2(w[j].z, w[j].w)), sh);
+                sl = __fadd2_rn(sl, MG); sh = __fadd2_rn(sh, MG);
+                b0 = __float_as_uint(sl.x); b1 = __float_as_uint(sl.y); b2 = __float_as_uint(sh.x); b3 = __float_as_uint(sh.y);
+            } else {
+                const float *c = reinterpret_cast<const float *>(&w[j + 3]);
+                uint32_t bb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float s = __fmul_rn(T.k[3], c[i]);
+#pragma unroll
+                    for (int k = 1; k <= 3; ++k) {
+                        const float pr = __fadd_rn(reinterpret_cast<const float *>(&w[j + 3 + k])[i], reinterpret_cast<const float *>(&w[j + 3 - k])[i]);
+                        s = __fadd_rn(s, __fmul_rn(T.k[3 - k], pr));
+                    }
+                    bb[i] = __float_as_uint(__fadd_rn(s, 12582912.0f));
+                }
+                b0 = bb[0]; b1 = bb[1]; b2 = bb[2]; b3 = bb[3];
             }
+            const uint32_t p01 = __byte_perm(b0, b1, 0x0040), p23 = __byte_perm(b2, b3, 0x0040);
+            *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r0 + j) * L.pitch + x0 + c4) = __byte_perm(p01, p23, 0x5410);
         }
     }
 }
@@ -476,6 +493,36 @@ __device__ __forceinline__ uint32_t float_order_key(float f)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Called by one full warp.  hist[256]: returns the largest bin B with sum(hist[B..255]) >= k and, through
+// `above`, sum(hist[B+1..255]); -1 if the whole histogram holds fewer than k.
+__device__ __forceinline__ int warp_kth_bin_from_top(const int *hist, int k, int &above)
+{
+    const int lane = threadIdx.x & 31;
+    int h[8], c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; c += h[i]; }
+    int suf = c;                                   // inclusive suffix sum over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += n;
+    }
+    const uint32_t ok = __ballot_sync(0xffffffffu, suf >= k);
+    if (ok == 0) { above = 0; return -1; }
+    const int owner = 31 - __clz(ok);              // suffix sums decrease with the lane index
+    int bin = -1, ab = 0;
+    if (lane == owner) {
+        int acc = suf - c;                         // everything in higher lanes
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            if (bin < 0 && acc + h[i] >= k) { bin = lane * 8 + i; ab = acc; }
+            acc += h[i];
+        }
+    }
+    above = __shfl_sync(0xffffffffu, ab, owner);
+    return __shfl_sync(0xffffffffu, bin, owner);
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(OrbGeom g, OrbBuffers b)
 {
@@ -511,20 +558,13 @@ select_kernel(OrbGeom g, OrbBuffers b)
         for (int i = lane; i < n; i += 32) atomicAdd(&hist[cand[(size_t)t * FT_CAP + i] >> 24], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-        int total = 0;
-        for (int i = 0; i < 256; ++i) total += hist[i];
-        const int K1 = 2 * L.quota;
+    if (warp == 0) {
+        // keep everything if there are at most K1 candidates, else cut at the K1-th largest score (ties kept)
+        int above;
+        const int bin = warp_kth_bin_from_top(hist, 2 * L.quota + 1, above);      // >= K1+1 exist <=> total > K1
         int thr = 0;
-        if (total > K1) {
-            int acc = 0;
-            thr = 256;
-            for (int s = 255; s >= 0; --s) {
-                acc += hist[s];
-                if (acc >= K1) { thr = s; break; }
-            }
-        }
-        s_thr = thr;
+        if (bin >= 0) thr = warp_kth_bin_from_top(hist, 2 * L.quota, above);
+        if (lane == 0) s_thr = thr;
     }
     __syncthreads();
     const uint32_t thr = (uint32_t)s_thr;
@@ -588,15 +628,12 @@ select_kernel(OrbGeom g, OrbBuffers b)
                 if ((key & maskbits) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 0xffu], 1);
             }
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0, k = s_k;
-                for (int bin = 255; bin >= 0; --bin) {
-                    if (acc + hist[bin] >= k) {
-                        s_k = k - acc;
-                        s_prefix = prefix | ((uint32_t)bin << (8 * pass));
-                        break;
-                    }
-                    acc += hist[bin];
+            if (warp == 0) {
+                int above;
+                const int bin = warp_kth_bin_from_top(hist, s_k, above);     // exists: the prefix class holds >= s_k keys
+                if (lane == 0) {
+                    s_k -= above;
+                    s_prefix = prefix | ((uint32_t)bin << (8 * pass));
                 }
             }
             maskbits |= 0xffu << (8 * pass);
@@ -665,30 +702,67 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-__device__ const int8_t c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
-constexpr int DP_ROWS = 39, DP_WORDS = 12;      // blurred patch: +-19 rows, 48-byte rows (aligned start)
+constexpr int DP_ROWS = 39, DP_WORDS = 12;      // blurred patch: +-19 rows of 12 aligned words
+constexpr int OP_ROWS = 31;                     // unblurred patch for the moments: +-15 rows, same row format
 
+// Stage `rows` rows of 12 aligned words starting at `src` (row 0, word 0) into smem: lanes 0..23 take two
+// rows per step, one 64-bit pointer bump per step, stores at compile-time offsets.
+template <int ROWS>
+__device__ __forceinline__ void stage_rows_load(const uint8_t *src, int pitch, int col0, int lane, uint32_t (&w)[(ROWS + 1) / 2])
+{
+    const int hi = lane >= 12 ? 1 : 0, wd = lane - 12 * hi;
+    const uint8_t *p = src + (size_t)hi * pitch + min(col0 + 4 * wd, pitch - 4);
+    const size_t step = 2 * (size_t)pitch;
+#pragma unroll
+    for (int it = 0; it < (ROWS + 1) / 2; ++it) {
+        w[it] = 0;
+        if (lane < 24 && 2 * it + hi < ROWS) w[it] = __ldg(reinterpret_cast<const uint32_t *>(p));
+        p += step;
+    }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void stage_rows_store(uint32_t *ps, int lane, const uint32_t (&w)[(ROWS + 1) / 2])
+{
+#pragma unroll
+    for (int it = 0; it < (ROWS + 1) / 2; ++it)
+        if (lane < 24 && 24 * it + lane < ROWS * DP_WORDS) ps[24 * it + lane] = w[it];
+}
+
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// grid.x = describe CTAs of all levels (LevelGeom::desc_block_off): the level is CTA-uniform.
 __global__ void __launch_bounds__(256)
 describe_kernel(OrbGeom g, OrbBuffers b)
 {
-    __shared__ uint32_t patch_s[8][DP_ROWS * DP_WORDS];
+    __shared__ uint32_t blur_s[8][DP_ROWS * DP_WORDS];
+    __shared__ uint32_t orig_s[8][OP_ROWS * DP_WORDS];
     const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * 8 + warp;     // keypoint index within the frame
-    const int32_t *sc = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS;
-    int l = -1, first = 0, total = 0;
+    int l = 0;
 #pragma unroll
-    for (int i = 0; i < ORB_MAX_LEVELS; ++i) {
-        const int n = i < g.nbuilt ? sc[i] : 0;
-        if (l < 0 && slot < total + n) { l = i; first = total; }
-        total += n;
-    }
-    const size_t fslot = (size_t)frame + 1;    // output slot 0 is the tracker's carry
-    if (blockIdx.x == 0 && threadIdx.x == 0) b.counts[fslot] = min(total, g.kp_cap);
-    if (l < 0 || slot >= g.kp_cap) return;
-
+    for (int i = 1; i < ORB_MAX_LEVELS; ++i)
+        if (i < g.nbuilt && (int)blockIdx.x >= g.lv[i].desc_block_off) l = i;
     const LevelGeom L = g.lv[l];
-    const int si = L.sel_off + (slot - first);
+    const int32_t *sc = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS;
+    const size_t fslot = (size_t)frame + 1;     // output slot 0 is the tracker's carry
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int total = 0;
+        for (int i = 0; i < g.nbuilt; ++i) total += sc[i];
+        b.counts[fslot] = min(total, g.kp_cap);
+    }
+    const int k = ((int)blockIdx.x - L.desc_block_off) * 8 + warp;     // keypoint index within the level
+    if (k >= sc[l]) return;
+    int slot = k;                                                       // position in the frame: levels in order
+    for (int i = 0; i < l; ++i) slot += sc[i];
+    if (slot >= g.kp_cap) return;
+
+    const int si = L.sel_off + k;
     const uint32_t xy = b.sel_xy[(size_t)frame * g.kp_cap + si];
     const float resp = b.sel_resp[(size_t)frame * g.kp_cap + si];
     const int x = (int)(xy & 0xfffu), y = (int)(xy >> 12);
@@ -697,36 +771,33 @@ describe_kernel(OrbGeom g, OrbBuffers b)
 
     // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
     const float kx = __fmul_rn((float)x, L.sf), ky = __fmul_rn((float)y, L.sf);
-    const float inv = __fdiv_rn(1.f, L.sf);
-    const int xi = __float2int_rn(__fmul_rn(kx, inv)), yi = __float2int_rn(__fmul_rn(ky, inv));
+    const int xi = __float2int_rn(__fmul_rn(kx, L.inv_sf)), yi = __float2int_rn(__fmul_rn(ky, L.inv_sf));
 
-    // Stage the 39-row blurred patch with aligned 32-bit loads (15 per lane, coalesced per row); the
-    // loads are in flight while the orientation is computed.  Every sample of the rotated pattern lies
-    // within +-19 px of the centre (pattern radius < 18.4).
-    const int ax = (xi - 19) & ~3;
-    uint32_t pw[15];
+    // Both patches are fetched with aligned 32-bit loads into registers first (36 loads in flight), then
+    // parked in shared memory, so every later access has a compile-time row stride.
+    const int ax = (xi - 19) & ~3, ox = (x - 15) & ~3;
+    uint32_t ow[(OP_ROWS + 1) / 2], bw[(DP_ROWS + 1) / 2];
+    stage_rows_load<OP_ROWS>(img + (size_t)(y - 15) * L.pitch, L.pitch, ox, lane, ow);
+    stage_rows_load<DP_ROWS>(blr + (size_t)(yi - 19) * L.pitch, L.pitch, ax, lane, bw);
+    uint32_t *os = orig_s[warp], *ps = blur_s[warp];
+    stage_rows_store<OP_ROWS>(os, lane, ow);
+    stage_rows_store<DP_ROWS>(ps, lane, bw);
+    __syncwarp();
+
+    // ICAngles: m10 = sum u*I, m01 = sum v*I over the radius-15 disc.  Task t = row*9 + word takes 4 staged
+    // bytes; the table holds their column weights u*mask (s8), the mask itself and the row v, for the
+    // alignment shift of this keypoint: two DP4A per word.
+    int m10 = 0, m01 = 0;
+    {
+        const uint4 *tab = b.ori_tab + ((x - 15) & 3) * 288 + lane;
 #pragma unroll
-    for (int it = 0; it < 15; ++it) {
-        const int idx = min(lane + 32 * it, DP_ROWS * DP_WORDS - 1);
-        const int r = idx / DP_WORDS, w = idx - r * DP_WORDS;
-        pw[it] = __ldg(reinterpret_cast<const uint32_t *>(blr + (size_t)(yi - 19 + r) * L.pitch + min(ax + 4 * w, L.pitch - 4)));
-    }
-
-    // ICAngles: m10 = sum u*I, m01 = sum v*I over |u| <= umax[|v|].  Lane = column u; the disc is
-    // symmetric, so column u spans rows |v| <= umax[|u|]: m10 = u * (column sum), m01 = sum v*I.
-    const int u = lane - 15;
-    int colsum = 0, m01 = 0;
-    if (lane < 31) {
-        const int vmax = c_umax[u < 0 ? -u : u];
-        const uint8_t *c = img + (size_t)y * L.pitch + x + u;
-#pragma unroll 1
-        for (int v = -vmax; v <= vmax; ++v) {
-            const int val = __ldg(c + (ptrdiff_t)v * L.pitch);
-            colsum += val;
-            m01 += v * val;
+        for (int it = 0; it < 9; ++it) {
+            const uint4 e = __ldg(tab + it * 32);
+            const uint32_t px = os[e.w];
+            m10 = dp4a_u8_s8(px, e.x, m10);
+            m01 += (int)e.z * (int)__dp4a(px, e.y, 0u);
         }
     }
-    int m10 = u * colsum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -734,43 +805,45 @@ describe_kernel(OrbGeom g, OrbBuffers b)
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    uint32_t *ps = patch_s[warp];
-#pragma unroll
-    for (int it = 0; it < 15; ++it)
-        if (lane + 32 * it < DP_ROWS * DP_WORDS) ps[lane + 32 * it] = pw[it];
-    __syncwarp();
-
     const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     double sd, cd;
     sincos((double)ang, &sd, &cd);
     const float ca = (float)cd, sa = (float)sd;
-    // cvRound by the 1.5*2^23 trick: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v) for |v| < 2^22.
-    // The constant is folded into the patch offset: byte = (iy+19)*48 + (xi-ax) + ix.
-    const uint8_t *pb = reinterpret_cast<const uint8_t *>(ps);
-    const uint32_t fold = (uint32_t)(19 * DP_WORDS * 4 + (xi - ax)) - 0x4B400000u * (uint32_t)(DP_WORDS * 4 + 1);
+    // Rotation on packed f32x2 lanes (x in .x, y in .y):
+    //   (px*ca, px*sa) and (py*sa, py*ca) by FMUL2, then FFMA2 with (-1,+1) performs the exactly rounded
+    //   subtraction / addition of the two rounded products, as OpenCV's unfused expression does.
+    // cvRound by the 1.5*2^23 trick: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v); the constant
+    // is folded into the patch base: byte = (iy+19)*48 + (xi-ax) + ix.
+    const float2 AB = make_float2(ca, sa), BA = make_float2(sa, ca), SGN = make_float2(-1.f, 1.f);
+    const float2 MG = make_float2(12582912.0f, 12582912.0f);
+    const uint8_t *pb = reinterpret_cast<const uint8_t *>(ps) +
+                        ((uint32_t)(19 * DP_WORDS * 4 + (xi - ax)) - 0x4B400000u * (uint32_t)(DP_WORDS * 4 + 1));
     uint32_t byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 pt = __ldg(b.pattern + j * 32 + lane);      // (x0, y0, x1, y1) of comparison 8*lane + j
-        const uint32_t X0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, ca), __fmul_rn(pt.y, sa)), 12582912.0f));
-        const uint32_t Y0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, sa), __fmul_rn(pt.y, ca)), 12582912.0f));
-        const uint32_t X1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, ca), __fmul_rn(pt.w, sa)), 12582912.0f));
-        const uint32_t Y1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, sa), __fmul_rn(pt.w, ca)), 12582912.0f));
-        const int t0 = pb[Y0 * (uint32_t)(DP_WORDS * 4) + X0 + fold];
-        const int t1 = pb[Y1 * (uint32_t)(DP_WORDS * 4) + X1 + fold];
+        const float4 p0 = __ldg(b.pattern + (j * 32 + lane) * 2);         // (x0, x0, y0, y0) of comparison 8*lane + j
+        const float4 p1 = __ldg(b.pattern + (j * 32 + lane) * 2 + 1);     // (x1, x1, y1, y1)
+        const float2 r0 = __fadd2_rn(__ffma2_rn(__fmul2_rn(make_float2(p0.z, p0.w), BA), SGN, __fmul2_rn(make_float2(p0.x, p0.y), AB)), MG);
+        const float2 r1 = __fadd2_rn(__ffma2_rn(__fmul2_rn(make_float2(p1.z, p1.w), BA), SGN, __fmul2_rn(make_float2(p1.x, p1.y), AB)), MG);
+        const int t0 = pb[__float_as_uint(r0.y) * (uint32_t)(DP_WORDS * 4) + __float_as_uint(r0.x)];
+        const int t1 = pb[__float_as_uint(r1.y) * (uint32_t)(DP_WORDS * 4) + __float_as_uint(r1.x)];
         byte |= (uint32_t)(t0 < t1) << j;
     }
     b.desc[(fslot * g.kp_cap + slot) * 32 + lane] = (uint8_t)byte;
     if (lane == 0) {
-        aslam_keypoint k;
-        k.x = kx; k.y = ky; k.size = __fmul_rn(31.f, L.sf); k.angle = angle; k.response = resp; k.octave = l;
-        b.kps[fslot * g.kp_cap + slot] = k;
+        aslam_keypoint kp;
+        kp.x = kx; kp.y = ky; kp.size = L.kp_size; kp.angle = angle; kp.response = resp; kp.octave = l;
+        b.kps[fslot * g.kp_cap + slot] = kp;
     }
 }
 
 int launch_describe(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
 {
-    dim3 grid((g.kp_cap + 7) / 8, nframes);
+    if (g.desc_blocks_per_frame == 0) {
+        ASLAM_CUDA(cudaMemsetAsync(b.counts + 1, 0, sizeof(int32_t) * nframes, ctx->stream));
+        return ASLAM_OK;
+    }
+    dim3 grid(g.desc_blocks_per_frame, nframes);
     ProfScope ps(ctx, PK_DESCRIBE);
     describe_kernel<<<grid, 256, 0, ctx->stream>>>(g, b);
     ASLAM_LAUNCH_CHECK();
