@@ -154,13 +154,13 @@ def run_reference(args):
     val = per_step * args.steps / dt
     sample = "%d frames per step of the 256-frame batch; cv2 %s ORB+BFMatcher, %d threads, %s" % (
         per_step, __import__("cv2").__version__, cores, cpu_model())
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": per_step},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # ----------------------------------------------------------------------------------- our arm
@@ -222,7 +222,7 @@ def run_ours(args):
     cap = tr.capacity
 
     # ---- e2e: pinned host frames in, pinned results out, two independent streams interleaved
-    n_streams = 2
+    n_streams = 4
     half = BATCH // n_streams
     h_in = torch.from_numpy(frames).pin_memory()
     pipes = []
@@ -341,12 +341,30 @@ def run_ours(args):
     if world == 1:
         out["cpu_baseline"] = cpu_baseline_frames(frames)
         out["loop_query"]["cpu_baseline"] = cpu_baseline_loop(db, q)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries (NCCL prints its version banner there)
+    must not share it: fd 1 is pointed at stderr for the whole run, the result goes to the saved fd."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
