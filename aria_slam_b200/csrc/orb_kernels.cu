@@ -737,6 +737,34 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c)
     return d;
 }
 
+// sin and cos of a double in [0, 2*pi + eps] to < 1 ulp (double): quadrant reduction with a two-part
+// pi/2 (k <= 4, so k*PIO2_HI is exact) and the fdlibm kernel polynomials on [-pi/4, pi/4].  OpenCV
+// evaluates cos/sin in double and keeps the float cast; a sub-ulp double error changes that cast
+// only when the true value sits within ~1e-16 relative of a float rounding boundary.
+__device__ __forceinline__ void sincos_0_2pi(double t, double &s, double &c)
+{
+    const double k = rint(t * 0.63661977236758134308);            // 2/pi
+    double r = fma(-k, 1.57079632679489655800e+00, t);            // pi/2 high part
+    r = fma(-k, 6.12323399573676603587e-17, r);                   // pi/2 low part
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int q = (int)k & 3;
+    const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+    s = (q & 2) ? -s0 : s0;
+    c = ((q + 1) & 2) ? -c0 : c0;
+}
+
 // grid.x = describe CTAs of all levels (LevelGeom::desc_block_off): the level is CTA-uniform.
 __global__ void __launch_bounds__(256)
 describe_kernel(OrbGeom g, OrbBuffers b)
@@ -807,7 +835,7 @@ describe_kernel(OrbGeom g, OrbBuffers b)
 
     const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     double sd, cd;
-    sincos((double)ang, &sd, &cd);
+    sincos_0_2pi((double)ang, sd, cd);
     const float ca = (float)cd, sa = (float)sd;
     // Rotation on packed f32x2 lanes (x in .x, y in .y):
     //   (px*ca, px*sa) and (py*sa, py*ca) by FMUL2, then FFMA2 with (-1,+1) performs the exactly rounded
