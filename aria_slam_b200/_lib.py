@@ -81,6 +81,9 @@ SYMBOLS = {
     "aslam_loopdb_keyframes": (C.c_int, [_P, _P, _P]),
     "aslam_loopdb_query_segmented": (C.c_int, [_P, _P, C.c_int, C.c_double, _P]),
     "aslam_loopdb_query_global_device": (C.c_int, [_P, _P, C.c_int, _P]),
+    "aslam_loopdb_query_global_push_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int]),
+    "aslam_loopdb_query_global_exchange_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_uint64, _P]),
+    "aslam_loop_exchange_buffer_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "aslam_loopdb_query_global": (C.c_int, [_P, _P, C.c_int, _P]),
     "aslam_loop_merge_top2_device": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "aslam_microbench": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),

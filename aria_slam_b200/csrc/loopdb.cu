@@ -27,6 +27,7 @@ struct aslam_loopdb {
     uint2 *d_partial = nullptr; size_t partial_cap = 0;
     int32_t *d_good = nullptr; int32_t *h_good = nullptr; int good_cap = 0;
     uint64_t *d_top2 = nullptr; int top2_cap = 0;
+    unsigned int *d_arrival = nullptr;   // CTA arrival counter of the fused exchange kernel
 };
 
 static int db_reserve(aslam_loopdb *db, int nq, int nprobs, size_t partial_elems)
@@ -86,7 +87,7 @@ void aslam_loopdb_destroy(aslam_loopdb *db)
     cudaSetDevice(db->ctx->device);
     cudaStreamSynchronize(db->ctx->stream);
     cudaFree(db->d_rows); cudaFree(db->d_q); cudaFree(db->d_probs); cudaFree(db->d_partial);
-    cudaFree(db->d_good); cudaFree(db->d_top2);
+    cudaFree(db->d_good); cudaFree(db->d_top2); cudaFree(db->d_arrival);
     if (db->h_probs) cudaFreeHost(db->h_probs);
     if (db->h_good) cudaFreeHost(db->h_good);
     delete db;
@@ -198,28 +199,66 @@ int aslam_loopdb_query_segmented(aslam_loopdb *db, const uint8_t *q, int nq, dou
     return ASLAM_OK;
 }
 
+// Shared body of the flat query: scan this shard, then either write d_top2 or push to the peers.
+static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_t *d_top2,
+                           uint64_t *const *d_peer_bufs, int nparts, int my_part, uint64_t round = 0)
+{
+    aslam_ctx *ctx = db->ctx;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t rows = db->tail - db->head;
+    if (rows > KNN_MAX_ROWS) return fail(ASLAM_E_INVALID, "shard holds %lld rows; at most %d per shard", (long long)rows, KNN_MAX_ROWS);
+    const int q_stride = (int)align_up((size_t)nq, 64);
+    int splits = 0;
+    if (rows > 0) {
+        splits = choose_splits(ctx, nq, rows, 1);
+        int rc = db_reserve(db, 0, splits, (size_t)splits * q_stride);
+        if (rc) return rc;
+        rc = launch_fill_split_problems(ctx, db->d_probs, d_q, db->d_rows + db->head * 32, nullptr, nullptr, nq, (int)rows, splits);
+        if (rc) return rc;
+        rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride);
+        if (rc) return rc;
+    } else {
+        int rc = db_reserve(db, 0, 1, 1);       // an empty shard still reports (empty, empty) per query
+        if (rc) return rc;
+    }
+    if (d_peer_bufs && round) {
+        if (!db->d_arrival) {
+            ASLAM_CUDA(cudaMalloc(&db->d_arrival, sizeof(unsigned int)));
+            ASLAM_CUDA(cudaMemsetAsync(db->d_arrival, 0, sizeof(unsigned int), ctx->stream));
+        }
+        return launch_knn2_finish_exchange(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_peer_bufs, nparts,
+                                           my_part, round, db->d_arrival, d_top2);
+    }
+    if (d_peer_bufs)
+        return launch_knn2_finish_global_push(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_peer_bufs, nparts, my_part);
+    return launch_knn2_finish_global(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_top2);
+}
+
 int aslam_loopdb_query_global_device(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_t *d_top2)
 {
     ASLAM_REQUIRE(db && (nq == 0 || (d_q && d_top2)), "NULL argument");
     ASLAM_REQUIRE(nq >= 0, "negative nq");
     if (nq == 0) return ASLAM_OK;
-    aslam_ctx *ctx = db->ctx;
-    ASLAM_CUDA(cudaSetDevice(ctx->device));
-    const int64_t rows = db->tail - db->head;
-    if (rows > KNN_MAX_ROWS) return fail(ASLAM_E_INVALID, "shard holds %lld rows; at most %d per shard", (long long)rows, KNN_MAX_ROWS);
-    if (rows == 0) {
-        ASLAM_CUDA(cudaMemsetAsync(d_top2, 0xFF, sizeof(uint64_t) * 2 * (size_t)nq, ctx->stream));
-        return ASLAM_OK;
-    }
-    const int splits = choose_splits(ctx, nq, rows, 1);
-    const int q_stride = (int)align_up((size_t)nq, 64);
-    int rc = db_reserve(db, 0, splits, (size_t)splits * q_stride);
-    if (rc) return rc;
-    rc = launch_fill_split_problems(ctx, db->d_probs, d_q, db->d_rows + db->head * 32, nullptr, nullptr, nq, (int)rows, splits);
-    if (rc) return rc;
-    rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride);
-    if (rc) return rc;
-    return launch_knn2_finish_global(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_top2);
+    return db_query_global(db, d_q, nq, d_top2, nullptr, 0, 0);
+}
+
+int aslam_loopdb_query_global_push_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
+                                          uint64_t *const *d_peer_bufs, int nparts, int my_part)
+{
+    ASLAM_REQUIRE(db && (nq == 0 || (d_q && d_peer_bufs)), "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nparts >= 1 && my_part >= 0 && my_part < nparts, "bad sizes");
+    if (nq == 0) return ASLAM_OK;
+    return db_query_global(db, d_q, nq, nullptr, d_peer_bufs, nparts, my_part);
+}
+
+int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
+                                              uint64_t *const *d_peer_bufs, int nparts, int my_part,
+                                              uint64_t round, uint64_t *d_out)
+{
+    ASLAM_REQUIRE(db && (nq == 0 || (d_q && d_peer_bufs && d_out)), "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nparts >= 1 && my_part >= 0 && my_part < nparts && round >= 1, "bad sizes or round");
+    if (nq == 0) return ASLAM_OK;
+    return db_query_global(db, d_q, nq, d_out, d_peer_bufs, nparts, my_part, round);
 }
 
 int aslam_loopdb_query_global(aslam_loopdb *db, const uint8_t *q, int nq, uint64_t *top2)

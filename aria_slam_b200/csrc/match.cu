@@ -267,6 +267,89 @@ knn2_finish_global_kernel(const uint2 *__restrict__ partial, int nslots, int nq,
         : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
 }
 
+// Fused finish + all-gather: the merged keys of this shard go directly into every peer's gather buffer
+// with plain 16-byte stores to peer-mapped addresses (NVLink / NVSwitch); one thread = one query.
+__global__ void __launch_bounds__(FIN_THREADS)
+knn2_finish_global_push_kernel(const uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
+                               long long row_base, unsigned long long *const *__restrict__ peer_bufs,
+                               int nparts, int my_part)
+{
+    const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
+    for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
+    const unsigned long long e = ~0ull;
+    ulonglong2 v;
+    v.x = k1 == KEY_EMPTY ? e : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
+    v.y = k2 == KEY_EMPTY ? e : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
+    const size_t at = ((size_t)my_part * nq + q) * 2;
+    for (int p = 0; p < nparts; ++p)
+        *reinterpret_cast<ulonglong2 *>(peer_bufs[p] + at) = v;
+}
+
+// ---- one-kernel exchange: scan finish -> P2P stores -> release flags -> acquire peers' flags -> merge
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+knn2_finish_exchange_kernel(const uint2 *__restrict__ partial, int nslots, int nq, int q_stride, long long row_base,
+                            unsigned long long *const *__restrict__ peer_bufs, int nparts, int my_part,
+                            unsigned long long round, unsigned int *arrival, unsigned long long *__restrict__ out)
+{
+    const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
+    const int half = (int)(round & 1ull);
+    const size_t data_words = (size_t)2 * nparts * nq * 2;                    // per peer buffer, before the flags
+    const size_t slot = ((size_t)half * nparts + my_part) * nq;
+    // phase 1: this shard's top-2 per query into every peer's gather buffer (NVLink stores)
+    if (q < nq) {
+        uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
+        for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
+        const unsigned long long e = ~0ull;
+        ulonglong2 v;
+        v.x = k1 == KEY_EMPTY ? e : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
+        v.y = k2 == KEY_EMPTY ? e : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
+        for (int p = 0; p < nparts; ++p)
+            *reinterpret_cast<ulonglong2 *>(peer_bufs[p] + (slot + q) * 2) = v;
+    }
+    // publish: the last CTA to arrive raises this shard's flag on every peer
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(arrival, 1u);
+        if (prev == gridDim.x - 1) {
+            *arrival = 0;                         // ready for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int p = 0; p < nparts; ++p)
+                st_release_sys(peer_bufs[p] + data_words + (size_t)half * nparts + my_part, round);
+        }
+    }
+    // phase 2: wait for every shard of this round, then merge this CTA's queries from the LOCAL buffer
+    unsigned long long *mine = peer_bufs[my_part];
+    if (threadIdx.x < nparts) {
+        const unsigned long long *f = mine + data_words + (size_t)half * nparts + threadIdx.x;
+        while (ld_acquire_sys(f) < round) __nanosleep(64);
+    }
+    __syncthreads();
+    if (q >= nq) return;
+    unsigned long long k1 = ~0ull, k2 = ~0ull;
+    for (int p = 0; p < nparts; ++p) {
+        const ulonglong2 ab = __ldcg(reinterpret_cast<const ulonglong2 *>(mine + (((size_t)half * nparts + p) * nq + q) * 2));
+        const unsigned long long n2 = min(max(k1, ab.x), min(k2, ab.y));
+        k1 = min(k1, ab.x);
+        k2 = n2;
+    }
+    out[2 * (size_t)q] = k1;
+    out[2 * (size_t)q + 1] = k2;
+}
+
 // Merge of all-gathered shard results: parts[nparts][nq][2] packed 64-bit keys.
 __global__ void __launch_bounds__(FIN_THREADS)
 merge_top2_kernel(const unsigned long long *__restrict__ parts, int nparts, int nq,
@@ -359,6 +442,32 @@ int launch_knn2_finish_global(aslam_ctx *ctx, const uint2 *d_partial, int nslots
     ProfScope ps(ctx, PK_KNN_FINISH);
     knn2_finish_global_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
         d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *)d_top2);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_finish_global_push(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
+                                   int q_stride, int64_t row_base, uint64_t *const *d_peer_bufs,
+                                   int nparts, int my_part)
+{
+    if (nq <= 0) return ASLAM_OK;
+    ProfScope ps(ctx, PK_KNN_FINISH);
+    knn2_finish_global_push_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
+        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_finish_exchange(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq, int q_stride,
+                                int64_t row_base, uint64_t *const *d_peer_bufs, int nparts, int my_part,
+                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out)
+{
+    if (nq <= 0) return ASLAM_OK;
+    if (nparts > FIN_THREADS) return fail(ASLAM_E_INVALID, "at most %d shards", FIN_THREADS);
+    ProfScope ps(ctx, PK_MERGE);
+    knn2_finish_exchange_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
+        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part,
+        (unsigned long long)round, d_arrival, (unsigned long long *)d_out);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
@@ -528,6 +637,11 @@ extern "C" int aslam_match_multi(aslam_ctx *ctx, const uint8_t *q, int nq, const
     ASLAM_CUDA(cudaMemcpyAsync(out, base + o_match, sizeof(aslam_match) * (size_t)nsets * nq, cudaMemcpyDeviceToHost, ctx->stream));
     ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
     return ASLAM_OK;
+}
+
+extern "C" size_t aslam_loop_exchange_buffer_bytes(int nparts, int nq)
+{
+    return sizeof(uint64_t) * ((size_t)2 * nparts * nq * 2 + (size_t)2 * nparts);
 }
 
 extern "C" int aslam_loop_merge_top2_device(aslam_ctx *ctx, const uint64_t *d_parts, int nparts, int nq, uint64_t *d_out)

@@ -59,4 +59,15 @@ int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const u
 int launch_knn2_finish_global(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
                               int q_stride, int64_t row_base, uint64_t *d_top2);
 
+// As launch_knn2_finish_global, with the result stored into slot `my_part` of every peer's
+// [nparts][nq][2] buffer (peer-mapped pointers in device memory): the all-gather is the epilogue.
+int launch_knn2_finish_global_push(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
+                                   int q_stride, int64_t row_base, uint64_t *const *d_peer_bufs,
+                                   int nparts, int my_part);
+
+// Fused finish + push + flag exchange + merge (see aslam_loopdb_query_global_exchange_device).
+int launch_knn2_finish_exchange(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq, int q_stride,
+                                int64_t row_base, uint64_t *const *d_peer_bufs, int nparts, int my_part,
+                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out);
+
 }  // namespace aslam

@@ -241,6 +241,13 @@ class LoopDB:
     def query_global_device(self, d_q, nq, d_top2):
         check(lib().aslam_loopdb_query_global_device(self.h, ptr(d_q), int(nq), ptr(d_top2)))
 
+    def query_global_push_device(self, d_q, nq, d_peer_ptrs, nparts, my_part):
+        check(lib().aslam_loopdb_query_global_push_device(self.h, ptr(d_q), int(nq), ptr(d_peer_ptrs), int(nparts), int(my_part)))
+
+    def query_global_exchange_device(self, d_q, nq, d_peer_ptrs, nparts, my_part, round_, d_out):
+        check(lib().aslam_loopdb_query_global_exchange_device(self.h, ptr(d_q), int(nq), ptr(d_peer_ptrs), int(nparts),
+                                                              int(my_part), int(round_), ptr(d_out)))
+
     def close(self):
         if self.h:
             lib().aslam_loopdb_destroy(self.h)

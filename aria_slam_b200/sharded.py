@@ -50,9 +50,16 @@ def all_gather_top2(local, world):
 
 
 class ShardedLoopQuery:
-    """This rank's shard of a flat descriptor database + the collective query."""
+    """This rank's shard of a flat descriptor database + the collective query.
 
-    def __init__(self, ctx, db_rows, rank, world, keyframe_rows=2000):
+    exchange = "fused": ONE kernel after the shard scan finishes it, stores the keys into every peer's
+    buffer over NVLink (buffers from torch's symmetric memory), raises a release flag, acquires the
+    peers' flags and merges -- no collective call and no separate barrier.
+    exchange = "push": the same stores, but symmetric-memory barriers and a separate merge kernel.
+    exchange = "nccl": NCCL all_gather_into_tensor + merge kernel.  "auto" tries fused, then nccl.
+    """
+
+    def __init__(self, ctx, db_rows, rank, world, keyframe_rows=2000, exchange="auto"):
         import torch
         from .frontend import LoopDB
         self.ctx, self.rank, self.world = ctx, rank, world
@@ -65,18 +72,60 @@ class ShardedLoopQuery:
         self.db.set_row_base(self.row_lo)
         self._torch = torch
         self._local = self._out = None
+        self._symm = None
+        self.exchange = "none" if world == 1 else exchange
+        self._nq = 0
+
+    def _setup_push(self, nq, device):
+        """Symmetric [world, nq, 2] gather buffer on every rank + the table of peer pointers."""
+        torch = self._torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._lib import lib
+        words = lib().aslam_loop_exchange_buffer_bytes(self.world, nq) // 8     # data[2][world][nq][2] + flags[2][world]
+        buf = symm_mem.empty((words,), dtype=torch.int64, device=device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+        ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize()
+        dist.barrier()                      # every rank's flags are zero before anyone starts round 1
+        self._symm = (buf, hdl, ptrs)
+        self._round = 0
 
     def query(self, d_q, nq):
         """d_q: device tensor [nq, 32] u8 (replicated).  Returns a device int64 tensor [nq, 2] of packed
         keys, identical on every rank.  Runs on the current torch stream == the context's stream."""
         torch = self._torch
         from ._lib import lib, check, ptr
-        if self._local is None or self._local.shape[0] != nq:
+        if self._local is None or self._nq != nq:
             self._local = torch.empty((nq, 2), dtype=torch.int64, device=d_q.device)
             self._out = torch.empty((nq, 2), dtype=torch.int64, device=d_q.device)
-        self.db.query_global_device(d_q, nq, self._local)
+            self._nq = nq
+            if self.exchange in ("auto", "push", "fused"):
+                try:
+                    self._setup_push(nq, d_q.device)
+                    if self.exchange == "auto":
+                        self.exchange = "fused"
+                except Exception:
+                    if self.exchange != "auto":
+                        raise
+                    self.exchange = "nccl"
         if self.world == 1:
+            self.db.query_global_device(d_q, nq, self._local)
             return self._local
-        parts = all_gather_top2(self._local, self.world)
+        if self.exchange == "fused":
+            buf, hdl, ptrs = self._symm
+            self._round += 1
+            self.db.query_global_exchange_device(d_q, nq, ptrs, self.world, self.rank, self._round, self._out)
+            return self._out
+        if self.exchange == "push":
+            buf, hdl, ptrs = self._symm
+            hdl.barrier(channel=0)          # every rank has consumed the previous round's buffer
+            self.db.query_global_push_device(d_q, nq, ptrs, self.world, self.rank)
+            hdl.barrier(channel=1)          # every shard has landed in every buffer
+            parts = buf[:self.world * nq * 2].view(self.world, nq, 2)
+        else:
+            self.db.query_global_device(d_q, nq, self._local)
+            parts = all_gather_top2(self._local, self.world)
         check(lib().aslam_loop_merge_top2_device(self.ctx.h, ptr(parts), self.world, nq, ptr(self._out)))
         return self._out

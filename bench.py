@@ -333,7 +333,11 @@ def run_ours(args):
         "checks": checks,
         "loop_query": {"metric": "loop_query_descriptors_per_s", "value": loop_val, "unit": "query-descriptors/s", "db_rows": LOOP_DB_ROWS,
                        "queries": LOOP_NQ, "n_gpus": world, "scaling": "strong", "ms_per_query_batch": loop_ms / K,
-                       "collective": "none (1 GPU)" if world == 1 else "NCCL all_gather of 2000x2 packed (dist,row) keys per rank + merge kernel",
+                       "collective": {"none": "none (1 GPU)",
+                                      "fused": "one kernel: scan finish + P2P stores of 2000x2 packed (dist,row) keys into every peer's buffer over NVLink + release/acquire flags + merge (no NCCL call)",
+                                      "push": "P2P stores from the finish kernel + symmetric-memory barriers + merge kernel",
+                                      "nccl": "NCCL all_gather of 2000x2 packed (dist,row) keys per rank + merge kernel"}[lq.exchange],
+                       "exchange": lq.exchange,
                        "best_row_is_source_row": loop_ok, "gpu_launches": int(loop_launches),
                        "stages_ms": {k: v[0] / K for k, v in loop_prof.items() if v[1]},
                        "pairs_per_s": LOOP_NQ * float(LOOP_DB_ROWS) * K / (loop_ms * 1e-3)},

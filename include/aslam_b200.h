@@ -222,6 +222,24 @@ ASLAM_API int aslam_loopdb_query_segmented(aslam_loopdb *db, const uint8_t *q, i
  * device pointers (top2[nq][2]); asynchronous on the context's stream. */
 ASLAM_API int aslam_loopdb_query_global_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
                                                uint64_t *d_top2);
+/* Fused shard scan + all-gather: as aslam_loopdb_query_global_device, but the kernel that finishes the
+ * scan stores this shard's keys straight into slot `my_part` of EVERY peer's gather buffer
+ * (d_peer_bufs[p] = device pointer of rank p's [nparts][nq][2] buffer, peer-mapped over NVLink; the
+ * array itself lives in device memory).  No collective call is needed afterwards, only a barrier
+ * before aslam_loop_merge_top2_device reads the local buffer.  Asynchronous on the context's stream. */
+ASLAM_API int aslam_loopdb_query_global_push_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
+                                                    uint64_t *const *d_peer_bufs, int nparts, int my_part);
+/* The whole exchange in ONE kernel after the shard scan (no collective call, no separate barrier):
+ * finish the scan, store the keys into every peer's buffer, publish a per-shard flag with release
+ * semantics, wait (acquire) for all peers' flags of this round, merge, write d_out[nq][2].
+ * Every peer buffer (peer-mapped, e.g. torch symmetric memory) is laid out as
+ *     uint64 data[2][nparts][nq][2];  uint64 flags[2][nparts];        (zeroed before round 1)
+ * `round` = 1, 2, 3, ... identical on all ranks; rounds alternate between the two halves.  Every rank
+ * must call this once per round, each on its own GPU. */
+ASLAM_API int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
+                                                        uint64_t *const *d_peer_bufs, int nparts, int my_part,
+                                                        uint64_t round, uint64_t *d_out);
+ASLAM_API size_t aslam_loop_exchange_buffer_bytes(int nparts, int nq);
 /* Host-buffer form of the flat query (copies in and out, synchronous). */
 ASLAM_API int aslam_loopdb_query_global(aslam_loopdb *db, const uint8_t *q, int nq, uint64_t *top2);
 /* Merge step after the all-gather of shard results: d_parts[nparts][nq][2] packed keys ->
