@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaslam_b200.so")
+LIB_PATH = os.environ.get("ASLAM_B200_LIB") or os.path.join(_HERE, "libaslam_b200.so")     # env override: A/B builds
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_OVERFLOW, E_NODEVICE = range(7)
 

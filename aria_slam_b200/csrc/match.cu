@@ -68,6 +68,19 @@ __device__ __forceinline__ uint32_t hamming256_parity(const uint32_t (&q)[8], co
     return __popc(s2) + __popc(x7) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
 }
 
+// CSA 6: as CSA 5 plus a fourth adder over the three carries: 13 logic ops + 4 POPC per pair.
+__device__ __forceinline__ uint32_t hamming256_parity4(const uint32_t (&q)[8], const QueryParity qp, const uint4 a, const uint4 b,
+                                                      uint32_t ta, uint32_t tb, uint32_t tc)
+{
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, s0 = qp.a ^ ta, c0 = carry_from_sum(x0, x1, s0);
+    const uint32_t x3 = q[3] ^ a.w, x4 = q[4] ^ b.x, s1 = qp.b ^ tb, c1 = carry_from_sum(x3, x4, s1);
+    const uint32_t s2 = qp.c ^ tc, c2 = carry_from_sum(s0, s1, s2);
+    const uint32_t x7 = q[7] ^ b.w;
+    uint32_t s3, c3;
+    csa(c0, c1, c2, s3, c3);
+    return __popc(s2) + __popc(x7) + 2u * __popc(s3) + 4u * __popc(c3);
+}
+
 template <int CSA>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride)
@@ -133,7 +146,8 @@ knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ pa
 #pragma unroll
             for (int j = 0; j < KNN_RQ; ++j) {
                 const uint32_t d = CSA == 5 ? hamming256_parity(qd[j], qp[j], a, b, ta, tbp, tc)
-                                            : hamming256<CSA>(qd[j], a, b);
+                                   : CSA == 6 ? hamming256_parity4(qd[j], qp[j], a, b, ta, tbp, tc)
+                                              : hamming256<CSA>(qd[j], a, b);
                 const uint32_t key = (d << KEY_IDX_BITS) + keybase;
                 b2[j] = min(b2[j], max(b1[j], key));
                 b1[j] = min(b1[j], key);
@@ -406,6 +420,7 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
     case 3: knn2_partial_kernel<3><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     case 4: knn2_partial_kernel<4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     case 5: knn2_partial_kernel<5><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    case 6: knn2_partial_kernel<6><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     default: knn2_partial_kernel<2><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     }
     ASLAM_LAUNCH_CHECK();

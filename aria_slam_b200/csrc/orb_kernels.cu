@@ -127,7 +127,10 @@ __device__ __forceinline__ uint32_t ring_pair(const uint16_t (*A)[FA_PITCH], con
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
-__global__ void __launch_bounds__(256)
+#ifndef ASLAM_FAST_MINB
+#define ASLAM_FAST_MINB 5
+#endif
+__global__ void __launch_bounds__(256, ASLAM_FAST_MINB)
 fast_kernel(OrbGeom g, OrbBuffers b)
 {
     __shared__ __align__(16) uint16_t A[FT_PIX_H][FA_PITCH];
@@ -311,7 +314,10 @@ __device__ __forceinline__ uint32_t u8_magic(uint32_t word, int k)
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
-__global__ void __launch_bounds__(256)
+#ifndef ASLAM_BLUR_MINB
+#define ASLAM_BLUR_MINB 4
+#endif
+__global__ void __launch_bounds__(256, ASLAM_BLUR_MINB)
 blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
 {
     __shared__ __align__(16) float R[BL_ROWS][BL_W];
