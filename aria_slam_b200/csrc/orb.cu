@@ -22,7 +22,7 @@ struct aslam_orb {
     OrbBuffers b{};
     uint32_t *d_tabs = nullptr;
     float4 *d_pattern = nullptr;
-    uint4 *d_ori_tab = nullptr;
+    uint2 *d_ori_tab = nullptr;
     // tracking
     aslam_match *d_matches = nullptr;      // [B][kp_cap]
     int32_t *d_match_counts = nullptr;     // [B]
@@ -151,33 +151,26 @@ int aslam_orb_create(aslam_ctx *ctx, const aslam_orb_params *p, int width, int h
     ASLAM_CUDA(cudaSetDevice(ctx->device));
     aslam_orb *o = new aslam_orb();
     o->ctx = ctx; o->prm = *p; o->width = width; o->height = height; o->max_batch = max_batch;
-    // entry (j*32 + k)*2 + e = point e of comparison 8*k + j as (x, x, y, y): coalesced per j, and each
-    // half is an aligned register pair for the packed f32x2 rotation
-    static float4 packed[512];
+    // entry j*32 + k = comparison 8*k + j as (x0, y0, x1, y1): one coalesced 16-byte load per j per warp
+    static float4 packed[256];
     for (int i = 0; i < 256; ++i)
-        for (int e = 0; e < 2; ++e)
-            packed[((i & 7) * 32 + (i >> 3)) * 2 + e] = make_float4((float)k_brief_pattern[i][2 * e], (float)k_brief_pattern[i][2 * e],
-                                                                    (float)k_brief_pattern[i][2 * e + 1], (float)k_brief_pattern[i][2 * e + 1]);
+        packed[(i & 7) * 32 + (i >> 3)] = make_float4((float)k_brief_pattern[i][0], (float)k_brief_pattern[i][1],
+                                                      (float)k_brief_pattern[i][2], (float)k_brief_pattern[i][3]);
     cudaError_t e = cudaMalloc(&o->d_pattern, sizeof(packed));
     if (e == cudaSuccess) e = cudaMemcpy(o->d_pattern, packed, sizeof(packed), cudaMemcpyHostToDevice);
-    // Orientation weights (ICAngles disc, radius 15): the 31x31 patch is staged as rows of 12 aligned words;
-    // task t = row*9 + word handles 4 bytes whose column is u = 4*word + byte - shift - 15.
-    static uint4 ori[4 * 288];
+    // Orientation weights (ICAngles disc, radius 15) of the patch-aligned word (row, word): byte bt is column
+    // u = 4*word + bt - 15 of row v = row - 15; entry it*32 + lane <-> row 4*it + lane/8, word lane%8.
+    static uint2 ori[8 * 32];
     static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    for (int sh = 0; sh < 4; ++sh)
-        for (int t = 0; t < 288; ++t) {
-            uint4 ent = make_uint4(0, 0, 0, 0);
-            if (t < 31 * 9) {
-                const int row = t / 9, word = t % 9, v = row - 15;
-                uint32_t wu = 0, wm = 0;
-                for (int bt = 0; bt < 4; ++bt) {
-                    const int u = 4 * word + bt - sh - 15;
-                    const bool in = u >= -15 && u <= 15 && (u < 0 ? -u : u) <= umax[v < 0 ? -v : v];
-                    if (in) { wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * bt); wm |= 1u << (8 * bt); }
-                }
-                ent = make_uint4(wu, wm, (uint32_t)v, (uint32_t)(row * 12 + word));
+    for (int it = 0; it < 8; ++it)
+        for (int ln = 0; ln < 32; ++ln) {
+            const int row = 4 * it + (ln >> 3), word = ln & 7, v = row - 15;
+            uint32_t wu = 0, wm = 0;
+            for (int bt = 0; bt < 4 && row < 31; ++bt) {
+                const int u = 4 * word + bt - 15;
+                if (u <= 15 && (u < 0 ? -u : u) <= umax[v < 0 ? -v : v]) { wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * bt); wm |= 1u << (8 * bt); }
             }
-            ori[sh * 288 + t] = ent;
+            ori[it * 32 + ln] = make_uint2(wu, wm);
         }
     if (e == cudaSuccess) e = cudaMalloc(&o->d_ori_tab, sizeof(ori));
     if (e == cudaSuccess) e = cudaMemcpy(o->d_ori_tab, ori, sizeof(ori), cudaMemcpyHostToDevice);

@@ -25,7 +25,7 @@ struct LevelGeom {
     int blur_tile_off;       // first 128x58 blur tile of this level within the frame
     int quota;               // N_l
     int sel_off, sel_cap;    // rows of this level in the per-frame selection buffer
-    int desc_block_off;      // first describe CTA (8 keypoints each) of this level within the frame
+    int desc_block_off;      // first describe CTA (64 keypoints each) of this level within the frame
     int xtab_off, ytab_off;  // resize tables (level l-1 -> l), in uint32 entries
     int row_fused_end;       // blur: row-pass columns below this use fused multiply-add
     int col_fused_end;

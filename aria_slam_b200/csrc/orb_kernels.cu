@@ -711,6 +711,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 constexpr int DP_ROWS = 39, DP_WORDS = 12;      // blurred patch: +-19 rows of 12 aligned words
 constexpr int OP_ROWS = 31;                     // unblurred patch for the moments: +-15 rows, same row format
+constexpr int DESC_KPW = 8;                     // keypoints per warp (the per-lane tables live in registers)
 
 // Stage `rows` rows of 12 aligned words starting at `src` (row 0, word 0) into smem: lanes 0..23 take two
 // rows per step, one 64-bit pointer bump per step, stores at compile-time offsets.
@@ -771,12 +772,15 @@ __device__ __forceinline__ void sincos_0_2pi(double t, double &s, double &c)
     c = ((q + 1) & 2) ? -c0 : c0;
 }
 
-// grid.x = describe CTAs of all levels (LevelGeom::desc_block_off): the level is CTA-uniform.
+// grid.x = describe CTAs of all levels (LevelGeom::desc_block_off): the level is CTA-uniform.  A warp
+// handles DESC_KPW keypoints one after another, so its per-lane constants are fetched once and stay
+// in registers: the 8 rBRIEF comparisons of lane k (bits of descriptor byte k) as (x,y) float pairs,
+// and the orientation weights of the lane's 8 patch words.
 __global__ void __launch_bounds__(256)
 describe_kernel(OrbGeom g, OrbBuffers b)
 {
     __shared__ uint32_t blur_s[8][DP_ROWS * DP_WORDS];
-    __shared__ uint32_t orig_s[8][OP_ROWS * DP_WORDS];
+    __shared__ uint32_t orig_s[8][(OP_ROWS + 1) * DP_WORDS];      // +1 row: the lanes of row 31 read (weight 0)
     const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l = 0;
 #pragma unroll
@@ -790,84 +794,106 @@ describe_kernel(OrbGeom g, OrbBuffers b)
         for (int i = 0; i < g.nbuilt; ++i) total += sc[i];
         b.counts[fslot] = min(total, g.kp_cap);
     }
-    const int k = ((int)blockIdx.x - L.desc_block_off) * 8 + warp;     // keypoint index within the level
-    if (k >= sc[l]) return;
-    int slot = k;                                                       // position in the frame: levels in order
-    for (int i = 0; i < l; ++i) slot += sc[i];
-    if (slot >= g.kp_cap) return;
+    const int cnt = sc[l];
+    const int k0 = (((int)blockIdx.x - L.desc_block_off) * 8 + warp) * DESC_KPW;
+    if (k0 >= cnt) return;
+    int level_base = 0;                         // position of the level's first keypoint in the frame
+    for (int i = 0; i < l; ++i) level_base += sc[i];
 
-    const int si = L.sel_off + k;
-    const uint32_t xy = b.sel_xy[(size_t)frame * g.kp_cap + si];
-    const float resp = b.sel_resp[(size_t)frame * g.kp_cap + si];
-    const int x = (int)(xy & 0xfffu), y = (int)(xy >> 12);
-    const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
-    const uint8_t *blr = b.blur + (size_t)frame * g.pyr_stride + L.off;
-
-    // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
-    const float kx = __fmul_rn((float)x, L.sf), ky = __fmul_rn((float)y, L.sf);
-    const int xi = __float2int_rn(__fmul_rn(kx, L.inv_sf)), yi = __float2int_rn(__fmul_rn(ky, L.inv_sf));
-
-    // Both patches are fetched with aligned 32-bit loads into registers first (36 loads in flight), then
-    // parked in shared memory, so every later access has a compile-time row stride.
-    const int ax = (xi - 19) & ~3, ox = (x - 15) & ~3;
-    uint32_t ow[(OP_ROWS + 1) / 2], bw[(DP_ROWS + 1) / 2];
-    stage_rows_load<OP_ROWS>(img + (size_t)(y - 15) * L.pitch, L.pitch, ox, lane, ow);
-    stage_rows_load<DP_ROWS>(blr + (size_t)(yi - 19) * L.pitch, L.pitch, ax, lane, bw);
-    uint32_t *os = orig_s[warp], *ps = blur_s[warp];
-    stage_rows_store<OP_ROWS>(os, lane, ow);
-    stage_rows_store<DP_ROWS>(ps, lane, bw);
-    __syncwarp();
-
-    // ICAngles: m10 = sum u*I, m01 = sum v*I over the radius-15 disc.  Task t = row*9 + word takes 4 staged
-    // bytes; the table holds their column weights u*mask (s8), the mask itself and the row v, for the
-    // alignment shift of this keypoint: two DP4A per word.
-    int m10 = 0, m01 = 0;
-    {
-        const uint4 *tab = b.ori_tab + ((x - 15) & 3) * 288 + lane;
-#pragma unroll
-        for (int it = 0; it < 9; ++it) {
-            const uint4 e = __ldg(tab + it * 32);
-            const uint32_t px = os[e.w];
-            m10 = dp4a_u8_s8(px, e.x, m10);
-            m01 += (int)e.z * (int)__dp4a(px, e.y, 0u);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-    double sd, cd;
-    sincos_0_2pi((double)ang, sd, cd);
-    const float ca = (float)cd, sa = (float)sd;
-    // Rotation on packed f32x2 lanes (x in .x, y in .y):
-    //   (px*ca, px*sa) and (py*sa, py*ca) by FMUL2, then FFMA2 with (-1,+1) performs the exactly rounded
-    //   subtraction / addition of the two rounded products, as OpenCV's unfused expression does.
-    // cvRound by the 1.5*2^23 trick: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v); the constant
-    // is folded into the patch base: byte = (iy+19)*48 + (xi-ax) + ix.
-    const float2 AB = make_float2(ca, sa), BA = make_float2(sa, ca), SGN = make_float2(-1.f, 1.f);
-    const float2 MG = make_float2(12582912.0f, 12582912.0f);
-    const uint8_t *pb = reinterpret_cast<const uint8_t *>(ps) +
-                        ((uint32_t)(19 * DP_WORDS * 4 + (xi - ax)) - 0x4B400000u * (uint32_t)(DP_WORDS * 4 + 1));
-    uint32_t byte = 0;
+    // per-lane constants
+    float2 P0[8], P1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 p0 = __ldg(b.pattern + (j * 32 + lane) * 2);         // (x0, x0, y0, y0) of comparison 8*lane + j
-        const float4 p1 = __ldg(b.pattern + (j * 32 + lane) * 2 + 1);     // (x1, x1, y1, y1)
-        const float2 r0 = __fadd2_rn(__ffma2_rn(__fmul2_rn(make_float2(p0.z, p0.w), BA), SGN, __fmul2_rn(make_float2(p0.x, p0.y), AB)), MG);
-        const float2 r1 = __fadd2_rn(__ffma2_rn(__fmul2_rn(make_float2(p1.z, p1.w), BA), SGN, __fmul2_rn(make_float2(p1.x, p1.y), AB)), MG);
-        const int t0 = pb[__float_as_uint(r0.y) * (uint32_t)(DP_WORDS * 4) + __float_as_uint(r0.x)];
-        const int t1 = pb[__float_as_uint(r1.y) * (uint32_t)(DP_WORDS * 4) + __float_as_uint(r1.x)];
-        byte |= (uint32_t)(t0 < t1) << j;
+        const float4 pt = __ldg(b.pattern + j * 32 + lane);        // (x0, y0, x1, y1) of comparison 8*lane + j
+        P0[j] = make_float2(pt.x, pt.y);
+        P1[j] = make_float2(pt.z, pt.w);
     }
-    b.desc[(fslot * g.kp_cap + slot) * 32 + lane] = (uint8_t)byte;
-    if (lane == 0) {
-        aslam_keypoint kp;
-        kp.x = kx; kp.y = ky; kp.size = L.kp_size; kp.angle = angle; kp.response = resp; kp.octave = l;
-        b.kps[fslot * g.kp_cap + slot] = kp;
+    uint2 OW[8];                                                   // (u*mask as s8x4, mask as u8x4) of patch word (row 4*it + lane/8, lane%8)
+#pragma unroll
+    for (int it = 0; it < 8; ++it) OW[it] = __ldg(b.ori_tab + it * 32 + lane);
+    const int vl = (lane >> 3) - 15;
+
+    const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
+    const uint8_t *blr = b.blur + (size_t)frame * g.pyr_stride + L.off;
+    uint32_t *os = orig_s[warp], *ps = blur_s[warp];
+
+#pragma unroll 1
+    for (int kk = 0; kk < DESC_KPW; ++kk) {
+        const int k = k0 + kk;
+        if (k >= cnt) break;
+        const int slot = level_base + k;
+        if (slot >= g.kp_cap) break;
+        const int si = L.sel_off + k;
+        const uint32_t xy = b.sel_xy[(size_t)frame * g.kp_cap + si];
+        const float resp = b.sel_resp[(size_t)frame * g.kp_cap + si];
+        const int x = (int)(xy & 0xfffu), y = (int)(xy >> 12);
+
+        // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
+        const float kx = __fmul_rn((float)x, L.sf), ky = __fmul_rn((float)y, L.sf);
+        const int xi = __float2int_rn(__fmul_rn(kx, L.inv_sf)), yi = __float2int_rn(__fmul_rn(ky, L.inv_sf));
+
+        // Both patches are fetched with aligned 32-bit loads into registers (36 in flight), then parked in
+        // shared memory, so every later access has a compile-time row stride.
+        const int ax = (xi - 19) & ~3, ox = (x - 15) & ~3;
+        {
+            uint32_t ow[(OP_ROWS + 1) / 2], bw[(DP_ROWS + 1) / 2];
+            stage_rows_load<OP_ROWS>(img + (size_t)(y - 15) * L.pitch, L.pitch, ox, lane, ow);
+            stage_rows_load<DP_ROWS>(blr + (size_t)(yi - 19) * L.pitch, L.pitch, ax, lane, bw);
+            __syncwarp();                       // the previous keypoint's reads are done
+            stage_rows_store<OP_ROWS>(os, lane, ow);
+            stage_rows_store<DP_ROWS>(ps, lane, bw);
+        }
+        __syncwarp();
+
+        // ICAngles: m10 = sum u*I, m01 = sum v*I over the radius-15 disc.  The lane's word of row
+        // 4*it + lane/8 is re-aligned to the patch (funnel shift of two staged words), so its column
+        // weights do not depend on the keypoint: two DP4A per word.
+        int m10 = 0, m01 = 0;
+        {
+            const uint32_t sh = (uint32_t)((x - 15) & 3) * 8u;
+            const uint32_t *row = os + (lane >> 3) * DP_WORDS + (lane & 7);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const uint32_t px = __funnelshift_r(row[it * 4 * DP_WORDS], row[it * 4 * DP_WORDS + 1], sh);
+                m10 = dp4a_u8_s8(px, OW[it].x, m10);
+                m01 += (vl + 4 * it) * (int)__dp4a(px, OW[it].y, 0u);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+        double sd, cd;
+        sincos_0_2pi((double)ang, sd, cd);
+        const float ca = (float)cd, sa = (float)sd;
+        // Rotation: (px*ca, py*ca) and (px*sa, py*sa) by FMUL2, then the two exactly rounded sums
+        //   X = px*ca - py*sa,  Y = px*sa + py*ca   as OpenCV's unfused expression evaluates them.
+        // cvRound by the 1.5*2^23 trick: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v); the constant
+        // is folded into the patch base: byte = (iy+19)*48 + (xi-ax) + ix.
+        const float2 CC = make_float2(ca, ca), SS = make_float2(sa, sa), MG = make_float2(12582912.0f, 12582912.0f);
+        const uint8_t *pb = reinterpret_cast<const uint8_t *>(ps) +
+                            ((uint32_t)(19 * DP_WORDS * 4 + (xi - ax)) - 0x4B400000u * (uint32_t)(DP_WORDS * 4 + 1));
+        uint32_t byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 a1 = __fmul2_rn(P0[j], CC), a2 = __fmul2_rn(P0[j], SS);
+            const float2 c1 = __fmul2_rn(P1[j], CC), c2 = __fmul2_rn(P1[j], SS);
+            const float2 r0 = __fadd2_rn(make_float2(__fsub_rn(a1.x, a2.y), __fadd_rn(a2.x, a1.y)), MG);
+            const float2 r1 = __fadd2_rn(make_float2(__fsub_rn(c1.x, c2.y), __fadd_rn(c2.x, c1.y)), MG);
+            const int t0 = pb[__float_as_uint(r0.y) * (uint32_t)(DP_WORDS * 4) + __float_as_uint(r0.x)];
+            const int t1 = pb[__float_as_uint(r1.y) * (uint32_t)(DP_WORDS * 4) + __float_as_uint(r1.x)];
+            byte |= (uint32_t)(t0 < t1) << j;
+        }
+        b.desc[(fslot * g.kp_cap + slot) * 32 + lane] = (uint8_t)byte;
+        if (lane == 0) {
+            aslam_keypoint kp;
+            kp.x = kx; kp.y = ky; kp.size = L.kp_size; kp.angle = angle; kp.response = resp; kp.octave = l;
+            b.kps[fslot * g.kp_cap + slot] = kp;
+        }
     }
 }
 

@@ -26,8 +26,8 @@ struct OrbBuffers {
     uint8_t *desc;         // [B+1][kp_cap][32]
     int32_t *counts;       // [B+1]
     int32_t *overflow;     // [B+1]
-    const uint4 *ori_tab;      // [4 shifts][288]: (u*mask as s8x4, mask as u8x4, v, staged word index)
-    const float4 *pattern;     // 512 x (x, x, y, y): entry (j*32 + k)*2 + e = point e of comparison 8*k + j
+    const uint2 *ori_tab;      // [8][32]: (u*mask as s8x4, mask as u8x4) of patch word (row 4*it + lane/8, lane%8)
+    const float4 *pattern;     // 256 x (x0, y0, x1, y1): entry j*32 + k = comparison 8*k + j
 };
 
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask);
