@@ -314,6 +314,106 @@ __device__ __forceinline__ uint32_t u8_magic(uint32_t word, int k)
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
+// Row pass of one task: 8 outputs at columns x..x+7 of two rows.  SLOW: the 14-byte window crosses the
+// image border (reflect per byte); FUSED: taps accumulate with FFMA2, else separately rounded products.
+template <bool SLOW, bool FUSED>
+__device__ __forceinline__ void blur_row_task(const uint8_t *__restrict__ rowa, const uint8_t *__restrict__ rowb, int x, int w,
+                                              const BlurTaps &T, float *__restrict__ outa, float *__restrict__ outb)
+{
+    float2 v[14];       // .x = first row, .y = second row; v[k] = pixel x-3+k
+    if (!SLOW) {
+        const uint32_t *pa = reinterpret_cast<const uint32_t *>(rowa + x - 4), *pb = reinterpret_cast<const uint32_t *>(rowb + x - 4);
+        const uint32_t aw[4] = {__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3)};
+        const uint32_t bw[4] = {__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3)};
+        const float2 M = f2(-8388608.0f, -8388608.0f);
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {
+            const int byte = k + 1;
+            v[k] = __fadd2_rn(f2(__uint_as_float(u8_magic(aw[byte >> 2], byte & 3)), __uint_as_float(u8_magic(bw[byte >> 2], byte & 3))), M);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {
+            const int xx = reflect101(x - 3 + k, w);
+            v[k] = f2((float)__ldg(rowa + xx), (float)__ldg(rowb + xx));
+        }
+    }
+    float2 r[8];
+    if (FUSED) {
+        const float2 K0 = f2(T.k[0], T.k[0]), K1 = f2(T.k[1], T.k[1]), K2 = f2(T.k[2], T.k[2]), K3 = f2(T.k[3], T.k[3]);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float2 s = __fmul2_rn(K0, v[o]);
+            s = __ffma2_rn(K1, v[o + 1], s);
+            s = __ffma2_rn(K2, v[o + 2], s);
+            s = __ffma2_rn(K3, v[o + 3], s);
+            s = __ffma2_rn(K2, v[o + 4], s);
+            s = __ffma2_rn(K1, v[o + 5], s);
+            s = __ffma2_rn(K0, v[o + 6], s);
+            r[o] = s;
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float sa = __fmul_rn(T.k[0], v[o].x), sb = __fmul_rn(T.k[0], v[o].y);
+#pragma unroll
+            for (int k = 1; k < 7; ++k) {
+                const float kk = T.k[k < 4 ? k : 6 - k];
+                sa = __fadd_rn(sa, __fmul_rn(kk, v[o + k].x));
+                sb = __fadd_rn(sb, __fmul_rn(kk, v[o + k].y));
+            }
+            r[o] = f2(sa, sb);
+        }
+    }
+    *reinterpret_cast<float4 *>(outa) = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
+    *reinterpret_cast<float4 *>(outa + 4) = make_float4(r[4].x, r[5].x, r[6].x, r[7].x);
+    *reinterpret_cast<float4 *>(outb) = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
+    *reinterpret_cast<float4 *>(outb + 4) = make_float4(r[4].y, r[5].y, r[6].y, r[7].y);
+}
+
+// Column pass of one task: 4 columns x up to 4 rows from 10 staged rows.
+template <bool FUSED>
+__device__ __forceinline__ void blur_col_task(const float (*R)[BL_W], int c4, int r0, int nrows, const BlurTaps &T, uint8_t *__restrict__ dst, int pitch)
+{
+    float4 w[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) w[k] = *reinterpret_cast<const float4 *>(&R[min(r0 + k, BL_ROWS - 1)][c4]);
+    const float2 K0 = f2(T.k[0], T.k[0]), K1 = f2(T.k[1], T.k[1]), K2 = f2(T.k[2], T.k[2]), K3 = f2(T.k[3], T.k[3]);
+    const float2 MG = f2(12582912.0f, 12582912.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= nrows) break;
+        uint32_t b0, b1, b2, b3;         // float bit patterns whose low byte is the rounded pixel
+        if (FUSED) {
+            float2 sl = __fmul2_rn(K3, f2(w[j + 3].x, w[j + 3].y)), sh = __fmul2_rn(K3, f2(w[j + 3].z, w[j + 3].w));
+            sl = __ffma2_rn(K2, __fadd2_rn(f2(w[j + 4].x, w[j + 4].y), f2(w[j + 2].x, w[j + 2].y)), sl);
+            sh = __ffma2_rn(K2, __fadd2_rn(f2(w[j + 4].z, w[j + 4].w), f2(w[j + 2].z, w[j + 2].w)), sh);
+            sl = __ffma2_rn(K1, __fadd2_rn(f2(w[j + 5].x, w[j + 5].y), f2(w[j + 1].x, w[j + 1].y)), sl);
+            sh = __ffma2_rn(K1, __fadd2_rn(f2(w[j + 5].z, w[j + 5].w), f2(w[j + 1].z, w[j + 1].w)), sh);
+            sl = __ffma2_rn(K0, __fadd2_rn(f2(w[j + 6].x, w[j + 6].y), f2(w[j].x, w[j].y)), sl);
+            sh = __ffma2_rn(K0, __fadd2_rn(f2(w[j + 6].z, w[j + 6].w), f2(w[j].z, w[j].w)), sh);
+            sl = __fadd2_rn(sl, MG); sh = __fadd2_rn(sh, MG);
+            b0 = __float_as_uint(sl.x); b1 = __float_as_uint(sl.y); b2 = __float_as_uint(sh.x); b3 = __float_as_uint(sh.y);
+        } else {
+            const float *c = reinterpret_cast<const float *>(&w[j + 3]);
+            uint32_t bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = __fmul_rn(T.k[3], c[i]);
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) {
+                    const float pr = __fadd_rn(reinterpret_cast<const float *>(&w[j + 3 + k])[i], reinterpret_cast<const float *>(&w[j + 3 - k])[i]);
+                    s = __fadd_rn(s, __fmul_rn(T.k[3 - k], pr));
+                }
+                bb[i] = __float_as_uint(__fadd_rn(s, 12582912.0f));
+            }
+            b0 = bb[0]; b1 = bb[1]; b2 = bb[2]; b3 = bb[3];
+        }
+        const uint32_t p01 = __byte_perm(b0, b1, 0x0040), p23 = __byte_perm(b2, b3, 0x0040);
+        *reinterpret_cast<uint32_t *>(dst + (size_t)j * pitch) = __byte_perm(p01, p23, 0x5410);
+    }
+}
+
 #ifndef ASLAM_BLUR_MINB
 #define ASLAM_BLUR_MINB 4
 #endif
@@ -333,111 +433,56 @@ blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
     const int x0 = tx * BL_W, y0 = ty * BL_H;
     const uint8_t *img = b.pyr + (size_t)blockIdx.y * g.pyr_stride + L.off;
     uint8_t *dst = b.blur + (size_t)blockIdx.y * g.pyr_stride + L.off;
-    const float2 K0 = f2(T.k[0], T.k[0]), K1 = f2(T.k[1], T.k[1]), K2 = f2(T.k[2], T.k[2]), K3 = f2(T.k[3], T.k[3]);
 
-    // ---- row pass: 32 row pairs x 16 groups of 8 outputs = 512 tasks, two per thread
+    // Column groups of 8 of this tile: [0, ng) lie inside the image; a group is "plain" when its 16-byte
+    // window is inside the image and it is left of row_fused_end.  Plain groups go through a branch-free
+    // main loop; the few others (left border, right border, unfused tail) are handled afterwards by a
+    // handful of threads, so no full warp pays for the slow paths.
+    const int ng = min(BL_W / 8, (L.w - x0 + 7) / 8);
+    const int left = (x0 == 0 && ng > 0) ? 1 : 0;                         // group 0 of the first tile needs reflection
+    const int lim = min(L.row_fused_end, L.w - 11);                       // plain <=> x >= 4 and x < lim
+    const int gs = max(left, min(ng, max(0, (lim - x0 + 7) / 8)));        // first non-plain group on the right
+    const int nspecial = left + (ng - gs);
+
+    // ---- row pass, plain groups: 32 row pairs x 16 groups of 8 outputs
 #pragma unroll 1
     for (int i = tid; i < (BL_ROWS / 2) * (BL_W / 8); i += 256) {
-        const int rp = i / (BL_W / 8), c8 = (i - rp * (BL_W / 8)) * 8;
-        const int x = x0 + c8;
-        if (x >= L.w) continue;
+        const int rp = i / (BL_W / 8), gi = i - rp * (BL_W / 8);
+        if (gi < left || gi >= gs) continue;
         const uint8_t *rowa = img + (size_t)reflect101(y0 - 3 + 2 * rp, L.h) * L.pitch;
         const uint8_t *rowb = img + (size_t)reflect101(y0 - 2 + 2 * rp, L.h) * L.pitch;
-        float2 v[14];       // .x = first row, .y = second row; v[k] = pixel x-3+k
-        if (x >= 4 && x + 12 <= L.w) {
-            const uint4 wa = make_uint4(__ldg(reinterpret_cast<const uint32_t *>(rowa + x - 4)), __ldg(reinterpret_cast<const uint32_t *>(rowa + x)),
-                                        __ldg(reinterpret_cast<const uint32_t *>(rowa + x + 4)), __ldg(reinterpret_cast<const uint32_t *>(rowa + x + 8)));
-            const uint4 wb = make_uint4(__ldg(reinterpret_cast<const uint32_t *>(rowb + x - 4)), __ldg(reinterpret_cast<const uint32_t *>(rowb + x)),
-                                        __ldg(reinterpret_cast<const uint32_t *>(rowb + x + 4)), __ldg(reinterpret_cast<const uint32_t *>(rowb + x + 8)));
-            const uint32_t aw[4] = {wa.x, wa.y, wa.z, wa.w}, bw[4] = {wb.x, wb.y, wb.z, wb.w};
-            const float2 M = f2(-8388608.0f, -8388608.0f);
-#pragma unroll
-            for (int k = 0; k < 14; ++k) {
-                const int byte = k + 1;
-                v[k] = __fadd2_rn(f2(__uint_as_float(u8_magic(aw[byte >> 2], byte & 3)), __uint_as_float(u8_magic(bw[byte >> 2], byte & 3))), M);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 14; ++k) {
-                const int xx = reflect101(x - 3 + k, L.w);
-                v[k] = f2((float)__ldg(rowa + xx), (float)__ldg(rowb + xx));
-            }
-        }
-        float2 r[8];
-        if (x < L.row_fused_end) {
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                float2 s = __fmul2_rn(K0, v[o]);
-                s = __ffma2_rn(K1, v[o + 1], s);
-                s = __ffma2_rn(K2, v[o + 2], s);
-                s = __ffma2_rn(K3, v[o + 3], s);
-                s = __ffma2_rn(K2, v[o + 4], s);
-                s = __ffma2_rn(K1, v[o + 5], s);
-                s = __ffma2_rn(K0, v[o + 6], s);
-                r[o] = s;
-            }
-        } else {
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                float sa = __fmul_rn(T.k[0], v[o].x), sb = __fmul_rn(T.k[0], v[o].y);
-#pragma unroll
-                for (int k = 1; k < 7; ++k) {
-                    const float kk = T.k[k < 4 ? k : 6 - k];
-                    sa = __fadd_rn(sa, __fmul_rn(kk, v[o + k].x));
-                    sb = __fadd_rn(sb, __fmul_rn(kk, v[o + k].y));
-                }
-                r[o] = f2(sa, sb);
-            }
-        }
-        *reinterpret_cast<float4 *>(&R[2 * rp][c8]) = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
-        *reinterpret_cast<float4 *>(&R[2 * rp][c8 + 4]) = make_float4(r[4].x, r[5].x, r[6].x, r[7].x);
-        *reinterpret_cast<float4 *>(&R[2 * rp + 1][c8]) = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
-        *reinterpret_cast<float4 *>(&R[2 * rp + 1][c8 + 4]) = make_float4(r[4].y, r[5].y, r[6].y, r[7].y);
+        blur_row_task<false, true>(rowa, rowb, x0 + gi * 8, L.w, T, &R[2 * rp][gi * 8], &R[2 * rp + 1][gi * 8]);
+    }
+    // ---- row pass, special groups
+#pragma unroll 1
+    for (int e = tid; e < (BL_ROWS / 2) * nspecial; e += 256) {
+        const int rp = e / nspecial, si = e - rp * nspecial;
+        const int gi = si < left ? 0 : gs + si - left;
+        const int x = x0 + gi * 8;
+        const uint8_t *rowa = img + (size_t)reflect101(y0 - 3 + 2 * rp, L.h) * L.pitch;
+        const uint8_t *rowb = img + (size_t)reflect101(y0 - 2 + 2 * rp, L.h) * L.pitch;
+        const bool slow = !(x >= 4 && x + 12 <= L.w), fused = x < L.row_fused_end;
+        float *oa = &R[2 * rp][gi * 8], *ob = &R[2 * rp + 1][gi * 8];
+        if (slow && fused) blur_row_task<true, true>(rowa, rowb, x, L.w, T, oa, ob);
+        else if (slow) blur_row_task<true, false>(rowa, rowb, x, L.w, T, oa, ob);
+        else blur_row_task<false, false>(rowa, rowb, x, L.w, T, oa, ob);
     }
     __syncthreads();
 
-    // ---- column pass: 32 groups of 4 columns x 15 runs of 4 rows (the last run has 2)
+    // ---- column pass: 32 groups of 4 columns x 15 runs of 4 rows (the last run has 2); fused groups first
+    const int nc = min(BL_W / 4, (L.w - x0 + 3) / 4);                     // column groups inside the image
+    const int cf = min(nc, max(0, (L.col_fused_end - x0) / 4));           // [0, cf) fused, [cf, nc) unfused
 #pragma unroll 1
     for (int t = tid; t < 32 * ((BL_H + 3) / 4); t += 256) {
-        const int c4 = (t & 31) * 4, r0 = (t >> 5) * 4;
-        if (x0 + c4 >= L.w || y0 + r0 >= L.h) continue;
-        float4 w[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) w[k] = *reinterpret_cast<const float4 *>(&R[min(r0 + k, BL_ROWS - 1)][c4]);
-        const bool fused = x0 + c4 < L.col_fused_end;
-        const float2 MG = f2(12582912.0f, 12582912.0f);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (r0 + j >= BL_H || y0 + r0 + j >= L.h) break;
-            uint32_t b0, b1, b2, b3;         // float bit patterns whose low byte is the rounded pixel
-            if (fused) {
-                float2 sl = __fmul2_rn(K3, f2(w[j + 3].x, w[j + 3].y)), sh = __fmul2_rn(K3, f2(w[j + 3].z, w[j + 3].w));
-                sl = __ffma2_rn(K2, __fadd2_rn(f2(w[j + 4].x, w[j + 4].y), f2(w[j + 2].x, w[j + 2].y)), sl);
-                sh = __ffma2_rn(K2, __fadd2_rn(f2(w[j + 4].z, w[j + 4].w), f2(w[j + 2].z, w[j + 2].w)), sh);
-                sl = __ffma2_rn(K1, __fadd2_rn(f2(w[j + 5].x, w[j + 5].y), f2(w[j + 1].x, w[j + 1].y)), sl);
-                sh = __ffma2_rn(K1, __fadd2_rn(f2(w[j + 5].z, w[j + 5].w), f2(w[j + 1].z, w[j + 1].w)), sh);
-                sl = __ffma2_rn(K0, __fadd2_rn(f2(w[j + 6].x, w[j + 6].y), f2(w[j].x, w[j].y)), sl);
-                sh = __ffma2_rn(K0, __fadd2_rn(f2(w[j + 6].z, w[j + 6].w), f2(w[j].z, w[j].w)), sh);
-                sl = __fadd2_rn(sl, MG); sh = __fadd2_rn(sh, MG);
-                b0 = __float_as_uint(sl.x); b1 = __float_as_uint(sl.y); b2 = __float_as_uint(sh.x); b3 = __float_as_uint(sh.y);
-            } else {
-                const float *c = reinterpret_cast<const float *>(&w[j + 3]);
-                uint32_t bb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float s = __fmul_rn(T.k[3], c[i]);
-#pragma unroll
-                    for (int k = 1; k <= 3; ++k) {
-                        const float pr = __fadd_rn(reinterpret_cast<const float *>(&w[j + 3 + k])[i], reinterpret_cast<const float *>(&w[j + 3 - k])[i]);
-                        s = __fadd_rn(s, __fmul_rn(T.k[3 - k], pr));
-                    }
-                    bb[i] = __float_as_uint(__fadd_rn(s, 12582912.0f));
-                }
-                b0 = bb[0]; b1 = bb[1]; b2 = bb[2]; b3 = bb[3];
-            }
-            const uint32_t p01 = __byte_perm(b0, b1, 0x0040), p23 = __byte_perm(b2, b3, 0x0040);
-            *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r0 + j) * L.pitch + x0 + c4) = __byte_perm(p01, p23, 0x5410);
-        }
+        const int ci = t & 31, r0 = (t >> 5) * 4;
+        if (ci >= cf || y0 + r0 >= L.h) continue;
+        blur_col_task<true>(R, ci * 4, r0, min(4, min(BL_H - r0, L.h - y0 - r0)), T, dst + (size_t)(y0 + r0) * L.pitch + x0 + ci * 4, L.pitch);
+    }
+#pragma unroll 1
+    for (int t = tid; t < (nc - cf) * ((BL_H + 3) / 4); t += 256) {
+        const int ci = cf + t % (nc - cf), r0 = (t / (nc - cf)) * 4;
+        if (y0 + r0 >= L.h) continue;
+        blur_col_task<false>(R, ci * 4, r0, min(4, min(BL_H - r0, L.h - y0 - r0)), T, dst + (size_t)(y0 + r0) * L.pitch + x0 + ci * 4, L.pitch);
     }
 }
 
