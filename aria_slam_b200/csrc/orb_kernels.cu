@@ -31,43 +31,79 @@ __device__ __forceinline__ HRow resize_hrow(uint32_t w0, uint32_t w1, uint32_t w
     return r;
 }
 
-// One thread = 4 consecutive output pixels of one row: six independent 32-bit loads issued up front
-// (no serial march down the image: the kernel is latency-, not instruction-limited), source-row reuse
-// between neighbouring output rows is left to L1.
-__global__ void __launch_bounds__(256)
+// One thread = 4 consecutive output columns of a strip of RS_ROWS output rows, marched top to bottom:
+// the column tables stay in registers, every source row of the strip goes through the horizontal pass
+// exactly once (the two latest results are kept), and the raw words of the next source row are
+// fetched one step ahead.  Source rows advance by 1 or 2 per output row (any scale in (1, 2]); the
+// advance depends on y only, so the control flow is uniform over the CTA.
+constexpr int RS_ROWS = 16;
+
+__global__ void __launch_bounds__(128)
 resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
               LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs, int thresh)
 {
     const int cg = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (cg * 4 >= D.w || y >= D.h) return;
-    const uint8_t *src = srcb + (size_t)blockIdx.z * stride + S.off;
-    uint8_t *dst = dstb + (size_t)blockIdx.z * stride + D.off;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * RS_ROWS;
+    if (cg * 4 >= D.w || y0 >= D.h) return;
+    // CTA-uniform bases + 32-bit per-thread offsets (a frame's pyramid is far below 4 GB)
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(srcb + (size_t)blockIdx.z * stride + S.off);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(dstb + (size_t)blockIdx.z * stride + D.off);
     const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
     const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
-    const uint32_t e = __ldg(tabs + D.ytab_off + y);
-    const int wy1 = (int)(e >> 16);
-    const uint32_t *ra = reinterpret_cast<const uint32_t *>(src + (size_t)(e & 0xffffu) * S.pitch) + t0.x;
-    const uint32_t *rb = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(ra) + S.pitch);
-    const uint32_t a0 = __ldg(ra), a1 = __ldg(ra + 1), a2 = __ldg(ra + 2);
-    const uint32_t b0 = __ldg(rb), b1 = __ldg(rb + 1), b2 = __ldg(rb + 2);
-    const HRow ha = resize_hrow(a0, a1, a2, t0, t1), hb = resize_hrow(b0, b1, b2, t0, t1);
-    uint32_t v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int d = (int)hb.h[i] - (int)ha.h[i];
-        v[i] = (uint32_t)(d * wy1 + (int)(ha.h[i] * 256u + 32768u));      // 16.16, byte 2 = rounded pixel
-        if (thresh && (v[i] >> 16) <= 254u) v[i] = 0;                     // mask levels: threshold(254, TOZERO)
+    const uint32_t *ytab = tabs + D.ytab_off;
+    const uint32_t yend = (uint32_t)min(y0 + RS_ROWS, D.h);
+    const uint32_t pw = (uint32_t)S.pitch >> 2, dpw = (uint32_t)D.pitch >> 2;
+    const uint32_t so_last = t0.x + (uint32_t)(S.h - 1) * pw;     // window offset in the last source row
+
+    // Source-row driven march with the two horizontal results in alternating registers (no copies):
+    // row s goes through the horizontal pass, then every output row whose lower tap is s is emitted.
+    uint32_t e = __ldg(ytab + y0);
+    int s_row = (int)(e & 0xffffu);                    // upper tap of the strip's first output row
+    uint32_t so = t0.x + (uint32_t)s_row * pw;         // window offset of the row fetched next
+    uint32_t n0 = __ldg(src + so), n1 = __ldg(src + so + 1), n2 = __ldg(src + so + 2);
+    uint32_t dofs = (uint32_t)y0 * dpw + (uint32_t)cg;
+    uint32_t y = (uint32_t)y0;
+#define ASLAM_RS_HROW(H)                                                    \
+    do {                                                                    \
+        H = resize_hrow(n0, n1, n2, t0, t1);                                \
+        so = min(so + pw, so_last);                                         \
+        n0 = __ldg(src + so); n1 = __ldg(src + so + 1); n2 = __ldg(src + so + 2); \
+    } while (0)
+#define ASLAM_RS_EMIT(OLD, NEW)                                             \
+    while ((int)(e & 0xffffu) + 1 == s_row) {                               \
+        const uint32_t wy1 = e >> 16, wy0 = 256u - wy1;                     \
+        uint32_t v[4];                                                      \
+        _Pragma("unroll")                                                   \
+        for (int i = 0; i < 4; ++i) {                                       \
+            v[i] = NEW.h[i] * wy1 + (OLD.h[i] * wy0 + 32768u);              /* 16.16, byte 2 = rounded pixel */ \
+            if (thresh && (v[i] >> 16) <= 254u) v[i] = 0;                   /* mask levels: threshold(254, TOZERO) */ \
+        }                                                                   \
+        const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062); \
+        dst[dofs] = __byte_perm(p01, p23, 0x5410);                          \
+        dofs += dpw;                                                        \
+        if (++y == yend) return;                                            \
+        e = __ldg(ytab + y);                                                \
     }
-    const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062);
-    *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch + cg * 4) = __byte_perm(p01, p23, 0x5410);
+    HRow h0, h1;
+    ASLAM_RS_HROW(h1);
+#pragma unroll 1
+    for (;;) {
+        ++s_row;
+        ASLAM_RS_HROW(h0);
+        ASLAM_RS_EMIT(h1, h0)
+        ++s_row;
+        ASLAM_RS_HROW(h1);
+        ASLAM_RS_EMIT(h0, h1)
+    }
+#undef ASLAM_RS_HROW
+#undef ASLAM_RS_EMIT
 }
 
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask)
 {
     const LevelGeom &D = g.lv[level], &S = g.lv[level - 1];
     const int cgs = (D.w + 3) / 4;
-    dim3 grid((cgs + 31) / 32, (D.h + 7) / 8, nframes), block(32, 8);
+    dim3 grid((cgs + 31) / 32, (D.h + 4 * RS_ROWS - 1) / (4 * RS_ROWS), nframes), block(32, 4);
     uint8_t *base = is_mask ? b.mask : b.pyr;
     ProfScope ps(ctx, PK_RESIZE);
     resize_kernel<<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, is_mask ? 1 : 0);
@@ -152,18 +188,28 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
 
     // stage 38 rows x 19 words; each word becomes four u16 in A, and (shifted by one pixel) in Bc
-    for (int i = tid; i < FT_PIX_H * FA_WORDS; i += 256) {
-        const int r = i / FA_WORDS, j = i - r * FA_WORDS;
-        const int y = min(sy0 - 3 + r, L.h - 1);
-        const int x = min(gx0 + 4 * j, L.pitch - 4);
-        const uint8_t *row = img + (size_t)y * L.pitch;
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-        const uint32_t nx = __ldg(row + min(x + 4, L.pitch - 1));
-        uint2 a, c;
-        a.x = __byte_perm(w, 0, 0x4140); a.y = __byte_perm(w, 0, 0x4342);
-        c.x = __byte_perm(w, 0, 0x4241); c.y = __byte_perm(w, nx, 0x7473);
-        *reinterpret_cast<uint2 *>(&A[r][4 * j]) = a;
-        *reinterpret_cast<uint2 *>(&Bc[r][4 * j]) = c;       // Bc[i] = pixel i+1
+    // (three passes of 13 rows x 19 words: the word column, its clamp and the shared-memory slot are
+    // per-thread constants, a pass costs two loads, four PRMTs and two stores)
+    {
+        const int rr = tid / FA_WORDS, jj = tid - rr * FA_WORDS;
+        const int x = min(gx0 + 4 * jj, L.pitch - 4);
+        const int xn = min(x + 4, L.pitch - 1);
+        if (rr < 13) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int r = rr + 13 * k;
+                if (k < 2 || r < FT_PIX_H) {
+                    const uint8_t *row = img + (size_t)min(sy0 - 3 + r, L.h - 1) * L.pitch;
+                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+                    const uint32_t nx = __ldg(row + xn);
+                    uint2 a, c;
+                    a.x = __byte_perm(w, 0, 0x4140); a.y = __byte_perm(w, 0, 0x4342);
+                    c.x = __byte_perm(w, 0, 0x4241); c.y = __byte_perm(w, nx, 0x7473);
+                    *reinterpret_cast<uint2 *>(&A[r][4 * jj]) = a;
+                    *reinterpret_cast<uint2 *>(&Bc[r][4 * jj]) = c;       // Bc[i] = pixel i+1
+                }
+            }
+        }
     }
     __syncthreads();
 
