@@ -163,6 +163,132 @@ knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ pa
     }
 }
 
+// ---- second-generation scan kernel (ASLAM_KNN_CSA 7 / 8)
+// Same adders as CSA 5 / 6, with the work that is not logic or POPC moved off the ALU pipe:
+//  * the three parity words of a train row are computed once when the row is staged (a third
+//    16-byte word per row in shared memory) instead of by every thread;
+//  * popcounts are combined and keys are built with IMADs whose multipliers are kernel
+//    parameters (the FMA pipe is idle in this kernel; literal powers of two would be turned back
+//    into ALU shifts/adds by the compiler);
+//  * inside a 128-row tile a neighbour is the 16-bit key distance << 7 | row-in-tile, two queries
+//    per register, so one VIMNMX.U16x2 triple updates the best-two of two queries; tile results are
+//    widened to 32-bit (distance, row) keys and merged after every tile.  Order and tie-breaking
+//    are unchanged: the unsigned order of both key formats is lexicographic (distance, row).
+struct KnnMul { uint32_t two, four, pack16, shl7; };      // 2, 4, 65536, 128
+
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+template <bool POPC4>
+__device__ __forceinline__ uint32_t hamming256_v2(const uint32_t (&q)[8], const QueryParity qp, const uint4 a, const uint4 b,
+                                                 const uint4 par, const KnnMul M)
+{
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, s0 = qp.a ^ par.x, c0 = carry_from_sum(x0, x1, s0);
+    const uint32_t x3 = q[3] ^ a.w, x4 = q[4] ^ b.x, s1 = qp.b ^ par.y, c1 = carry_from_sum(x3, x4, s1);
+    const uint32_t s2 = qp.c ^ par.z, c2 = carry_from_sum(s0, s1, s2);
+    const uint32_t x7 = q[7] ^ b.w;
+    if (POPC4) {
+        uint32_t s3, c3;
+        csa(c0, c1, c2, s3, c3);
+        return imad(__popc(c3), M.four, imad(__popc(s3), M.two, __popc(s2) + __popc(x7)));
+    }
+    return imad(__popc(c0) + __popc(c1) + __popc(c2), M.two, __popc(s2) + __popc(x7));
+}
+
+// tile-local 16-bit key -> global 32-bit key
+__device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t t0)
+{
+    return k16 == 0xffffu ? KEY_EMPTY : ((k16 >> 7) << KEY_IDX_BITS) + t0 + (k16 & 127u);
+}
+
+template <bool POPC4>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride, const KnnMul M)
+{
+    static_assert(KNN_TILE == KNN_THREADS && KNN_TILE == 128 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
+    __shared__ uint4 tile[2][KNN_TILE * 3];
+
+    const KnnProblem P = probs[blockIdx.y];
+    const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
+    const int nt = P.nt_dev ? min(*P.nt_dev, P.nt) : P.nt;
+    const int qbase = blockIdx.x * KNN_QBLOCK;
+    if (qbase >= nq) return;
+    const int t_lo = P.t_lo, t_hi = min(P.t_hi, nt);
+    const int tid = threadIdx.x;
+
+    uint32_t qd[KNN_RQ][8];
+    uint32_t b1[KNN_RQ], b2[KNN_RQ];
+    QueryParity qp[KNN_RQ];
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        const int qi = qbase + j * KNN_THREADS + tid;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (qi < nq) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.q) + (size_t)qi * 2;
+            lo = __ldg(src); hi = __ldg(src + 1);
+        }
+        qd[j][0] = lo.x; qd[j][1] = lo.y; qd[j][2] = lo.z; qd[j][3] = lo.w;
+        qd[j][4] = hi.x; qd[j][5] = hi.y; qd[j][6] = hi.z; qd[j][7] = hi.w;
+        b1[j] = KEY_EMPTY; b2[j] = KEY_EMPTY;
+        qp[j].a = qd[j][0] ^ qd[j][1] ^ qd[j][2];
+        qp[j].b = qd[j][3] ^ qd[j][4] ^ qd[j][5];
+        qp[j].c = qp[j].a ^ qp[j].b ^ qd[j][6];
+    }
+
+    const uint4 *trows = reinterpret_cast<const uint4 *>(P.t);
+    uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;      // both halves of train row t0 + tid
+    if (t_lo + tid < t_hi) { pre0 = __ldg(trows + 2 * (size_t)(t_lo + tid)); pre1 = __ldg(trows + 2 * (size_t)(t_lo + tid) + 1); }
+    int buf = 0;
+    for (int t0 = t_lo; t0 < t_hi; t0 += KNN_TILE, buf ^= 1) {
+        {
+            uint4 par;
+            par.x = pre0.x ^ pre0.y ^ pre0.z; par.y = pre0.w ^ pre1.x ^ pre1.y; par.z = par.x ^ par.y ^ pre1.z; par.w = 0;
+            tile[buf][3 * tid] = pre0; tile[buf][3 * tid + 1] = pre1; tile[buf][3 * tid + 2] = par;
+        }
+        __syncthreads();
+        if (t0 + KNN_TILE + tid < t_hi) {
+            pre0 = __ldg(trows + 2 * (size_t)(t0 + KNN_TILE + tid)); pre1 = __ldg(trows + 2 * (size_t)(t0 + KNN_TILE + tid) + 1);
+        }
+        const int rows = min(KNN_TILE, t_hi - t0);
+        const uint4 *tb = tile[buf];
+        uint32_t l1[KNN_RQ / 2], l2[KNN_RQ / 2];           // tile-local best / second, two queries per register
+#pragma unroll
+        for (int j = 0; j < KNN_RQ / 2; ++j) { l1[j] = 0xffffffffu; l2[j] = 0xffffffffu; }
+        uint32_t rr = 0;                                   // row-in-tile in both halves
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r) {
+            const uint4 a = tb[3 * r], b = tb[3 * r + 1], par = tb[3 * r + 2];
+#pragma unroll
+            for (int j = 0; j < KNN_RQ / 2; ++j) {
+                const uint32_t da = hamming256_v2<POPC4>(qd[2 * j], qp[2 * j], a, b, par, M);
+                const uint32_t db = hamming256_v2<POPC4>(qd[2 * j + 1], qp[2 * j + 1], a, b, par, M);
+                const uint32_t key = imad(imad(db, M.pack16, da), M.shl7, rr);
+                l2[j] = __vminu2(l2[j], __vmaxu2(l1[j], key));
+                l1[j] = __vminu2(l1[j], key);
+            }
+            rr += 0x00010001u;
+        }
+#pragma unroll
+        for (int j = 0; j < KNN_RQ; ++j) {
+            const int sh = (j & 1) * 16;
+            const uint32_t k1 = widen_key((l1[j >> 1] >> sh) & 0xffffu, (uint32_t)t0);
+            const uint32_t k2 = widen_key((l2[j >> 1] >> sh) & 0xffffu, (uint32_t)t0);
+            const uint32_t n2 = min(max(b1[j], k1), min(b2[j], k2));      // k1 <= k2
+            b1[j] = min(b1[j], k1);
+            b2[j] = n2;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        const int qi = qbase + j * KNN_THREADS + tid;
+        if (qi < nq) partial[(size_t)blockIdx.y * q_stride + qi] = make_uint2(b1[j], b2[j]);
+    }
+}
+
 // Merge `splits` partial (best, second) pairs of one query: keys are distinct across splits
 // (disjoint row ranges), so the two smallest of the union are the answer.
 __device__ __forceinline__ void merge_pair(uint32_t &k1, uint32_t &k2, const uint2 p)
@@ -421,6 +547,8 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
     case 4: knn2_partial_kernel<4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     case 5: knn2_partial_kernel<5><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     case 6: knn2_partial_kernel<6><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
+    case 7: knn2_partial_v2_kernel<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, KnnMul{2u, 4u, 65536u, 128u}); break;
+    case 8: knn2_partial_v2_kernel<true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, KnnMul{2u, 4u, 65536u, 128u}); break;
     default: knn2_partial_kernel<2><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
     }
     ASLAM_LAUNCH_CHECK();

@@ -36,7 +36,10 @@ __device__ __forceinline__ HRow resize_hrow(uint32_t w0, uint32_t w1, uint32_t w
 // exactly once (the two latest results are kept), and the raw words of the next source row are
 // fetched one step ahead.  Source rows advance by 1 or 2 per output row (any scale in (1, 2]); the
 // advance depends on y only, so the control flow is uniform over the CTA.
-constexpr int RS_ROWS = 16;
+#ifndef ASLAM_RS_ROWS
+#define ASLAM_RS_ROWS 16
+#endif
+constexpr int RS_ROWS = ASLAM_RS_ROWS;
 
 __global__ void __launch_bounds__(128)
 resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
@@ -59,15 +62,18 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
     // row s goes through the horizontal pass, then every output row whose lower tap is s is emitted.
     uint32_t e = __ldg(ytab + y0);
     int s_row = (int)(e & 0xffffu);                    // upper tap of the strip's first output row
-    uint32_t so = t0.x + (uint32_t)s_row * pw;         // window offset of the row fetched next
-    uint32_t n0 = __ldg(src + so), n1 = __ldg(src + so + 1), n2 = __ldg(src + so + 2);
+    // raw words of the next two source rows are always in flight (buffers a and b alternate)
+    uint32_t so = t0.x + (uint32_t)s_row * pw;
+    uint32_t a0 = __ldg(src + so), a1 = __ldg(src + so + 1), a2 = __ldg(src + so + 2);
+    so = min(so + pw, so_last);
+    uint32_t b0 = __ldg(src + so), b1 = __ldg(src + so + 1), b2 = __ldg(src + so + 2);
     uint32_t dofs = (uint32_t)y0 * dpw + (uint32_t)cg;
     uint32_t y = (uint32_t)y0;
-#define ASLAM_RS_HROW(H)                                                    \
+#define ASLAM_RS_HROW(H, N0, N1, N2)                                        \
     do {                                                                    \
-        H = resize_hrow(n0, n1, n2, t0, t1);                                \
+        H = resize_hrow(N0, N1, N2, t0, t1);                                \
         so = min(so + pw, so_last);                                         \
-        n0 = __ldg(src + so); n1 = __ldg(src + so + 1); n2 = __ldg(src + so + 2); \
+        N0 = __ldg(src + so); N1 = __ldg(src + so + 1); N2 = __ldg(src + so + 2); \
     } while (0)
 #define ASLAM_RS_EMIT(OLD, NEW)                                             \
     while ((int)(e & 0xffffu) + 1 == s_row) {                               \
@@ -85,14 +91,14 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
         e = __ldg(ytab + y);                                                \
     }
     HRow h0, h1;
-    ASLAM_RS_HROW(h1);
+    ASLAM_RS_HROW(h1, a0, a1, a2);
 #pragma unroll 1
     for (;;) {
         ++s_row;
-        ASLAM_RS_HROW(h0);
+        ASLAM_RS_HROW(h0, b0, b1, b2);
         ASLAM_RS_EMIT(h1, h0)
         ++s_row;
-        ASLAM_RS_HROW(h1);
+        ASLAM_RS_HROW(h1, a0, a1, a2);
         ASLAM_RS_EMIT(h0, h1)
     }
 #undef ASLAM_RS_HROW
