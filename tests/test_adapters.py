@@ -18,8 +18,9 @@ def test_adapters_compile_against_reference_headers():
     if not os.path.exists(os.path.join(REF_INC, "interfaces", "IFeatureExtractor.hpp")):
         pytest.skip("reference tree not present on this machine")
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DARIA_UPSTREAM_HEADERS", "-I" + REF_INC,
-                        "-I" + os.path.join(ROOT, "tests", "eigen_stub"),
-                        os.path.join(AD, "b200_adapters.cpp"), os.path.join(AD, "selftest.cpp")],
+                        "-I" + os.path.join(AD, "compat"),
+                        os.path.join(AD, "b200_adapters.cpp"), os.path.join(AD, "selftest.cpp"),
+                        os.path.join(AD, "slam_pipeline.cpp"), os.path.join(AD, "pipeline_selftest.cpp")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
 
@@ -30,6 +31,53 @@ def test_adapter_library_is_built_and_links_the_c_abi():
     out = subprocess.run(["nm", "-D", "--undefined-only", so], stdout=subprocess.PIPE, text=True).stdout
     for sym in ("aslam_orb_extract_async", "aslam_orb_sync", "aslam_match_knn2", "aslam_loopdb_query_segmented"):
         assert sym in out
+
+
+def test_pipeline_mock_mode_runs_without_a_gpu():
+    """SlamPipeline::processFrame + PipelineFactory::createMock()/createCpu(), the dynamic-object filter
+    (src/main.cpp:29-50 semantics) and the callbacks, with mock ports only."""
+    r = subprocess.run([os.path.join(AD, "pipeline_selftest"), "mock"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_pipeline_gpu_mode_matches_oracle(tmp_path, oracle):
+    """PipelineFactory::create(GPU) and a hand-built pipeline over the B200 adapters: what processFrame
+    extracted and matched (previous frame = query, src/main.cpp:158-163) equals the oracle."""
+    from aria_slam_b200 import synth
+    from oracle.oracle import KP_DTYPE
+    w, h, n, nframes = 640, 480, 800, 4
+    frames = [synth.frame(w, h, 91)]
+    for i in range(1, nframes):
+        frames.append(synth.shifted(frames[-1], seed=91 + i))
+    raw = tmp_path / "in.raw"
+    raw.write_bytes(b"".join(f.tobytes() for f in frames))
+    out = tmp_path / "out.bin"
+    r = subprocess.run([os.path.join(AD, "pipeline_selftest"), "gpu", str(raw), str(w), str(h), str(nframes), str(n), str(out)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    buf = out.read_bytes()
+    pos, got = 0, []
+    for _ in range(nframes):
+        (k,) = struct.unpack_from("<i", buf, pos); pos += 4
+        kps = np.frombuffer(buf, KP_DTYPE, k, pos); pos += 24 * k
+        desc = np.frombuffer(buf, np.uint8, 32 * k, pos).reshape(k, 32); pos += 32 * k
+        (m,) = struct.unpack_from("<i", buf, pos); pos += 4
+        matches = np.frombuffer(buf, np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), m, pos); pos += 12 * m
+        got.append((kps, desc, matches))
+    tail = struct.unpack_from("<3i", buf, pos)
+    assert tail[0] == nframes and tail[1] == nframes
+    key = lambda k: sorted(zip(k["octave"].tolist(), k["x"].tolist(), k["y"].tolist()))
+    for i, img in enumerate(frames):
+        ko, do = oracle.orb(img, n)
+        kps, desc, matches = got[i]
+        assert key(kps) == key(ko)
+        if i:
+            idx, dist = oracle.knn2(got[i - 1][1], desc)              # query = previous frame
+            ref = oracle.ratio_matches(idx, dist, 3, 4)
+            mine = np.stack([matches["q"], matches["t"], matches["d"].astype(np.int32)], 1)
+            assert mine.shape == ref.shape and (mine == ref).all()
+            assert len(ref) >= 8                                       # enough for the motion step
 
 
 @pytest.mark.gpu
