@@ -29,4 +29,13 @@ dt = (time.perf_counter() - t0) / K
 out["ms_per_batch256"] = dt * 1e3
 out["frames_per_s_device"] = B / dt
 out["stages_ms_per_batch"] = {k: (v[0] / K, v[1] / K) for k, v in ctx.prof_read().items()}
+ctx.prof_enable(False)
+for it in range(2):
+    tr.track_async(d, 0.75, on_device=True); tr.device_results()
+ctx.sync()
+t0 = time.perf_counter()
+for it in range(K):
+    tr.track_async(d, 0.75, on_device=True); tr.device_results()
+ctx.sync()
+out["ms_per_batch256_noprof"] = (time.perf_counter() - t0) / K * 1e3
 print(json.dumps(out, indent=1))
