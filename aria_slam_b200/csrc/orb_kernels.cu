@@ -227,8 +227,10 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     const int px_x = sx0 + 2 * p;
     const uint32_t neg_thr = ((uint32_t)(px_x < L.w - 3 ? -g.fast_thr : -30000) & 0xffffu) |
                              ((uint32_t)(px_x + 1 < L.w - 3 ? -g.fast_thr : -30000) << 16);
+    // rows below y = h - edge feed no output (the NMS of row y reads y-1 .. y+1 and emits y < h - edge only)
+    const int r_end = min(FT_SCORE_H, L.h - g.edge - sy0 + 1);
 #pragma unroll 1
-    for (int r = warp; r < FT_SCORE_H; r += 8) {
+    for (int r = warp; r < r_end; r += 8) {
         uint32_t v[16];
         v[0] = ring_pair<0, 3>(A, Bc, r, gp);    v[1] = ring_pair<1, 3>(A, Bc, r, gp);
         v[2] = ring_pair<2, 2>(A, Bc, r, gp);    v[3] = ring_pair<3, 1>(A, Bc, r, gp);
@@ -283,7 +285,7 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     for (int k = 0; k < 4; ++k) {
         const int r = 1 + 4 * warp + k;
         uint32_t e = 0;
-        if (r <= FT_OUT_H) {
+        if (r <= FT_OUT_H && sy0 + r < L.h - g.edge) {
             const uint32_t up = S[r - 1][p], cur = S[r][p], dn = S[r + 1][p];
             const uint32_t V = __vmaxu2(up, dn), C3 = max3(up, cur, dn);
             const uint32_t Lw = __shfl_up_sync(0xffffffffu, C3, 1), Rw = __shfl_down_sync(0xffffffffu, C3, 1);
@@ -291,7 +293,6 @@ fast_kernel(OrbGeom g, OrbBuffers b)
             const int y = sy0 + r;
             // strict maximum per lane: cur - nb > 0; adjacent pixels are never both maxima
             uint32_t d = __vimax_s16x2_relu(__vsub2(cur, nb), 0u) & col_ok;
-            if (y >= L.h - g.edge) d = 0;
             if (d) {
                 const bool second = (d & 0xffffu) == 0;
                 const int x = px_x + (second ? 1 : 0);
