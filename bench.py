@@ -321,6 +321,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel + all stages
     hbm_peak, peak_src = measured_peaks()
     popc_peak = ctx.microbench(0)                      # G popc32/s, measured on this GPU now
+    vimnmx_peak = ctx.microbench(3)                    # G VIMNMX3.U16x2 lane-ops/s
     frames_total = BATCH * K
     stages = {}
     step_ms = sum(v[0] for v in prof.values()) / K
@@ -337,8 +338,15 @@ def run_ours(args):
             ach = BYTES_PER_FRAME[name] * frames_total / (tot_ms * 1e-3) / 1e9
             ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
         elif name == "knn2_partial":
+            # algorithmic: 8 POPC32 per descriptor pair; the kernel's carry-save adders execute 4
             ach = 8.0 * pairs_per_step * K / (tot_ms * 1e-3) / 1e9
-            ent.update(bound="int_pipe(popc)", achieved=ach, peak=popc_peak, unit="Gpopc32/s", frac=ach / popc_peak)
+            ent.update(bound="int_pipe(popc)", achieved=ach, peak=popc_peak, unit="Gpopc32/s", frac=ach / popc_peak,
+                       executed_popc_per_pair=4, frac_executed=0.5 * ach / popc_peak)
+        if name == "fast_nms":
+            # why FAST is not HBM-bound: >= 40 three-input u16x2 min/max per pixel, issued on the ALU pipe
+            ops = 40.0 * BYTES_PER_FRAME["fast_nms"] * frames_total / (tot_ms * 1e-3) / 1e9
+            ent["alu_pipe"] = {"achieved": ops, "peak": vimnmx_peak, "unit": "Gops/s (VIMNMX3.U16x2 lanes)", "frac": ops / vimnmx_peak,
+                               "note": "40 ops per pyramid pixel (the kernel evaluates only the border-free ROI, so this can overstate)"}
         ent["traffic"] = traffic.get(name)
         stages[name] = ent
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
