@@ -215,7 +215,7 @@ static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_
         if (rc) return rc;
         rc = launch_fill_split_problems(ctx, db->d_probs, d_q, db->d_rows + db->head * 32, nullptr, nullptr, nq, (int)rows, splits);
         if (rc) return rc;
-        rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride);
+        rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride, splits);
         if (rc) return rc;
     } else {
         int rc = db_reserve(db, 0, 1, 1);       // an empty shard still reports (empty, empty) per query
@@ -226,12 +226,12 @@ static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_
             ASLAM_CUDA(cudaMalloc(&db->d_arrival, sizeof(unsigned int)));
             ASLAM_CUDA(cudaMemsetAsync(db->d_arrival, 0, sizeof(unsigned int), ctx->stream));
         }
-        return launch_knn2_finish_exchange(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_peer_bufs, nparts,
+        return launch_knn2_finish_exchange(ctx, db->d_partial, 1, nq, q_stride, db->row_base, d_peer_bufs, nparts,
                                            my_part, round, db->d_arrival, d_top2);
     }
     if (d_peer_bufs)
-        return launch_knn2_finish_global_push(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_peer_bufs, nparts, my_part);
-    return launch_knn2_finish_global(ctx, db->d_partial, splits, nq, q_stride, db->row_base, d_top2);
+        return launch_knn2_finish_global_push(ctx, db->d_partial, 1, nq, q_stride, db->row_base, d_peer_bufs, nparts, my_part);
+    return launch_knn2_finish_global(ctx, db->d_partial, 1, nq, q_stride, db->row_base, d_top2);
 }
 
 int aslam_loopdb_query_global_device(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_t *d_top2)

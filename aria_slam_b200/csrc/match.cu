@@ -5,6 +5,7 @@
 // (src/adapters/gpu/CudaMatcher.cpp:56, src/main.cpp:159, src/euroc_eval.cpp:168) and the CPU
 // cv::BFMatcher::knnMatch of src/legacy/LoopClosure.cpp:87; results follow the CPU matcher:
 // ascending (distance, train index).
+#include <cmath>
 #include <cstdlib>
 
 #include "match.cuh"
@@ -13,39 +14,16 @@ namespace aslam {
 
 constexpr int KNN_TILE = 128;   // train rows per shared-memory stage (4 KB)
 
-// popcount(q ^ t) over 256 bits.  POPC issues at 16 lanes/clk/SM (measured 4.39 Tpopc/s), LOP3 and
-// IADD3 at 64: carry-save adders (2 LOP3 each) compress three equal-weight words into a sum and a
-// carry word and so trade one quarter-rate POPC for two full-rate logic ops.
-//   CSA 0: 8 POPC            CSA 2: 6 POPC + 2 adders        CSA 3: 5 POPC + 3 adders
-//   CSA 4: 4 POPC + 4 adders (ones, ones, twos, fours)
-//   CSA 5: as CSA 3, but the adder sums come from precomputed word parities: with Qa = q0^q1^q2 kept
-//          per query and Ta = t0^t1^t2 computed once per train row, s0 = Qa^Ta needs no x2, and the
-//          carry maj(x0,x1,x2) = f(x0,x1,s0) is still one LOP3 -- 11 logic ops per pair instead of 14.
+// popcount(q ^ t) over 256 bits.  POPC issues at 16 lanes/clk/SM (measured 4.38 Tpopc/s), LOP3 at 64:
+// carry-save adders (2 LOP3 each) compress three equal-weight words into a sum and a carry word and so
+// trade one quarter-rate POPC for two full-rate logic ops.  With Qa = q0^q1^q2 kept per query and
+// Ta = t0^t1^t2 computed once per train row, the adder sum s0 = Qa^Ta needs no x2, and the carry
+// maj(x0,x1,x2) = f(x0,x1,s0) is still one LOP3: three such adders + one over their carries leave
+// four words to count (weights 1, 1, 2, 4): 13 logic ops + 4 POPC per pair instead of 8 + 8.
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
 {
     sum = a ^ b ^ c;
     carry = (a & b) | (c & (a ^ b));
-}
-
-template <int CSA>
-__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4 a, const uint4 b)
-{
-    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
-    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
-    if (CSA == 0)
-        return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
-    uint32_t s0, c0, s1, c1;
-    csa(x0, x1, x2, s0, c0);
-    csa(x3, x4, x5, s1, c1);
-    if (CSA == 2)
-        return __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2u * (__popc(c0) + __popc(c1));
-    uint32_t s2, c2;
-    csa(s0, s1, x6, s2, c2);
-    if (CSA == 3)
-        return __popc(s2) + __popc(x7) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
-    uint32_t s3, c3;
-    csa(c0, c1, c2, s3, c3);
-    return __popc(s2) + __popc(x7) + 2u * __popc(s3) + 4u * __popc(c3);
 }
 
 // carry of a full adder given two inputs and the SUM of all three: x2 = s ^ x0 ^ x1
@@ -58,113 +36,8 @@ __device__ __forceinline__ uint32_t carry_from_sum(uint32_t x0, uint32_t x1, uin
 
 struct QueryParity { uint32_t a, b, c; };      // q0^q1^q2, q3^q4^q5, q0^..^q6
 
-__device__ __forceinline__ uint32_t hamming256_parity(const uint32_t (&q)[8], const QueryParity qp, const uint4 a, const uint4 b,
-                                                     uint32_t ta, uint32_t tb, uint32_t tc)
-{
-    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, s0 = qp.a ^ ta, c0 = carry_from_sum(x0, x1, s0);
-    const uint32_t x3 = q[3] ^ a.w, x4 = q[4] ^ b.x, s1 = qp.b ^ tb, c1 = carry_from_sum(x3, x4, s1);
-    const uint32_t s2 = qp.c ^ tc, c2 = carry_from_sum(s0, s1, s2);
-    const uint32_t x7 = q[7] ^ b.w;
-    return __popc(s2) + __popc(x7) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
-}
-
-// CSA 6: as CSA 5 plus a fourth adder over the three carries: 13 logic ops + 4 POPC per pair.
-__device__ __forceinline__ uint32_t hamming256_parity4(const uint32_t (&q)[8], const QueryParity qp, const uint4 a, const uint4 b,
-                                                      uint32_t ta, uint32_t tb, uint32_t tc)
-{
-    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, s0 = qp.a ^ ta, c0 = carry_from_sum(x0, x1, s0);
-    const uint32_t x3 = q[3] ^ a.w, x4 = q[4] ^ b.x, s1 = qp.b ^ tb, c1 = carry_from_sum(x3, x4, s1);
-    const uint32_t s2 = qp.c ^ tc, c2 = carry_from_sum(s0, s1, s2);
-    const uint32_t x7 = q[7] ^ b.w;
-    uint32_t s3, c3;
-    csa(c0, c1, c2, s3, c3);
-    return __popc(s2) + __popc(x7) + 2u * __popc(s3) + 4u * __popc(c3);
-}
-
-template <int CSA>
-__global__ void __launch_bounds__(KNN_THREADS)
-knn2_partial_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride)
-{
-    __shared__ uint4 tile[2][KNN_TILE * 2];
-
-    const KnnProblem P = probs[blockIdx.y];
-    const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
-    const int nt = P.nt_dev ? min(*P.nt_dev, P.nt) : P.nt;
-    const int qbase = blockIdx.x * KNN_QBLOCK;
-    if (qbase >= nq) return;
-    const int t_lo = P.t_lo, t_hi = min(P.t_hi, nt);
-    const int tid = threadIdx.x;
-
-    uint32_t qd[KNN_RQ][8];
-    uint32_t b1[KNN_RQ], b2[KNN_RQ];
-#pragma unroll
-    for (int j = 0; j < KNN_RQ; ++j) {
-        const int qi = qbase + j * KNN_THREADS + tid;
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (qi < nq) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.q) + (size_t)qi * 2;
-            lo = __ldg(src); hi = __ldg(src + 1);
-        }
-        qd[j][0] = lo.x; qd[j][1] = lo.y; qd[j][2] = lo.z; qd[j][3] = lo.w;
-        qd[j][4] = hi.x; qd[j][5] = hi.y; qd[j][6] = hi.z; qd[j][7] = hi.w;
-        b1[j] = KEY_EMPTY; b2[j] = KEY_EMPTY;
-    }
-    QueryParity qp[KNN_RQ];
-#pragma unroll
-    for (int j = 0; j < KNN_RQ; ++j) {
-        qp[j].a = qd[j][0] ^ qd[j][1] ^ qd[j][2];
-        qp[j].b = qd[j][3] ^ qd[j][4] ^ qd[j][5];
-        qp[j].c = qp[j].a ^ qp[j].b ^ qd[j][6];
-    }
-
-    const uint4 *trows = reinterpret_cast<const uint4 *>(P.t);
-    // stage 0
-    uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
-    {
-        const int e0 = t_lo * 2 + tid, e1 = e0 + KNN_THREADS;
-        if (e0 < t_hi * 2) pre0 = __ldg(trows + e0);
-        if (e1 < t_hi * 2) pre1 = __ldg(trows + e1);
-    }
-    int buf = 0;
-    for (int t0 = t_lo; t0 < t_hi; t0 += KNN_TILE, buf ^= 1) {
-        tile[buf][tid] = pre0;
-        tile[buf][tid + KNN_THREADS] = pre1;
-        __syncthreads();
-        // prefetch the next stage into registers while this one is consumed
-        {
-            const int e0 = (t0 + KNN_TILE) * 2 + tid, e1 = e0 + KNN_THREADS;
-            if (e0 < t_hi * 2) pre0 = __ldg(trows + e0);
-            if (e1 < t_hi * 2) pre1 = __ldg(trows + e1);
-        }
-        const int rows = min(KNN_TILE, t_hi - t0);
-        const uint4 *tb = tile[buf];
-        uint32_t keybase = (uint32_t)t0;
-#pragma unroll 4
-        for (int r = 0; r < rows; ++r) {
-            const uint4 a = tb[2 * r], b = tb[2 * r + 1];
-            const uint32_t ta = a.x ^ a.y ^ a.z, tbp = a.w ^ b.x ^ b.y, tc = ta ^ tbp ^ b.z;
-#pragma unroll
-            for (int j = 0; j < KNN_RQ; ++j) {
-                const uint32_t d = CSA == 5 ? hamming256_parity(qd[j], qp[j], a, b, ta, tbp, tc)
-                                   : CSA == 6 ? hamming256_parity4(qd[j], qp[j], a, b, ta, tbp, tc)
-                                              : hamming256<CSA>(qd[j], a, b);
-                const uint32_t key = (d << KEY_IDX_BITS) + keybase;
-                b2[j] = min(b2[j], max(b1[j], key));
-                b1[j] = min(b1[j], key);
-            }
-            ++keybase;
-        }
-        // two buffers: the barrier of the next trip orders this trip's reads before the rewrite
-    }
-#pragma unroll
-    for (int j = 0; j < KNN_RQ; ++j) {
-        const int qi = qbase + j * KNN_THREADS + tid;
-        if (qi < nq) partial[(size_t)blockIdx.y * q_stride + qi] = make_uint2(b1[j], b2[j]);
-    }
-}
-
-// ---- second-generation scan kernel (ASLAM_KNN_CSA 7 / 8)
-// Same adders as CSA 5 / 6, with the work that is not logic or POPC moved off the ALU pipe:
+// ---- scan kernel (ASLAM_KNN_CSA 7: 5 POPC per pair, 8: 4 POPC per pair)
+// Everything that is not logic or POPC is kept off the ALU pipe:
 //  * the three parity words of a train row are computed once when the row is staged (a third
 //    16-byte word per row in shared memory) instead of by every thread;
 //  * popcounts are combined and keys are built with IMADs whose multipliers are kernel
@@ -207,7 +80,7 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t t0)
 
 template <bool POPC4>
 __global__ void __launch_bounds__(KNN_THREADS)
-knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride, const KnnMul M)
+knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride, const KnnMul M, int merge_div)
 {
     static_assert(KNN_TILE == KNN_THREADS && KNN_TILE == 128 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
     __shared__ uint4 tile[2][KNN_TILE * 3];
@@ -282,10 +155,25 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__
             b2[j] = n2;
         }
     }
+    // Row ranges of one (query set, train set) pair are consecutive problems: with merge_div > 1 they are merged
+    // here, into one (best, second) per query and group, by three order-independent atomic minima (the slot
+    // was preset to KEY_EMPTY): B1 <- min(B1, b1) returns the previous best; whichever of the two lost goes to
+    // B2, as does b2.  Every key except the overall minimum thus reaches B2, so B2 ends as the second smallest.
 #pragma unroll
     for (int j = 0; j < KNN_RQ; ++j) {
         const int qi = qbase + j * KNN_THREADS + tid;
-        if (qi < nq) partial[(size_t)blockIdx.y * q_stride + qi] = make_uint2(b1[j], b2[j]);
+        if (qi >= nq) continue;
+        if (merge_div <= 1) {
+            partial[(size_t)blockIdx.y * q_stride + qi] = make_uint2(b1[j], b2[j]);
+        } else {
+            unsigned int *slot = reinterpret_cast<unsigned int *>(partial + (size_t)(blockIdx.y / merge_div) * q_stride + qi);
+            if (b1[j] != KEY_EMPTY) {
+                const uint32_t old = atomicMin(slot, b1[j]);
+                const uint32_t lost = max(old, b1[j]);
+                if (lost != KEY_EMPTY) atomicMin(slot + 1, lost);
+                if (b2[j] != KEY_EMPTY) atomicMin(slot + 1, b2[j]);
+            }
+        }
     }
 }
 
@@ -345,9 +233,7 @@ knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__
     for (int q0 = 0; q0 < nq; q0 += FIN_THREADS) {
         const int q = q0 + threadIdx.x;
         uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
-        if (q < nq)
-            for (int s = 0; s < splits; ++s)
-                merge_pair(k1, k2, partial[(size_t)(g * splits + s) * q_stride + q]);
+        if (q < nq) merge_pair(k1, k2, partial[(size_t)g * q_stride + q]);      // the scan merged the group's row ranges
         const uint32_t d0 = k1 >> KEY_IDX_BITS, d1 = k2 >> KEY_IDX_BITS;
         const int i0 = (int)(k1 & (KNN_MAX_ROWS - 1)), i1 = (int)(k2 & (KNN_MAX_ROWS - 1));
         if (q < nq && raw_idx) {
@@ -535,22 +421,17 @@ int launch_fill_split_problems(aslam_ctx *ctx, KnnProblem *d_probs, const uint8_
 }
 
 int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int max_nq,
-                        uint2 *d_partial, int q_stride)
+                        uint2 *d_partial, int q_stride, int merge_div)
 {
     if (nprobs <= 0 || max_nq <= 0) return ASLAM_OK;
     dim3 grid((max_nq + KNN_QBLOCK - 1) / KNN_QBLOCK, nprobs);
     static const int csa = [] { const char *e = getenv("ASLAM_KNN_CSA"); return e ? atoi(e) : ASLAM_KNN_CSA; }();
+    if (merge_div > 1)
+        ASLAM_CUDA(cudaMemsetAsync(d_partial, 0xff, sizeof(uint2) * (size_t)(nprobs / merge_div) * q_stride, ctx->stream));
+    const KnnMul M{2u, 4u, 65536u, 128u};
     ProfScope ps(ctx, PK_KNN_PARTIAL);
-    switch (csa) {
-    case 0: knn2_partial_kernel<0><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
-    case 3: knn2_partial_kernel<3><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
-    case 4: knn2_partial_kernel<4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
-    case 5: knn2_partial_kernel<5><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
-    case 6: knn2_partial_kernel<6><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
-    case 7: knn2_partial_v2_kernel<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, KnnMul{2u, 4u, 65536u, 128u}); break;
-    case 8: knn2_partial_v2_kernel<true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, KnnMul{2u, 4u, 65536u, 128u}); break;
-    default: knn2_partial_kernel<2><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride); break;
-    }
+    if (csa == 7) knn2_partial_v2_kernel<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div);
+    else knn2_partial_v2_kernel<true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
@@ -622,17 +503,30 @@ static RatioTest make_ratio(double ratio, int as_double)
     return rt;
 }
 
-// How many row ranges to cut a train set of nt rows into so the grid covers the GPU a few times.
+// How many row ranges to cut a train set of nt rows into.  The scan kernel keeps 5 CTAs of equal work
+// resident per SM, so the grid should be a whole number of such waves (a 1.4-wave grid runs as long as
+// a 2-wave grid): among the cuts that leave at least 128 rows per range, take the one with the best
+// wave efficiency, preferring fewer ranges on ties.
 int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets)
 {
-    const int qblocks = (nq + KNN_QBLOCK - 1) / KNN_QBLOCK;
-    const long long want = 8LL * ctx->sm_count;               // CTAs
-    long long s = (want + (long long)qblocks * nsets - 1) / ((long long)qblocks * nsets);
-    const long long max_by_rows = (nt + 255) / 256;           // at least 256 rows per split
-    if (s > max_by_rows) s = max_by_rows;
-    if (s < 1) s = 1;
-    if (s > 4096) s = 4096;
-    return (int)s;
+    const long long units = (long long)((nq + KNN_QBLOCK - 1) / KNN_QBLOCK) * nsets;      // CTAs per range
+    const double slots = 5.0 * ctx->sm_count;
+    const long long max_s = nt / 128 < 1 ? 1 : (nt / 128 > 4096 ? 4096 : nt / 128);
+    static const int forced = [] { const char *e = getenv("ASLAM_KNN_SPLITS"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return (int)(forced < max_s ? forced : max_s);
+    // first choice: the coarsest cut with at least ASLAM_KNN_WAVES (6) nearly full waves -- CTAs of several
+    // waves run out of phase, which keeps the POPC pipe busier than one wave of CTAs in lock step
+    static const int min_waves = [] { const char *e = getenv("ASLAM_KNN_WAVES"); return e ? atoi(e) : 6; }();
+    int best = 1;
+    double best_score = -1.0;
+    for (long long s = 1; s <= max_s; ++s) {
+        const double waves = (double)(units * s) / slots;
+        const double eff = waves / ceil(waves);
+        if (waves >= (double)min_waves && eff >= 0.97) return (int)s;
+        const double score = eff * (waves < 4.0 ? 0.8 + 0.05 * waves : 1.0);
+        if (score > best_score + 1e-9) { best_score = score; best = (int)s; }
+    }
+    return best;
 }
 
 }  // namespace aslam
@@ -672,7 +566,7 @@ static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t
     rc = launch_fill_split_problems(ctx, dp, dq, dt, nullptr, nullptr, nq, nt, splits);
     if (rc) return rc;
     uint2 *dpart = (uint2 *)(base + o_part);
-    rc = launch_knn2_partial(ctx, dp, splits, nq, dpart, q_stride);
+    rc = launch_knn2_partial(ctx, dp, splits, nq, dpart, q_stride, splits);
     if (rc) return rc;
     aslam_match *dm = d_out_user ? d_out_user : (aslam_match *)(base + o_match);
     int32_t *dn = d_nout_user ? d_nout_user : (int32_t *)(base + o_nout);

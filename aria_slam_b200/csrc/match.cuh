@@ -37,11 +37,14 @@ int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets);
 int launch_fill_split_problems(aslam_ctx *ctx, KnnProblem *d_probs, const uint8_t *q, const uint8_t *t,
                                const int32_t *nq_dev, const int32_t *nt_dev, int nq, int nt, int splits);
 
-// partial[slot * q_stride + q] = (best, second) keys of problem `slot`.
+// merge_div <= 1: partial[slot * q_stride + q] = (best, second) keys of problem `slot`.
+// merge_div  > 1: every merge_div consecutive problems (the row ranges of one pair) are merged by the scan
+//                 itself: partial[(slot / merge_div) * q_stride + q]; nprobs must be a multiple of merge_div.
 int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int max_nq,
-                        uint2 *d_partial, int q_stride);
+                        uint2 *d_partial, int q_stride, int merge_div = 1);
 
-// Groups of `splits` consecutive slots are merged per query; survivors of the ratio test are
+// One merged slot per group of `splits` consecutive problems (launch_knn2_partial with merge_div = splits);
+// survivors of the ratio test are
 // written in query order to d_out[group * out_stride ...], their number to d_nout[group].
 // d_raw_idx/d_raw_dist (optional, [group][q_stride][2]) receive the merged neighbours.
 int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,

@@ -104,7 +104,7 @@ static int orb_plan(aslam_orb *o)
     b.pattern = o->d_pattern;
     b.ori_tab = o->d_ori_tab;
     // tracking scratch
-    o->track_splits = choose_splits(ctx, g.kp_cap, g.kp_cap, o->max_batch);
+    o->track_splits = choose_splits(ctx, o->prm.nfeatures, o->prm.nfeatures, o->max_batch);     // expected rows, not the capacity
     ASLAM_CUDA(cudaMalloc(&o->d_matches, sizeof(aslam_match) * B * g.kp_cap));
     ASLAM_CUDA(cudaMalloc(&o->d_match_counts, sizeof(int32_t) * B));
     ASLAM_CUDA(cudaMalloc(&o->d_probs, sizeof(KnnProblem) * B * o->track_splits));
@@ -393,7 +393,7 @@ int aslam_orb_track_batch_async(aslam_orb *o, const uint8_t *images, int n, size
                                                                                   n, splits, cap, rows_per);
     }
     ASLAM_LAUNCH_CHECK();
-    if ((rc = launch_knn2_partial(ctx, o->d_probs, n * splits, cap, o->d_partial, cap))) return rc;
+    if ((rc = launch_knn2_partial(ctx, o->d_probs, n * splits, cap, o->d_partial, cap, splits))) return rc;
     RatioTest rt; rt.ratio = (double)ratio; rt.as_double = 0; rt.disabled = ratio < 0;
     if ((rc = launch_knn2_finish_matches(ctx, o->d_probs, o->d_partial, n, splits, cap, rt, o->d_matches, cap,
                                          o->d_match_counts, nullptr, nullptr))) return rc;
