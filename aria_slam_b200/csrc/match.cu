@@ -78,8 +78,11 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t t0)
     return k16 == 0xffffu ? KEY_EMPTY : ((k16 >> 7) << KEY_IDX_BITS) + t0 + (k16 & 127u);
 }
 
+#ifndef ASLAM_KNN_MINB
+#define ASLAM_KNN_MINB 1
+#endif
 template <bool POPC4>
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, ASLAM_KNN_MINB)
 knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride, const KnnMul M, int merge_div)
 {
     static_assert(KNN_TILE == KNN_THREADS && KNN_TILE == 128 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
@@ -510,7 +513,7 @@ static RatioTest make_ratio(double ratio, int as_double)
 int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets)
 {
     const long long units = (long long)((nq + KNN_QBLOCK - 1) / KNN_QBLOCK) * nsets;      // CTAs per range
-    const double slots = 5.0 * ctx->sm_count;
+    const double slots = (double)(ASLAM_KNN_MINB > 1 ? ASLAM_KNN_MINB : 5) * ctx->sm_count;     // resident CTAs (by registers)
     const long long max_s = nt / 128 < 1 ? 1 : (nt / 128 > 4096 ? 4096 : nt / 128);
     static const int forced = [] { const char *e = getenv("ASLAM_KNN_SPLITS"); return e ? atoi(e) : 0; }();
     if (forced > 0) return (int)(forced < max_s ? forced : max_s);
