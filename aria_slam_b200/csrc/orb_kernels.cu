@@ -143,8 +143,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int &total
 }
 
 // ------------------------------------------------------------------ FAST-9/16 + NMS (A3, A4 filters)
-// One CTA = one tile of 62x30 output pixels = a 64x32 block of scores = a (64+6)x(32+6) block of
-// pixels.  Pixels are staged in shared memory twice as u16 -- copy A at even alignment, copy Bc
+// One CTA = one tile of 62 x FT_OUT_H output pixels = a 64 x (FT_OUT_H+2) block of scores = a
+// (64+6) x (FT_OUT_H+8) block of pixels.  Pixels are staged in shared memory twice as u16 -- copy A at even alignment, copy Bc
 // shifted by one pixel -- so that ANY horizontally adjacent pixel pair is one aligned 32-bit word.
 // The ring test then runs on u16x2 lanes with the 3-input min/max instruction (VIMNMX3.U16x2):
 // two pixels per thread per instruction.
@@ -194,17 +194,20 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
 
     // stage 38 rows x 19 words; each word becomes four u16 in A, and (shifted by one pixel) in Bc
-    // (three passes of 13 rows x 19 words: the word column, its clamp and the shared-memory slot are
-    // per-thread constants, a pass costs two loads, four PRMTs and two stores)
+    // (passes of 13 rows x 19 words: the word column, its clamp and the shared-memory slot are per-thread
+    // constants, a pass costs two loads, four PRMTs and two stores)
+    // rows below y = h - edge feed no output (the NMS of row y reads y-1 .. y+1 and emits y < h - edge only)
+    const int r_end = min(FT_SCORE_H, L.h - g.edge - sy0 + 1);
     {
+        constexpr int PASSES = (FT_PIX_H + 12) / 13;
         const int rr = tid / FA_WORDS, jj = tid - rr * FA_WORDS;
         const int x = min(gx0 + 4 * jj, L.pitch - 4);
         const int xn = min(x + 4, L.pitch - 1);
         if (rr < 13) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < PASSES; ++k) {
                 const int r = rr + 13 * k;
-                if (k < 2 || r < FT_PIX_H) {
+                if (13 * (k + 1) <= FT_PIX_H || r < FT_PIX_H) {
                     const uint8_t *row = img + (size_t)min(sy0 - 3 + r, L.h - 1) * L.pitch;
                     const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + x));
                     const uint32_t nx = __ldg(row + xn);
@@ -227,8 +230,6 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     const int px_x = sx0 + 2 * p;
     const uint32_t neg_thr = ((uint32_t)(px_x < L.w - 3 ? -g.fast_thr : -30000) & 0xffffu) |
                              ((uint32_t)(px_x + 1 < L.w - 3 ? -g.fast_thr : -30000) << 16);
-    // rows below y = h - edge feed no output (the NMS of row y reads y-1 .. y+1 and emits y < h - edge only)
-    const int r_end = min(FT_SCORE_H, L.h - g.edge - sy0 + 1);
 #pragma unroll 1
     for (int r = warp; r < r_end; r += 8) {
         uint32_t v[16];
@@ -270,20 +271,21 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     }
     __syncthreads();
 
-    // 3x3 strict non-max suppression in the same pair layout.  Warp w owns rows 1+4w .. 4+4w, so the
+    // 3x3 strict non-max suppression in the same pair layout.  Warp w owns RPW consecutive rows, so the
     // emitted order is row-major; positions come from ballots (no atomics, deterministic).
     // For a column x: C3 = max of the three rows (centre row included), V = max of rows above/below.
     // neighbours(x) = max(V[x], C3[x-1], C3[x+1]); columns x-1 / x+1 of a pair come from the lanes beside it.
     const uint8_t *mrow = b.mask ? b.mask + (size_t)frame * g.pyr_stride + L.off : nullptr;
-    uint32_t found[4];
-    int off[4];
+    constexpr int RPW = FT_SCORE_H / 8;
+    uint32_t found[RPW];
+    int off[RPW];
     int local = 0;
     const uint32_t col_ok = ((p >= 1 && px_x >= g.edge && px_x < L.w - g.edge) ? 0xffffu : 0u) |
                             ((p <= 30 && px_x + 1 >= g.edge && px_x + 1 < L.w - g.edge) ? 0xffff0000u : 0u);
     const uint32_t resp_bias = (uint32_t)(g.fast_thr - 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = 1 + 4 * warp + k;
+    for (int k = 0; k < RPW; ++k) {
+        const int r = 1 + RPW * warp + k;
         uint32_t e = 0;
         if (r <= FT_OUT_H && sy0 + r < L.h - g.edge) {
             const uint32_t up = S[r - 1][p], cur = S[r][p], dn = S[r + 1][p];
@@ -317,7 +319,7 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     }
     uint32_t *out = b.cand + ((size_t)frame * g.tiles_per_frame + tile) * FT_CAP;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < RPW; ++k)
         if (found[k]) out[base + off[k]] = found[k];
     if (tid == 0) b.cand_cnt[(size_t)frame * g.tiles_per_frame + tile] = (uint32_t)total;
 }
