@@ -95,7 +95,7 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
         L.tiles_y = active ? (rh + FT_OUT_H - 1) / FT_OUT_H : 0;
         L.tile_off = tile_off;
         L.blur_tile_off = blur_off;
-        if (active) blur_off += ((L.w + 127) / 128) * ((L.h + 57) / 58);      // 128x58 blur tiles
+        if (active) blur_off += ((L.w + BL_W - 1) / BL_W) * ((L.h + BL_H - 1) / BL_H);
         tile_off += L.tiles_x * L.tiles_y;
         L.sel_off = sel_off;
         L.sel_cap = L.quota + SEL_TIE_ROOM;

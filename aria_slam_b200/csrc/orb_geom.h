@@ -23,6 +23,16 @@ static_assert(FT_SCORE_H % 8 == 0, "score rows are dealt to 8 warps");
 // No two 3x3-strict maxima are 8-neighbours, so a tile holds at most 31 * FT_OUT_H/2 corners.
 constexpr int FT_CAP = FT_OUT_H <= 32 ? 512 : FT_OUT_H <= 64 ? 1024 : 2048;
 static_assert(31 * ((FT_OUT_H + 1) / 2) <= FT_CAP, "candidate slots per tile");
+// Blur work tile: BL_W x BL_H output pixels from BL_H + 6 row-pass rows held in shared memory as floats
+// (BL_W * (BL_H + 6) * 4 bytes; BL_W a multiple of 8, BL_H + 6 even).
+#ifndef ASLAM_BL_W
+#define ASLAM_BL_W 128
+#endif
+#ifndef ASLAM_BL_H
+#define ASLAM_BL_H 58
+#endif
+constexpr int BL_W = ASLAM_BL_W, BL_H = ASLAM_BL_H, BL_ROWS = BL_H + 6;
+static_assert(BL_W % 8 == 0 && BL_ROWS % 2 == 0 && BL_W * BL_ROWS * 4 <= 48 * 1024, "blur tile");
 constexpr int SEL_TIE_ROOM = 64;   // extra output rows per level for tied Harris responses
 
 struct LevelGeom {

@@ -349,7 +349,7 @@ __device__ __forceinline__ int reflect101(int i, int n)
 }
 
 // v4: one launch covers every level (tile table in LevelGeom::blur_tile_off); a CTA produces a
-// 128x58 tile from 64 staged rows.
+// BL_W x BL_H tile (128x58; 64x122 and 32x250 measured slower) from BL_H + 6 staged rows.
 //  * Row pass: a thread takes 8 outputs of TWO adjacent rows.  It reads the 16 aligned bytes around
 //    them straight from global memory (L1-resident), converts with the exponent trick (u8 -> f32
 //    without the conversion unit) and runs the 7 taps on packed f32x2 lanes (FFMA2: one lane per
@@ -360,7 +360,6 @@ __device__ __forceinline__ int reflect101(int i, int n)
 //  * Columns at or beyond row_fused_end / col_fused_end (the build's scalar tail) take a scalar
 //    path with separately rounded products.  (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2,
 //    so packed arithmetic is used only where fusion is the wanted behaviour.)
-constexpr int BL_W = 128, BL_H = 58, BL_ROWS = BL_H + 6;
 
 __device__ __forceinline__ uint32_t u8_magic(uint32_t word, int k)
 {
@@ -528,8 +527,8 @@ blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
     const int nc = min(BL_W / 4, (L.w - x0 + 3) / 4);                     // column groups inside the image
     const int cf = min(nc, max(0, (L.col_fused_end - x0) / 4));           // [0, cf) fused, [cf, nc) unfused
 #pragma unroll 1
-    for (int t = tid; t < 32 * ((BL_H + 3) / 4); t += 256) {
-        const int ci = t & 31, r0 = (t >> 5) * 4;
+    for (int t = tid; t < (BL_W / 4) * ((BL_H + 3) / 4); t += 256) {
+        const int ci = t % (BL_W / 4), r0 = (t / (BL_W / 4)) * 4;
         if (ci >= cf || y0 + r0 >= L.h) continue;
         blur_col_task<true>(R, ci * 4, r0, min(4, min(BL_H - r0, L.h - y0 - r0)), T, dst + (size_t)(y0 + r0) * L.pitch + x0 + ci * 4, L.pitch);
     }
