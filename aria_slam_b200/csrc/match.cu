@@ -506,26 +506,31 @@ static RatioTest make_ratio(double ratio, int as_double)
     return rt;
 }
 
-// How many row ranges to cut a train set of nt rows into.  The scan kernel keeps 5 CTAs of equal work
-// resident per SM, so the grid should be a whole number of such waves (a 1.4-wave grid runs as long as
+// How many row ranges to cut a train set of nt rows into.  The scan kernel keeps a few CTAs of equal work
+// resident per SM (occupancy API), so the grid should be a whole number of such waves (a 1.4-wave grid runs as long as
 // a 2-wave grid): among the cuts that leave at least 128 rows per range, take the one with the best
 // wave efficiency, preferring fewer ranges on ties.
 int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets)
 {
     const long long units = (long long)((nq + KNN_QBLOCK - 1) / KNN_QBLOCK) * nsets;      // CTAs per range
-    const double slots = (double)(ASLAM_KNN_MINB > 1 ? ASLAM_KNN_MINB : 5) * ctx->sm_count;     // resident CTAs (by registers)
+    static const int ctas_per_sm = [] {                // resident scan CTAs per SM, as the compiler's register count allows
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, knn2_partial_v2_kernel<true>, KNN_THREADS, 0) != cudaSuccess || n < 1) n = 4;
+        return n;
+    }();
+    const double slots = (double)ctas_per_sm * ctx->sm_count;
     const long long max_s = nt / 128 < 1 ? 1 : (nt / 128 > 4096 ? 4096 : nt / 128);
     static const int forced = [] { const char *e = getenv("ASLAM_KNN_SPLITS"); return e ? atoi(e) : 0; }();
     if (forced > 0) return (int)(forced < max_s ? forced : max_s);
-    // first choice: the coarsest cut with at least ASLAM_KNN_WAVES (6) nearly full waves -- CTAs of several
+    // first choice: the coarsest cut with at least ASLAM_KNN_WAVES (10) nearly full waves -- CTAs of several
     // waves run out of phase, which keeps the POPC pipe busier than one wave of CTAs in lock step
-    static const int min_waves = [] { const char *e = getenv("ASLAM_KNN_WAVES"); return e ? atoi(e) : 6; }();
+    static const int min_waves = [] { const char *e = getenv("ASLAM_KNN_WAVES"); return e ? atoi(e) : 10; }();
     int best = 1;
     double best_score = -1.0;
     for (long long s = 1; s <= max_s; ++s) {
         const double waves = (double)(units * s) / slots;
         const double eff = waves / ceil(waves);
-        if (waves >= (double)min_waves && eff >= 0.97) return (int)s;
+        if (waves >= (double)min_waves && eff >= 0.95) return (int)s;
         const double score = eff * (waves < 4.0 ? 0.8 + 0.05 * waves : 1.0);
         if (score > best_score + 1e-9) { best_score = score; best = (int)s; }
     }

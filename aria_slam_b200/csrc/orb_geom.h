@@ -12,14 +12,16 @@ constexpr int ORB_MAX_LEVELS = 8;
 // FAST work tile: 62 x FT_OUT_H output pixels from a 64 x (FT_OUT_H+2) score block and a 70 x (FT_OUT_H+8)
 // pixel block; FT_OUT_H + 2 must be a multiple of 8 (rows are dealt to 8 warps).
 #ifndef ASLAM_FT_OUT_H
-#define ASLAM_FT_OUT_H 94
+#define ASLAM_FT_OUT_H 62
 #endif
 constexpr int FT_OUT_W = 62, FT_OUT_H = ASLAM_FT_OUT_H;
 constexpr int FT_SCORE_W = 64, FT_SCORE_H = FT_OUT_H + 2;
 constexpr int FT_PIX_W = 70, FT_PIX_H = FT_OUT_H + 8;
 static_assert(FT_SCORE_H % 8 == 0, "score rows are dealt to 8 warps");
-// Measured on B200 (ms per 256 frames of 752x480): 30 rows 1.08, 46 rows 0.99, 62 rows 0.96, 94 rows 0.92 -- taller
-// tiles amortise the per-CTA prologue and the 8 halo rows; 94 is what fits the 48 KB of static shared memory.
+// Measured on B200 (ms per 256 frames of 752x480, kernel alone): 30 rows 1.08, 46 rows 0.99, 62 rows 0.96, 94 rows
+// 0.92 -- taller tiles amortise the per-CTA prologue and the 8 halo rows.  With 8 frame streams overlapping,
+// 62 rows (30 KB of shared memory per CTA) is fastest overall: 94-row CTAs (46 KB) crowd the other streams'
+// kernels out of the SMs (frames/s: 30 rows 74.9 k, 46 rows 77.2 k, 62 rows 77.6 k, 94 rows 72.0 k).
 // No two 3x3-strict maxima are 8-neighbours, so a tile holds at most 31 * FT_OUT_H/2 corners.
 constexpr int FT_CAP = FT_OUT_H <= 32 ? 512 : FT_OUT_H <= 64 ? 1024 : 2048;
 static_assert(31 * ((FT_OUT_H + 1) / 2) <= FT_CAP, "candidate slots per tile");

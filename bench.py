@@ -148,6 +148,26 @@ def cpu_baseline_loop(db, q, rows=100_000):
             "sample": "cv2 BFMatcher knnMatch(k=2) of %d queries against %d of the %d rows, time scaled x%d" % (len(q), rows, len(db), len(db) // rows)}
 
 
+def single_frame_latency(ctx, frames, reps=50):
+    """C1-like use: one 752x480 frame through IFeatureExtractor::extract (host image in, host keypoints and
+    descriptors out) and one IMatcher::match against the previous frame, 1000 keypoints; wall clock."""
+    from aria_slam_b200.frontend import OrbB200Extractor, B200Matcher, Frame
+    ex, m = OrbB200Extractor(1000, ctx), B200Matcher(ctx)
+    fa, fb = Frame(), Frame()
+    for _ in range(5):
+        ex.extract(frames[0], W, H, fa); ex.extract(frames[1], W, H, fb); mm = []; m.match(fb, fa, mm, 0.75)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ex.extract(frames[1], W, H, fb)
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        mm = []; m.match(fb, fa, mm, 0.75)
+    t2 = time.perf_counter()
+    ex.close()
+    return {"config": "C1: 752x480, ORB 1000 kpts, kNN2 + 0.75 ratio, one frame per call", "extract_ms": (t1 - t0) / reps * 1e3,
+            "match_ms": (t2 - t1) / reps * 1e3, "keypoints": fb.numKeypoints(), "matches": len(mm)}
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -396,6 +416,7 @@ def run_ours(args):
                        "pairs_per_s": LOOP_NQ * float(LOOP_DB_ROWS) * K / (loop_ms * 1e-3)},
     }
     if world == 1:
+        out["latency_single_frame"] = single_frame_latency(ctx, frames)
         out["cpu_baseline"] = cpu_baseline_frames(frames)
         out["loop_query"]["cpu_baseline"] = cpu_baseline_loop(db, q)
     emit(out)

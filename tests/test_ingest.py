@@ -113,6 +113,22 @@ def test_reader_decodes_every_png_filter_and_follows_the_reference_reader(tmp_pa
     assert abs(g[4] - np.cos(0.1)) < 1e-9 and abs(g[7] - np.sin(0.1)) < 1e-9
 
 
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 5), (97, 13), (640, 7)])
+def test_reader_handles_ragged_frame_sizes(tmp_path, w, h):
+    rs = np.random.RandomState(w * 131 + h)
+    frames = [rs.randint(0, 256, (h, w), dtype=np.uint8) for _ in range(2)]
+    stamps = write_dataset(str(tmp_path / "ds"), frames, shuffle=False)
+    out = tmp_path / "out.bin"
+    r = subprocess.run([EXE, "read", str(tmp_path / "ds"), str(out)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "2 frames" in r.stdout, r.stdout
+    buf = out.read_bytes()
+    pos = 12 + 32
+    for i in range(2):
+        ts, fw, fh, _ = struct.unpack_from("<d3i", buf, pos); pos += 20
+        img = np.frombuffer(buf, np.uint8, fw * fh, pos).reshape(fh, fw); pos += fw * fh
+        assert (fw, fh) == (w, h) and (img == frames[i]).all()
+
+
 def test_png_decoder_rejects_what_it_does_not_support(tmp_path):
     frames = frames_for_test(1, 64, 48, 9)
     root = tmp_path / "ds"
