@@ -93,3 +93,40 @@ def test_pyramid_and_orb_random_sizes(ctx, oracle, w, h, seed):
     o1, o2 = np.lexsort((k["x"], k["y"], k["octave"])), np.lexsort((ko["x"], ko["y"], ko["octave"]))
     assert (d[o1] == do[o2]).all()
     tr.close()
+
+
+def _checker(w, h, s):
+    y, x = np.mgrid[0:h, 0:w]
+    return (((x // s) + (y // s)) % 2 * 200 + 20).astype(np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["checker16", "checker40", "ramp", "lowcontrast", "saturated"])
+def test_structured_frames_with_ties_match_oracle(ctx, oracle, kind):
+    """Inputs with mass ties (equal FAST scores, equal Harris responses) and flat regions: the tie-inclusive
+    retainBest cuts, the strict NMS and the empty levels must all follow cv::ORB."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import OrbB200Extractor, Frame
+    w, h, n = 752, 480, 1000
+    if kind.startswith("checker"):
+        img = _checker(w, h, int(kind[7:]))
+    elif kind == "ramp":
+        y, x = np.mgrid[0:h, 0:w]
+        img = ((x + 2 * y) % 256).astype(np.uint8)                 # sawtooth: long straight edges, no corners off the seams
+    elif kind == "lowcontrast":
+        img = (100 + synth.frame(w, h, 31) // 4).astype(np.uint8)   # contrast near the FAST threshold: levels below quota
+    else:
+        img = np.clip(synth.frame(w, h, 32).astype(np.int32) * 3, 0, 255).astype(np.uint8)   # large saturated areas
+    ko, do = oracle.orb(img, n)
+    ex = OrbB200Extractor(n, ctx)
+    f = Frame()
+    ex.extract(img, w, h, f)
+    assert f.numKeypoints() == len(ko)
+    key = lambda k: sorted(zip(k["octave"].tolist(), k["x"].tolist(), k["y"].tolist()))
+    assert key(f.keypoints) == key(ko)
+    if len(ko):
+        og = np.lexsort((f.keypoints["x"], f.keypoints["y"], f.keypoints["octave"]))
+        oo = np.lexsort((ko["x"], ko["y"], ko["octave"]))
+        assert (f.keypoints["response"][og] == ko["response"][oo]).all() and (f.keypoints["angle"][og] == ko["angle"][oo]).all()
+        assert (f.descriptors.reshape(-1, 32)[og] == do[oo]).all(1).mean() >= 0.99
+    ex.close()
