@@ -172,8 +172,17 @@ __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { r
 #ifndef ASLAM_FAST_MINB
 #define ASLAM_FAST_MINB 5
 #endif
+struct FastMul { uint32_t one, minus1, bias; };      // 1, 0xffffffff, 0x01000100
+
+__device__ __forceinline__ uint32_t imad32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 __global__ void __launch_bounds__(256, ASLAM_FAST_MINB)
-fast_kernel(OrbGeom g, OrbBuffers b)
+fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
 {
     __shared__ __align__(16) uint16_t A[FT_PIX_H][FA_PITCH];
     __shared__ __align__(16) uint16_t Bc[FT_PIX_H][FA_PITCH];
@@ -228,8 +237,8 @@ fast_kernel(OrbGeom g, OrbBuffers b)
     // The score block holds s - t (>= 1 for corners, 0 otherwise): same order for the NMS, and the
     // response max(A,B) - 1 is restored at emit time.  neg_thr: -t per valid u16 lane, -30000 otherwise.
     const int px_x = sx0 + 2 * p;
-    const uint32_t neg_thr = ((uint32_t)(px_x < L.w - 3 ? -g.fast_thr : -30000) & 0xffffu) |
-                             ((uint32_t)(px_x + 1 < L.w - 3 ? -g.fast_thr : -30000) << 16);
+    const uint32_t neg_thr = ((uint32_t)(px_x < L.w - 3 ? -g.fast_thr - 256 : -30000) & 0xffffu) |
+                             ((uint32_t)(px_x + 1 < L.w - 3 ? -g.fast_thr - 256 : -30000) << 16);     // incl. the bias below
 #pragma unroll 1
     for (int r = warp; r < r_end; r += 8) {
         uint32_t v[16];
@@ -264,10 +273,15 @@ fast_kernel(OrbGeom g, OrbBuffers b)
         mx = max3(mx, max3(arc_min[9], arc_min[10], arc_min[11]), max3(arc_min[12], arc_min[13], arc_min[14]));
         mx = __vmaxu2(mx, arc_min[15]);
 
-        // per u16 lane: s = max(c - mn, mx - c); stored value = max(s - t, 0)
-        const uint32_t a = __vsub2(c, mn), bq = __vsub2(mx, c);
-        const uint32_t sc = __viaddmax_s16x2_relu(__vmaxs2(a, bq), neg_thr, 0u);
-        S[r][p] = sy0 + r < L.h - 3 ? sc : 0u;
+        // per u16 lane: s = max(c - mn, mx - c); stored value = max(s - t, 0).  The two differences are taken
+        // with a +256 bias per lane (no borrow between lanes: every lane stays in [1, 511]) as 32-bit IMADs
+        // whose multipliers are kernel parameters -- FMA pipe; the ALU pipe is this loop's bottleneck.
+        // (rows r < r_end lie above y = h - edge, inside cv::FAST's [3, h-3) range)
+        const uint32_t cb = imad32(c, M.one, M.bias);              // c + 256
+        const uint32_t cn = imad32(c, M.minus1, M.bias);           // 256 - c
+        const uint32_t a = imad32(mn, M.minus1, cb);               // c - mn + 256
+        const uint32_t bq = imad32(mx, M.one, cn);                 // mx - c + 256
+        S[r][p] = __viaddmax_s16x2_relu(__vmaxu2(a, bq), neg_thr, 0u);
     }
     __syncthreads();
 
@@ -329,7 +343,7 @@ int launch_fast(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfram
     if (g.tiles_per_frame == 0) return ASLAM_OK;
     dim3 grid(g.tiles_per_frame, nframes);
     ProfScope ps(ctx, PK_FAST);
-    fast_kernel<<<grid, 256, 0, ctx->stream>>>(g, b);
+    fast_kernel<<<grid, 256, 0, ctx->stream>>>(g, b, FastMul{1u, 0xffffffffu, 0x01000100u});
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
