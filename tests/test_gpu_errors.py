@@ -1,0 +1,82 @@
+"""Error behaviour of the C ABI (include/aslam_b200.h): every misuse is a status code + message, never a
+crash or a silent fallback; results after an error-free call are unaffected by a previous failed one."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(**kw):
+    from aria_slam_b200 import _lib
+    p = _lib.OrbParams()
+    _lib.lib().aslam_orb_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@pytest.mark.parametrize("kw,w,h,batch", [
+    (dict(nfeatures=-1), 640, 480, 1), (dict(nlevels=9), 640, 480, 1), (dict(nlevels=0), 640, 480, 1),
+    (dict(scale_factor=1.0), 640, 480, 1), (dict(scale_factor=2.5), 640, 480, 1), (dict(edge_threshold=10), 640, 480, 1),
+    (dict(wta_k=3), 640, 480, 1), (dict(patch_size=15), 640, 480, 1), (dict(fast_threshold=0), 640, 480, 1),
+    (dict(), 0, 480, 1), (dict(), 640, 5000, 1), (dict(), 640, 480, 0)])
+def test_orb_create_rejects_bad_arguments(ctx, kw, w, h, batch):
+    from aria_slam_b200 import _lib
+    hnd = C.c_void_p()
+    rc = _lib.lib().aslam_orb_create(ctx.h, C.byref(_params(**kw)), w, h, batch, C.byref(hnd))
+    assert rc == _lib.E_INVALID and not hnd.value
+    assert len(_lib.lib().aslam_last_error()) > 0
+
+
+def test_call_order_violations_are_state_errors(ctx):
+    from aria_slam_b200 import _lib, synth
+    L = _lib.lib()
+    hnd = C.c_void_p()
+    assert L.aslam_orb_create(ctx.h, C.byref(_params(nfeatures=300)), 320, 240, 2, C.byref(hnd)) == _lib.OK
+    cap = L.aslam_orb_capacity(hnd)
+    kps = np.zeros((2, cap), _lib.KP_DTYPE); desc = np.zeros((2, cap, 32), np.uint8); cnt = np.zeros(2, np.int32)
+    assert L.aslam_orb_sync(hnd, _lib.ptr(kps), _lib.ptr(desc), _lib.ptr(cnt)) == _lib.E_STATE        # nothing pending
+    img = synth.frame(320, 240, 3)
+    assert L.aslam_orb_extract_async(hnd, _lib.ptr(img), 320, 240, 320, None, None, 0) == _lib.OK
+    assert L.aslam_orb_extract_async(hnd, _lib.ptr(img), 320, 240, 320, None, None, 0) == _lib.E_STATE  # already pending
+    assert L.aslam_orb_set_max_features(hnd, 100) == _lib.E_STATE
+    assert L.aslam_orb_sync(hnd, _lib.ptr(kps), _lib.ptr(desc), _lib.ptr(cnt)) == _lib.OK
+    first = (int(cnt[0]), kps[0, :cnt[0]].copy(), desc[0, :cnt[0]].copy())
+    assert L.aslam_orb_extract_async(hnd, _lib.ptr(img), 640, 240, 640, None, None, 0) == _lib.E_INVALID  # wrong frame size
+    imgs = np.stack([img, img, img])
+    assert L.aslam_orb_extract_batch_async(hnd, _lib.ptr(imgs), 3, 320 * 240, 320, None) == _lib.E_INVALID    # above max_batch
+    # the handle still works and gives the same answer
+    assert L.aslam_orb_extract_async(hnd, _lib.ptr(img), 320, 240, 320, None, None, 0) == _lib.OK
+    assert L.aslam_orb_sync(hnd, _lib.ptr(kps), _lib.ptr(desc), _lib.ptr(cnt)) == _lib.OK
+    assert int(cnt[0]) == first[0] and (kps[0, :cnt[0]] == first[1]).all() and (desc[0, :cnt[0]] == first[2]).all()
+    L.aslam_orb_destroy(hnd)
+
+
+def test_matcher_argument_errors_and_degenerate_sizes(ctx):
+    from aria_slam_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(3)
+    q = rs.randint(0, 256, (10, 32), dtype=np.uint8); t = rs.randint(0, 256, (1, 32), dtype=np.uint8)
+    out = np.zeros(16, _lib.MATCH_DTYPE); n = C.c_int(-1)
+    # one train row: no second neighbour, so no match (CudaMatcher.cpp:60) -- not an error
+    assert L.aslam_match_knn2(ctx.h, _lib.ptr(q), 10, _lib.ptr(t), 1, C.c_float(0.75), _lib.ptr(out), C.byref(n)) == _lib.OK and n.value == 0
+    assert L.aslam_match_knn2(ctx.h, _lib.ptr(q), 0, _lib.ptr(t), 1, C.c_float(0.75), _lib.ptr(out), C.byref(n)) == _lib.OK and n.value == 0
+    t5 = rs.randint(0, 256, (5, 32), dtype=np.uint8)
+    assert L.aslam_match_knn2(ctx.h, None, 10, _lib.ptr(t5), 5, C.c_float(0.75), _lib.ptr(out), C.byref(n)) == _lib.E_INVALID
+    assert L.aslam_match_knn2(ctx.h, _lib.ptr(q), -1, _lib.ptr(t5), 5, C.c_float(0.75), _lib.ptr(out), C.byref(n)) == _lib.E_INVALID
+    assert L.aslam_match_knn2(None, _lib.ptr(q), 10, _lib.ptr(t5), 5, C.c_float(0.75), _lib.ptr(out), C.byref(n)) == _lib.E_INVALID
+
+
+def test_loopdb_capacity_is_an_error_not_a_truncation(ctx):
+    from aria_slam_b200 import _lib
+    from aria_slam_b200.frontend import LoopDB
+    rs = np.random.RandomState(4)
+    db = LoopDB(ctx, 1000, 4)
+    db.add(rs.randint(0, 256, (600, 32), dtype=np.uint8), 0)
+    with pytest.raises(_lib.AslamError) as e:
+        db.add(rs.randint(0, 256, (1200, 32), dtype=np.uint8), 1)      # one keyframe larger than the whole store
+    assert e.value.code in (_lib.E_INVALID, _lib.E_OVERFLOW, _lib.E_NOMEM)
+    assert db.num_keyframes == 1 and db.num_rows == 600
+    db.close()
