@@ -41,12 +41,13 @@ __device__ __forceinline__ HRow resize_hrow(uint32_t w0, uint32_t w1, uint32_t w
 #endif
 constexpr int RS_ROWS = ASLAM_RS_ROWS;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
               LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs, int thresh)
 {
-    const int cg = blockIdx.x * 32 + threadIdx.x;
-    const int y0 = (blockIdx.y * 4 + threadIdx.y) * RS_ROWS;
+    // a CTA's warps sit side by side on the same strip of rows, so the CTA reads and writes whole row segments
+    const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * RS_ROWS;
     if (cg * 4 >= D.w || y0 >= D.h) return;
     // CTA-uniform bases + 32-bit per-thread offsets (a frame's pyramid is far below 4 GB)
     const uint32_t *src = reinterpret_cast<const uint32_t *>(srcb + (size_t)blockIdx.z * stride + S.off);
@@ -109,7 +110,8 @@ int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, i
 {
     const LevelGeom &D = g.lv[level], &S = g.lv[level - 1];
     const int cgs = (D.w + 3) / 4;
-    dim3 grid((cgs + 31) / 32, (D.h + 4 * RS_ROWS - 1) / (4 * RS_ROWS), nframes), block(32, 4);
+    const int warps = min(8, (cgs + 31) / 32);
+    dim3 grid((cgs + 32 * warps - 1) / (32 * warps), (D.h + RS_ROWS - 1) / RS_ROWS, nframes), block(32 * warps);
     uint8_t *base = is_mask ? b.mask : b.pyr;
     ProfScope ps(ctx, PK_RESIZE);
     resize_kernel<<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, is_mask ? 1 : 0);
