@@ -2,6 +2,7 @@
 // (they need Eigen3, which this image lacks).  API-identical restatement of
 //   include/core/Types.hpp:9-31,34-45,48-64,67-88,91-95,97-121
 //   include/interfaces/{IFeatureExtractor,IMatcher,ILoopDetector,IObjectDetector,ISensorFusion,IMapper}.hpp
+//   include/interfaces/IAriaDevice.hpp:9-61
 //   include/pipeline/SlamPipeline.hpp:15-106 and include/factory/PipelineFactory.hpp:9-46
 // so that the adapters and the pipeline bodies compile and can be exercised here; inside the
 // reference tree, build with -DARIA_UPSTREAM_HEADERS and none of this is seen.
@@ -169,6 +170,34 @@ public:
     virtual size_t size() const = 0;
 };
 using MapperPtr = std::unique_ptr<IMapper>;
+
+// include/interfaces/IAriaDevice.hpp:9-61
+enum class AriaCamera { RGB, SLAM_LEFT, SLAM_RIGHT };
+
+struct AriaImage {
+    const uint8_t* data;
+    int width, height, channels;
+    uint64_t timestamp_ns;
+    AriaCamera camera;
+};
+
+using ImageCallback = std::function<void(const AriaImage&)>;
+using ImuCallback = std::function<void(const core::ImuMeasurement&)>;
+
+class IAriaDevice {
+public:
+    virtual ~IAriaDevice() = default;
+    virtual bool connect(const std::string& ip_address = "") = 0;
+    virtual void disconnect() = 0;
+    virtual bool isConnected() const = 0;
+    virtual bool startStreaming(int cameras = 0x7) = 0;
+    virtual void stopStreaming() = 0;
+    virtual void setImageCallback(ImageCallback callback) = 0;
+    virtual void setImuCallback(ImuCallback callback) = 0;
+    virtual bool getCalibration(AriaCamera camera, float& fx, float& fy, float& cx, float& cy) const = 0;
+    virtual void spinOnce() = 0;
+};
+using AriaDevicePtr = std::unique_ptr<IAriaDevice>;
 
 }  // namespace aria::interfaces
 

@@ -20,7 +20,8 @@ def test_adapters_compile_against_reference_headers():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DARIA_UPSTREAM_HEADERS", "-I" + REF_INC,
                         "-I" + os.path.join(AD, "compat"),
                         os.path.join(AD, "b200_adapters.cpp"), os.path.join(AD, "selftest.cpp"),
-                        os.path.join(AD, "slam_pipeline.cpp"), os.path.join(AD, "pipeline_selftest.cpp")],
+                        os.path.join(AD, "slam_pipeline.cpp"), os.path.join(AD, "pipeline_selftest.cpp"),
+                        os.path.join(AD, "aria_stereo.cpp"), os.path.join(AD, "stereo_selftest.cpp")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
 
@@ -78,6 +79,50 @@ def test_pipeline_gpu_mode_matches_oracle(tmp_path, oracle):
             mine = np.stack([matches["q"], matches["t"], matches["d"].astype(np.int32)], 1)
             assert mine.shape == ref.shape and (mine == ref).all()
             assert len(ref) >= 8                                       # enough for the motion step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pairs_per_batch", [1, 3])
+def test_aria_stereo_frontend_matches_oracle(tmp_path, oracle, pairs_per_batch):
+    """BASELINE config 4 through the IAriaDevice callback shape: SLAM_LEFT/SLAM_RIGHT 640x480 frames paired by
+    timestamp, both extracted and left matched against right in one batched call."""
+    from aria_slam_b200 import synth
+    from oracle.oracle import KP_DTYPE
+    w, h, n, npairs = 640, 480, 1000, 4
+    pairs = []
+    for i in range(npairs):
+        left = synth.frame(w, h, 4000 + i)
+        pairs.append((left, synth.shifted(left, dx=12, dy=0, sigma=1.0, seed=4100 + i)))
+    raw = tmp_path / "in.raw"
+    raw.write_bytes(b"".join(l.tobytes() + r.tobytes() for l, r in pairs))
+    out = tmp_path / "out.bin"
+    r = subprocess.run([os.path.join(AD, "stereo_selftest"), str(raw), str(w), str(h), str(npairs), str(n), str(pairs_per_batch), str(out)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    buf = out.read_bytes()
+    pos = 0
+    key = lambda k: sorted(zip(k["octave"].tolist(), k["x"].tolist(), k["y"].tolist()))
+    for i, (left, right) in enumerate(pairs):
+        (ts,) = struct.unpack_from("<Q", buf, pos); pos += 8
+        assert ts == 1000000000 + 33333333 * i
+        sides = []
+        for img in (left, right):
+            (k,) = struct.unpack_from("<i", buf, pos); pos += 4
+            kps = np.frombuffer(buf, KP_DTYPE, k, pos); pos += 24 * k
+            desc = np.frombuffer(buf, np.uint8, 32 * k, pos).reshape(k, 32); pos += 32 * k
+            ko, _ = oracle.orb(img, n)
+            assert key(kps) == key(ko)
+            sides.append((kps, desc))
+        (m,) = struct.unpack_from("<i", buf, pos); pos += 4
+        matches = np.frombuffer(buf, np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), m, pos); pos += 12 * m
+        idx, dist = oracle.knn2(sides[0][1], sides[1][1])              # left = query, right = train
+        ref = oracle.ratio_matches(idx, dist, 3, 4)
+        got = np.stack([matches["q"], matches["t"], matches["d"].astype(np.int32)], 1)
+        assert got.shape == ref.shape and (got == ref).all()
+        lvl0 = [(a, b) for a, b, _ in got if sides[0][0]["octave"][a] == 0 and sides[1][0]["octave"][b] == 0]
+        dx = np.array([sides[1][0]["x"][b] - sides[0][0]["x"][a] for a, b in lvl0])
+        assert len(lvl0) > 50 and (np.abs(dx - 12) <= 1).mean() > 0.9
+    assert pos == len(buf)
 
 
 @pytest.mark.gpu
