@@ -28,6 +28,10 @@ struct aslam_loopdb {
     int32_t *d_good = nullptr; int32_t *h_good = nullptr; int good_cap = 0;
     uint64_t *d_top2 = nullptr; int top2_cap = 0;
     unsigned int *d_arrival = nullptr;   // CTA arrival counter of the fused exchange kernel
+    // flat-query fast path: the row-range table of the last query (rebuilt only when the query buffer, the
+    // live region or the cut changes) and whether the merged result slots were left holding KEY_EMPTY
+    const uint8_t *tab_q = nullptr; int tab_nq = 0, tab_splits = 0; int64_t tab_head = -1, tab_rows = -1;
+    bool armed = false; int armed_stride = 0;
 };
 
 static int db_reserve(aslam_loopdb *db, int nq, int nprobs, size_t partial_elems)
@@ -187,6 +191,7 @@ int aslam_loopdb_query_segmented(aslam_loopdb *db, const uint8_t *q, int nq, dou
         P.q = db->d_q; P.t = db->d_rows + db->segs[s].start * 32;
         P.nq_dev = nullptr; P.nt_dev = nullptr; P.nq = nq; P.nt = db->segs[s].n; P.t_lo = 0; P.t_hi = db->segs[s].n;
     }
+    db->tab_splits = 0; db->armed = false;      // the flat query's table and preset slots are overwritten here
     ASLAM_CUDA(cudaMemcpyAsync(db->d_probs, db->h_probs, sizeof(KnnProblem) * (size_t)nseg, cudaMemcpyHostToDevice, ctx->stream));
     rc = launch_knn2_partial(ctx, db->d_probs, nseg, nq, db->d_partial, q_stride);
     if (rc) return rc;
@@ -209,29 +214,45 @@ static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_
     if (rows > KNN_MAX_ROWS) return fail(ASLAM_E_INVALID, "shard holds %lld rows; at most %d per shard", (long long)rows, KNN_MAX_ROWS);
     const int q_stride = (int)align_up((size_t)nq, 64);
     int splits = 0;
+    bool rearm = false;
     if (rows > 0) {
         splits = choose_splits(ctx, nq, rows, 1);
+        const KnnProblem *probs_before = db->d_probs;
+        const uint2 *partial_before = db->d_partial;
         int rc = db_reserve(db, 0, splits, (size_t)splits * q_stride);
         if (rc) return rc;
-        rc = launch_fill_split_problems(ctx, db->d_probs, d_q, db->d_rows + db->head * 32, nullptr, nullptr, nq, (int)rows, splits);
+        if (db->d_probs != probs_before) db->tab_splits = 0;
+        if (db->d_partial != partial_before) db->armed = false;
+        if (db->tab_q != d_q || db->tab_nq != nq || db->tab_splits != splits || db->tab_head != db->head || db->tab_rows != rows) {
+            rc = launch_fill_split_problems(ctx, db->d_probs, d_q, db->d_rows + db->head * 32, nullptr, nullptr, nq, (int)rows, splits);
+            if (rc) return rc;
+            db->tab_q = d_q; db->tab_nq = nq; db->tab_splits = splits; db->tab_head = db->head; db->tab_rows = rows;
+        }
+        const bool armed = db->armed && db->armed_stride == q_stride;
+        db->armed = false;
+        rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride, splits, armed);
         if (rc) return rc;
-        rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride, splits);
-        if (rc) return rc;
+        rearm = splits > 1;                     // a single range writes its slot directly; nothing to preset
     } else {
-        int rc = db_reserve(db, 0, 1, 1);       // an empty shard still reports (empty, empty) per query
+        int rc = db_reserve(db, 0, 1, 1);       // an empty shard reports (empty, empty) per query
         if (rc) return rc;
     }
+    const int nslots = rows > 0 ? 1 : 0;
+    int rc;
     if (d_peer_bufs && round) {
         if (!db->d_arrival) {
             ASLAM_CUDA(cudaMalloc(&db->d_arrival, sizeof(unsigned int)));
             ASLAM_CUDA(cudaMemsetAsync(db->d_arrival, 0, sizeof(unsigned int), ctx->stream));
         }
-        return launch_knn2_finish_exchange(ctx, db->d_partial, 1, nq, q_stride, db->row_base, d_peer_bufs, nparts,
-                                           my_part, round, db->d_arrival, d_top2);
+        rc = launch_knn2_finish_exchange(ctx, db->d_partial, nslots, nq, q_stride, db->row_base, d_peer_bufs, nparts,
+                                         my_part, round, db->d_arrival, d_top2, rearm);
+    } else if (d_peer_bufs) {
+        rc = launch_knn2_finish_global_push(ctx, db->d_partial, nslots, nq, q_stride, db->row_base, d_peer_bufs, nparts, my_part, rearm);
+    } else {
+        rc = launch_knn2_finish_global(ctx, db->d_partial, nslots, nq, q_stride, db->row_base, d_top2, rearm);
     }
-    if (d_peer_bufs)
-        return launch_knn2_finish_global_push(ctx, db->d_partial, 1, nq, q_stride, db->row_base, d_peer_bufs, nparts, my_part);
-    return launch_knn2_finish_global(ctx, db->d_partial, 1, nq, q_stride, db->row_base, d_top2);
+    if (rc == ASLAM_OK && rearm) { db->armed = true; db->armed_stride = q_stride; }
+    return rc;
 }
 
 int aslam_loopdb_query_global_device(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_t *d_top2)

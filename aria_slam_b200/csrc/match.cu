@@ -282,13 +282,14 @@ knn2_finish_counts_kernel(const KnnProblem *__restrict__ probs, const uint2 *__r
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
-knn2_finish_global_kernel(const uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
-                          long long row_base, unsigned long long *__restrict__ top2)
+knn2_finish_global_kernel(uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
+                          long long row_base, unsigned long long *__restrict__ top2, int rearm)
 {
     const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
     if (q >= nq) return;
     uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
     for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
+    if (rearm && nslots) partial[q] = make_uint2(KEY_EMPTY, KEY_EMPTY);       // the merged slot is ready for the next scan
     const unsigned long long e = ~0ull;
     top2[2 * (size_t)q] = k1 == KEY_EMPTY ? e
         : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
@@ -299,14 +300,15 @@ knn2_finish_global_kernel(const uint2 *__restrict__ partial, int nslots, int nq,
 // Fused finish + all-gather: the merged keys of this shard go directly into every peer's gather buffer
 // with plain 16-byte stores to peer-mapped addresses (NVLink / NVSwitch); one thread = one query.
 __global__ void __launch_bounds__(FIN_THREADS)
-knn2_finish_global_push_kernel(const uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
+knn2_finish_global_push_kernel(uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
                                long long row_base, unsigned long long *const *__restrict__ peer_bufs,
-                               int nparts, int my_part)
+                               int nparts, int my_part, int rearm)
 {
     const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
     if (q >= nq) return;
     uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
     for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
+    if (rearm && nslots) partial[q] = make_uint2(KEY_EMPTY, KEY_EMPTY);       // the merged slot is ready for the next scan
     const unsigned long long e = ~0ull;
     ulonglong2 v;
     v.x = k1 == KEY_EMPTY ? e : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
@@ -329,9 +331,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
-knn2_finish_exchange_kernel(const uint2 *__restrict__ partial, int nslots, int nq, int q_stride, long long row_base,
+knn2_finish_exchange_kernel(uint2 *__restrict__ partial, int nslots, int nq, int q_stride, long long row_base,
                             unsigned long long *const *__restrict__ peer_bufs, int nparts, int my_part,
-                            unsigned long long round, unsigned int *arrival, unsigned long long *__restrict__ out)
+                            unsigned long long round, unsigned int *arrival, unsigned long long *__restrict__ out, int rearm)
 {
     const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
     const int half = (int)(round & 1ull);
@@ -341,6 +343,7 @@ knn2_finish_exchange_kernel(const uint2 *__restrict__ partial, int nslots, int n
     if (q < nq) {
         uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
         for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
+        if (rearm && nslots) partial[q] = make_uint2(KEY_EMPTY, KEY_EMPTY);       // the merged slot is ready for the next scan
         const unsigned long long e = ~0ull;
         ulonglong2 v;
         v.x = k1 == KEY_EMPTY ? e : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
@@ -424,12 +427,12 @@ int launch_fill_split_problems(aslam_ctx *ctx, KnnProblem *d_probs, const uint8_
 }
 
 int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int max_nq,
-                        uint2 *d_partial, int q_stride, int merge_div)
+                        uint2 *d_partial, int q_stride, int merge_div, bool armed)
 {
     if (nprobs <= 0 || max_nq <= 0) return ASLAM_OK;
     dim3 grid((max_nq + KNN_QBLOCK - 1) / KNN_QBLOCK, nprobs);
     static const int csa = [] { const char *e = getenv("ASLAM_KNN_CSA"); return e ? atoi(e) : ASLAM_KNN_CSA; }();
-    if (merge_div > 1)
+    if (merge_div > 1 && !armed)
         ASLAM_CUDA(cudaMemsetAsync(d_partial, 0xff, sizeof(uint2) * (size_t)(nprobs / merge_div) * q_stride, ctx->stream));
     const KnnMul M{2u, 4u, 65536u, 128u};
     ProfScope ps(ctx, PK_KNN_PARTIAL);
@@ -462,39 +465,39 @@ int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const u
     return ASLAM_OK;
 }
 
-int launch_knn2_finish_global(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
-                              int q_stride, int64_t row_base, uint64_t *d_top2)
+int launch_knn2_finish_global(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
+                              int q_stride, int64_t row_base, uint64_t *d_top2, bool rearm)
 {
     if (nq <= 0) return ASLAM_OK;
     ProfScope ps(ctx, PK_KNN_FINISH);
     knn2_finish_global_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
-        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *)d_top2);
+        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *)d_top2, rearm ? 1 : 0);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
 
-int launch_knn2_finish_global_push(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
+int launch_knn2_finish_global_push(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
                                    int q_stride, int64_t row_base, uint64_t *const *d_peer_bufs,
-                                   int nparts, int my_part)
+                                   int nparts, int my_part, bool rearm)
 {
     if (nq <= 0) return ASLAM_OK;
     ProfScope ps(ctx, PK_KNN_FINISH);
     knn2_finish_global_push_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
-        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part);
+        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part, rearm ? 1 : 0);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
 
-int launch_knn2_finish_exchange(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq, int q_stride,
+int launch_knn2_finish_exchange(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq, int q_stride,
                                 int64_t row_base, uint64_t *const *d_peer_bufs, int nparts, int my_part,
-                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out)
+                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out, bool rearm)
 {
     if (nq <= 0) return ASLAM_OK;
     if (nparts > FIN_THREADS) return fail(ASLAM_E_INVALID, "at most %d shards", FIN_THREADS);
     ProfScope ps(ctx, PK_MERGE);
     knn2_finish_exchange_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
         d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part,
-        (unsigned long long)round, d_arrival, (unsigned long long *)d_out);
+        (unsigned long long)round, d_arrival, (unsigned long long *)d_out, rearm ? 1 : 0);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

@@ -41,7 +41,8 @@ int launch_fill_split_problems(aslam_ctx *ctx, KnnProblem *d_probs, const uint8_
 // merge_div  > 1: every merge_div consecutive problems (the row ranges of one pair) are merged by the scan
 //                 itself: partial[(slot / merge_div) * q_stride + q]; nprobs must be a multiple of merge_div.
 int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int max_nq,
-                        uint2 *d_partial, int q_stride, int merge_div = 1);
+                        uint2 *d_partial, int q_stride, int merge_div = 1, bool armed = false);
+// armed: the merged slots already hold KEY_EMPTY (a finish kernel launched with rearm reset them), no memset.
 
 // One merged slot per group of `splits` consecutive problems (launch_knn2_partial with merge_div = splits);
 // survivors of the ratio test are
@@ -59,18 +60,18 @@ int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const u
 // All slots merged into one top-2 per query, as 64-bit keys (distance << 40 | row_base + row
 // + slot_row_offset), where slot rows are relative to the problem's t base and row_base is
 // added on top.
-int launch_knn2_finish_global(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
-                              int q_stride, int64_t row_base, uint64_t *d_top2);
+int launch_knn2_finish_global(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
+                              int q_stride, int64_t row_base, uint64_t *d_top2, bool rearm = false);
 
 // As launch_knn2_finish_global, with the result stored into slot `my_part` of every peer's
 // [nparts][nq][2] buffer (peer-mapped pointers in device memory): the all-gather is the epilogue.
-int launch_knn2_finish_global_push(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq,
+int launch_knn2_finish_global_push(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
                                    int q_stride, int64_t row_base, uint64_t *const *d_peer_bufs,
-                                   int nparts, int my_part);
+                                   int nparts, int my_part, bool rearm = false);
 
 // Fused finish + push + flag exchange + merge (see aslam_loopdb_query_global_exchange_device).
-int launch_knn2_finish_exchange(aslam_ctx *ctx, const uint2 *d_partial, int nslots, int nq, int q_stride,
+int launch_knn2_finish_exchange(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq, int q_stride,
                                 int64_t row_base, uint64_t *const *d_peer_bufs, int nparts, int my_part,
-                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out);
+                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out, bool rearm = false);
 
 }  // namespace aslam

@@ -190,3 +190,35 @@ def test_loop_detector_candidates_follow_reference_ranking(ctx, oracle):
     hit = det.detect(query)
     assert hit is not None and hit.match_id == 4 and hit.query_id == 31 and len(hit.matches) >= 150
     assert det.getLoopCount() == 1
+
+
+def test_loopdb_repeated_flat_queries_reuse_state_correctly(ctx, oracle):
+    """The flat query keeps its row-range table and leaves the merged result slots preset between calls; a
+    segmented query, a different query size or a database change in between must not leak into the next answer."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import LoopDB
+    rows = synth.descriptor_db(40_000, 9)
+    q1, _ = synth.loop_queries(rows, 300, 10)
+    q2, _ = synth.loop_queries(rows, 777, 11)
+    db = LoopDB(ctx, 60_000, 64)
+    r0, d0 = db.query_global(q1)                                   # empty database: no neighbours at all
+    assert (r0 == -1).all() and (d0 == -1).all()
+    for k in range(20):
+        db.add(rows[k * 2000:(k + 1) * 2000], k)
+    ref1 = oracle.knn2(q1, rows)
+    ref2 = oracle.knn2(q2, rows)
+    for q, ref in ((q1, ref1), (q1, ref1), (q2, ref2), (q1, ref1)):
+        r, d = db.query_global(q)
+        assert (r == ref[0]).all() and (d == ref[1]).all()
+    good = db.query_segmented(q1, 0.7)                             # overwrites the shared scratch
+    start = np.arange(0, 40_001, 2000).astype(np.int32)
+    assert (good == oracle.loop_segment_counts(q1, rows, start, 7, 10)).all()
+    r, d = db.query_global(q1)
+    assert (r == ref1[0]).all() and (d == ref1[1]).all()
+    extra = synth.descriptor_db(2000, 12)
+    db.add(extra, 20)                                              # the live region grows: the table is rebuilt
+    allrows = np.concatenate([rows, extra])
+    ref3 = oracle.knn2(q2, allrows)
+    r, d = db.query_global(q2)
+    assert (r == ref3[0]).all() and (d == ref3[1]).all()
+    db.close()
