@@ -352,13 +352,38 @@ static int orb_collect(aslam_orb *o, aslam_keypoint *kps, uint8_t *desc, int32_t
     int32_t *h_cnt = o->h_counts, *h_ovf = o->h_counts + (B + 1), *h_mc = o->h_counts + 2 * (B + 1);
     ASLAM_CUDA(cudaMemcpyAsync(h_cnt, o->b.counts + 1, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     ASLAM_CUDA(cudaMemcpyAsync(h_ovf, o->b.overflow + 1, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (kps) ASLAM_CUDA(cudaMemcpyAsync(kps, o->b.kps + cap, sizeof(aslam_keypoint) * cap * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (desc) ASLAM_CUDA(cudaMemcpyAsync(desc, o->b.desc + cap * 32, cap * 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    // Per frame only the first `head` = nfeatures rows are copied up front: a frame holds more than that only when
+    // responses tie at a level's cut (rows up to the capacity); those tails are fetched in a second pass
+    // below, which almost never runs.  Rows beyond a frame's count are not part of the result.
+    const size_t head = std::min(cap, (size_t)std::max(o->prm.nfeatures, 1));
+    auto copy_rows = [&](void *dst, const void *src, size_t row_bytes, size_t first, size_t nrows) -> cudaError_t {
+        return cudaMemcpy2DAsync(static_cast<uint8_t *>(dst) + first * row_bytes, cap * row_bytes,
+                                 static_cast<const uint8_t *>(src) + first * row_bytes, cap * row_bytes,
+                                 nrows * row_bytes, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    };
+    const bool with_matches = o->pending_track && matches;
+    if (kps) ASLAM_CUDA(copy_rows(kps, o->b.kps + cap, sizeof(aslam_keypoint), 0, head));
+    if (desc) ASLAM_CUDA(copy_rows(desc, o->b.desc + cap * 32, 32, 0, head));
     if (o->pending_track) {
-        if (match_counts) ASLAM_CUDA(cudaMemcpyAsync(h_mc, o->d_match_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (matches) ASLAM_CUDA(cudaMemcpyAsync(matches, o->d_matches, sizeof(aslam_match) * cap * n, cudaMemcpyDeviceToHost, ctx->stream));
+        ASLAM_CUDA(cudaMemcpyAsync(h_mc, o->d_match_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (with_matches) ASLAM_CUDA(copy_rows(matches, o->d_matches, sizeof(aslam_match), 0, head));
     }
     ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (head < cap) {
+        int most = 0, most_m = 0;
+        for (int i = 0; i < n; ++i) { most = std::max(most, h_cnt[i]); if (o->pending_track) most_m = std::max(most_m, h_mc[i]); }
+        bool again = false;
+        if ((size_t)most > head) {
+            if (kps) ASLAM_CUDA(copy_rows(kps, o->b.kps + cap, sizeof(aslam_keypoint), head, (size_t)most - head));
+            if (desc) ASLAM_CUDA(copy_rows(desc, o->b.desc + cap * 32, 32, head, (size_t)most - head));
+            again = kps || desc;
+        }
+        if (with_matches && (size_t)most_m > head) {
+            ASLAM_CUDA(copy_rows(matches, o->d_matches, sizeof(aslam_match), head, (size_t)most_m - head));
+            again = true;
+        }
+        if (again) ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     o->pending = 0;
     int ovf = 0;
     for (int i = 0; i < n; ++i) {

@@ -276,7 +276,8 @@ def run_ours(args):
         pipes.append((c, t, outs, h_in[s * half:(s + 1) * half]))
         pipe_streams.append(st)
     h2d = BATCH * W * H
-    d2h = BATCH * cap * (24 + 32 + 12) + BATCH * 8
+    # the library copies nfeatures rows per frame up front (tie tails beyond that only when a frame has them) + 3 counters
+    d2h = BATCH * min(cap, NFEAT) * (24 + 32 + 12) + BATCH * 12
 
     # ---- value: batch resident in HBM, all streams running, timed on the device (fork/join events)
     def value_run(steps):

@@ -101,7 +101,7 @@ def _checker(w, h, s):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["checker16", "checker40", "ramp", "lowcontrast", "saturated"])
+@pytest.mark.parametrize("kind", ["checker16", "checker40", "ramp", "lowcontrast", "saturated", "tiled94"])
 def test_structured_frames_with_ties_match_oracle(ctx, oracle, kind):
     """Inputs with mass ties (equal FAST scores, equal Harris responses) and flat regions: the tie-inclusive
     retainBest cuts, the strict NMS and the empty levels must all follow cv::ORB."""
@@ -113,6 +113,11 @@ def test_structured_frames_with_ties_match_oracle(ctx, oracle, kind):
     elif kind == "ramp":
         y, x = np.mgrid[0:h, 0:w]
         img = ((x + 2 * y) % 256).astype(np.uint8)                 # sawtooth: long straight edges, no corners off the seams
+    elif kind == "tiled94":
+        # a 94x94 block repeated: identical corners tie at the level-0 cut, the frame returns MORE than nfeatures
+        # keypoints (1013), which also exercises the second D2H pass for rows beyond nfeatures
+        blk = synth.frame(w, h, 77)[:94, :94]
+        img = np.tile(blk, (h // 94 + 1, w // 94 + 1))[:h, :w].copy()
     elif kind == "lowcontrast":
         img = (100 + synth.frame(w, h, 31) // 4).astype(np.uint8)   # contrast near the FAST threshold: levels below quota
     else:
@@ -122,6 +127,8 @@ def test_structured_frames_with_ties_match_oracle(ctx, oracle, kind):
     f = Frame()
     ex.extract(img, w, h, f)
     assert f.numKeypoints() == len(ko)
+    if kind == "tiled94":
+        assert len(ko) > n
     key = lambda k: sorted(zip(k["octave"].tolist(), k["x"].tolist(), k["y"].tolist()))
     assert key(f.keypoints) == key(ko)
     if len(ko):
