@@ -75,6 +75,8 @@ SYMBOLS = {
     "aslam_loopdb_add": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
     "aslam_loopdb_add_device": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
     "aslam_loopdb_clear": (C.c_int, [_P]),
+    "aslam_loopdb_save": (C.c_int, [_P, C.c_char_p]),
+    "aslam_loopdb_load": (C.c_int, [_P, C.c_char_p]),
     "aslam_loopdb_num_keyframes": (C.c_int, [_P]),
     "aslam_loopdb_num_rows": (C.c_int64, [_P]),
     "aslam_loopdb_set_row_base": (C.c_int, [_P, C.c_int64]),

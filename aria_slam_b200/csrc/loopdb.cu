@@ -5,6 +5,7 @@
 // per-keyframe knnMatch + ratio count (:86-95).  Layout: one [rows, 32] u8 array, keyframes are
 // contiguous row segments in insertion order; eviction advances the head, and the live region
 // is slid back to row 0 only when the tail would run past the capacity.
+#include <cstdio>
 #include <vector>
 
 #include "match.cuh"
@@ -148,6 +149,64 @@ int aslam_loopdb_clear(aslam_loopdb *db)
 {
     ASLAM_REQUIRE(db, "db is NULL");
     db->segs.clear(); db->head = db->tail = 0; db->row_base = 0;
+    return ASLAM_OK;
+}
+
+// Persistence (the keyframe store survives a restart / moves between shards): one file =
+// header {magic, version, keyframes, rows, row_base}, the (id, rows) table, then the live rows.
+static const uint64_t k_db_magic = 0x31424450554F4C41ull;      // "ALOUPDB1"
+
+int aslam_loopdb_save(aslam_loopdb *db, const char *path)
+{
+    ASLAM_REQUIRE(db && path, "NULL argument");
+    aslam_ctx *ctx = db->ctx;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t rows = db->tail - db->head;
+    std::vector<uint8_t> host((size_t)rows * 32);
+    if (rows) ASLAM_CUDA(cudaMemcpyAsync(host.data(), db->d_rows + db->head * 32, host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(ASLAM_E_INVALID, "cannot open %s for writing", path);
+    const uint64_t hdr[5] = {k_db_magic, 1, (uint64_t)db->segs.size(), (uint64_t)rows, (uint64_t)db->row_base};
+    bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1;
+    for (const auto &sg : db->segs) {
+        const uint64_t e[2] = {sg.id, (uint64_t)sg.n};
+        ok = ok && fwrite(e, sizeof(e), 1, f) == 1;
+    }
+    ok = ok && (host.empty() || fwrite(host.data(), 1, host.size(), f) == host.size());
+    ok = (fclose(f) == 0) && ok;
+    return ok ? ASLAM_OK : fail(ASLAM_E_INVALID, "short write to %s", path);
+}
+
+int aslam_loopdb_load(aslam_loopdb *db, const char *path)
+{
+    ASLAM_REQUIRE(db && path, "NULL argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(ASLAM_E_INVALID, "cannot open %s", path);
+    uint64_t hdr[5];
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != k_db_magic || hdr[1] != 1) { fclose(f); return fail(ASLAM_E_INVALID, "%s is not a loop database file", path); }
+    const uint64_t nkf = hdr[2], rows = hdr[3];
+    if ((int64_t)rows > db->capacity || (int64_t)nkf > db->max_keyframes) {
+        fclose(f);
+        return fail(ASLAM_E_NOMEM, "%s holds %llu keyframes / %llu rows; this database takes %d / %lld",
+                    path, (unsigned long long)nkf, (unsigned long long)rows, db->max_keyframes, (long long)db->capacity);
+    }
+    std::vector<uint64_t> table(2 * (size_t)nkf);
+    std::vector<uint8_t> host((size_t)rows * 32);
+    bool ok = (nkf == 0 || fread(table.data(), 16, (size_t)nkf, f) == nkf) && (rows == 0 || fread(host.data(), 32, (size_t)rows, f) == rows);
+    fclose(f);
+    uint64_t sum = 0;
+    for (uint64_t i = 0; ok && i < nkf; ++i) sum += table[2 * i + 1];
+    if (!ok || sum != rows) return fail(ASLAM_E_INVALID, "%s is truncated or inconsistent", path);
+    aslam_ctx *ctx = db->ctx;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    if (rows) ASLAM_CUDA(cudaMemcpyAsync(db->d_rows, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
+    db->segs.clear();
+    int64_t at = 0;
+    for (uint64_t i = 0; i < nkf; ++i) { db->segs.push_back({table[2 * i], at, (int32_t)table[2 * i + 1]}); at += (int64_t)table[2 * i + 1]; }
+    db->head = 0; db->tail = (int64_t)rows; db->row_base = (int64_t)hdr[4];
+    db->tab_splits = 0;
     return ASLAM_OK;
 }
 

@@ -208,6 +208,12 @@ class LoopDB:
     def clear(self):
         check(lib().aslam_loopdb_clear(self.h))
 
+    def save(self, path):
+        check(lib().aslam_loopdb_save(self.h, str(path).encode()))
+
+    def load(self, path):
+        check(lib().aslam_loopdb_load(self.h, str(path).encode()))
+
     def set_row_base(self, base):
         check(lib().aslam_loopdb_set_row_base(self.h, int(base)))
 

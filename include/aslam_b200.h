@@ -208,6 +208,11 @@ ASLAM_API void aslam_loopdb_destroy(aslam_loopdb *db);
 ASLAM_API int aslam_loopdb_add(aslam_loopdb *db, const uint8_t *desc, int n, uint64_t keyframe_id);
 ASLAM_API int aslam_loopdb_add_device(aslam_loopdb *db, const uint8_t *d_desc, int n, uint64_t keyframe_id);
 ASLAM_API int aslam_loopdb_clear(aslam_loopdb *db);
+/* Persistence of the keyframe store (the reference keeps it in memory only, LoopClosure.hpp; its H14 notes plan
+ * chunked stores): save writes ids, per-keyframe row counts, row_base and the live rows to one file; load
+ * replaces the content of db (capacity and max_keyframes of db must suffice). */
+ASLAM_API int aslam_loopdb_save(aslam_loopdb *db, const char *path);
+ASLAM_API int aslam_loopdb_load(aslam_loopdb *db, const char *path);
 ASLAM_API int aslam_loopdb_num_keyframes(const aslam_loopdb *db);
 ASLAM_API int64_t aslam_loopdb_num_rows(const aslam_loopdb *db);
 ASLAM_API int aslam_loopdb_set_row_base(aslam_loopdb *db, int64_t row_base);

@@ -222,3 +222,38 @@ def test_loopdb_repeated_flat_queries_reuse_state_correctly(ctx, oracle):
     r, d = db.query_global(q2)
     assert (r == ref3[0]).all() and (d == ref3[1]).all()
     db.close()
+
+
+def test_loopdb_save_load_round_trip(ctx, oracle, tmp_path):
+    """The keyframe store written to a file and read into a fresh database answers every query identically
+    (segmented counts, flat top-2, keyframe table, row base); a bad or oversized file is an error."""
+    from aria_slam_b200 import _lib
+    from aria_slam_b200.frontend import LoopDB
+    rs = np.random.RandomState(21)
+    kfs = [rs.randint(0, 256, (n, 32), dtype=np.uint8) for n in (300, 0, 1200, 777, 64)]
+    q = np.concatenate([kfs[2][:100], rs.randint(0, 256, (150, 32), dtype=np.uint8)])
+    a = LoopDB(ctx, 4000, 8)
+    for i, k in enumerate(kfs):
+        a.add(k, 100 + i)
+    a.set_row_base(5000)
+    path = tmp_path / "loop.db"
+    a.save(path)
+    b = LoopDB(ctx, 4000, 8)
+    b.add(kfs[0], 1)                                   # replaced by load
+    b.load(path)
+    assert b.num_keyframes == 5 and b.num_rows == sum(len(k) for k in kfs)
+    ia, ra = a.keyframes(); ib, rb = b.keyframes()
+    assert (ia == ib).all() and (ra == rb).all()
+    assert (a.query_segmented(q, 0.7) == b.query_segmented(q, 0.7)).all()
+    (r1, d1), (r2, d2) = a.query_global(q), b.query_global(q)
+    assert (r1 == r2).all() and (d1 == d2).all() and r1[:100, 0].min() >= 5000
+    small = LoopDB(ctx, 1000, 8)
+    with pytest.raises(_lib.AslamError):
+        small.load(path)                               # more rows than this database can hold
+    bad = tmp_path / "bad.db"
+    bad.write_bytes(b"not a database")
+    with pytest.raises(_lib.AslamError):
+        b.load(bad)
+    assert b.num_keyframes == 5                        # a failed load leaves the database as it was
+    for d in (a, b, small):
+        d.close()
