@@ -152,7 +152,7 @@ int aslam_orb_create(aslam_ctx *ctx, const aslam_orb_params *p, int width, int h
     aslam_orb *o = new aslam_orb();
     o->ctx = ctx; o->prm = *p; o->width = width; o->height = height; o->max_batch = max_batch;
     // entry j*32 + k = comparison 8*k + j as (x0, y0, x1, y1): one coalesced 16-byte load per j per warp
-    static float4 packed[256];
+    float4 packed[256];
     for (int i = 0; i < 256; ++i)
         packed[(i & 7) * 32 + (i >> 3)] = make_float4((float)k_brief_pattern[i][0], (float)k_brief_pattern[i][1],
                                                       (float)k_brief_pattern[i][2], (float)k_brief_pattern[i][3]);
@@ -160,7 +160,7 @@ int aslam_orb_create(aslam_ctx *ctx, const aslam_orb_params *p, int width, int h
     if (e == cudaSuccess) e = cudaMemcpy(o->d_pattern, packed, sizeof(packed), cudaMemcpyHostToDevice);
     // Orientation weights (ICAngles disc, radius 15) of the patch-aligned word (row, word): byte bt is column
     // u = 4*word + bt - 15 of row v = row - 15; entry it*32 + lane <-> row 4*it + lane/8, word lane%8.
-    static uint2 ori[8 * 32];
+    uint2 ori[8 * 32];
     static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     for (int it = 0; it < 8; ++it)
         for (int ln = 0; ln < 32; ++ln) {
