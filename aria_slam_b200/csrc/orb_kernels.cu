@@ -240,7 +240,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     __shared__ uint32_t S[FT_SCORE_H][FT_SCORE_W / 2];      // two u16 scores per word
     __shared__ int warp_tot[8];
 #if ASLAM_FAST_COMPACT
-    __shared__ uint16_t Q[8][FT_SCORE_H / 8 * 32];          // per warp: queued (row << 5 | lane) of pairs to score
+    __shared__ uint16_t Q[8][FT_SCORE_H / 8 * 32 + 2];      // per warp: queued (row << 5 | lane) of pairs to score (+ a sink slot)
 #endif
 
     const int tile = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
@@ -319,7 +319,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             const bool pass = ((ub | ud) & colbits) != 0;
             S[r][p] = 0u;
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-            if (pass) queue[nq + __popc(bal & ((1u << p) - 1u))] = (uint16_t)((r << 5) | p);
+            queue[pass ? nq + __popc(bal & ((1u << p) - 1u)) : FT_SCORE_H / 8 * 32] = (uint16_t)((r << 5) | p);      // branch-free: slot 256 is a sink
             nq += __popc(bal);
         }
         __syncwarp();

@@ -39,38 +39,74 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of the profiling recipe, sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled through NVML from a thread every few milliseconds while the timed
+    regions run (the regions last tens of milliseconds: an nvidia-smi process would return a handful of
+    samples at best); falls back to the recipe's nvidia-smi line when NVML is not importable."""
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period, self.rows, self.max_mhz = index, period_s, [], None
+        self.timed = False                  # set by the bench around its timed regions
+        self._stop = threading.Event()
+        self._thread = self.proc = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        why = reasons(h)
+                        self.rows.append((self.timed, float(mhz), int(why)))
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+
+            def read():
+                for line in self.proc.stdout:
+                    c = [x.strip() for x in line.split(",")]
+                    if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                        self.max_mhz = float(c[1]) if c[1].replace(".", "").isdigit() else self.max_mhz
+                        why = sum(bit for (_, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
+                        self.rows.append((self.timed, float(c[0]), why))
+
+            threading.Thread(target=read, daemon=True).start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        timed = [r for r in self.rows if r[0]] or self.rows
+        sm = [r[1] for r in timed]
+        bits = 0
+        for r in timed:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for name, bit in self.REASONS if bits & bit),
+                "samples": len(sm), "samples_total": len(self.rows), "source": "nvml" if self._thread else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -293,6 +329,7 @@ def run_ours(args):
         clocks.start()
     launches0 = kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.timed = True
     e0.record(stream)
     for st in pipe_streams:
         st.wait_event(e0)
@@ -301,6 +338,7 @@ def run_ours(args):
         ev = torch.cuda.Event(); ev.record(st); stream.wait_event(ev)
     e1.record(stream)
     barrier()
+    clocks.timed = False
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = kernel_launches() - launches0
     value = world * BATCH * K / (ms * 1e-3)
@@ -344,12 +382,14 @@ def run_ours(args):
     g0.record(stream)
     for st in pipe_streams:
         st.wait_event(g0)
+    clocks.timed = True
     t0 = time.perf_counter()
     e2e_run(K)
     for st in pipe_streams:
         ev = torch.cuda.Event(); ev.record(st); stream.wait_event(ev)
     g1.record(stream)
     torch.cuda.synchronize()
+    clocks.timed = False
     e2e_wall_s = max_over_ranks(time.perf_counter() - t0)
     e2e_s = max_over_ranks(g0.elapsed_time(g1) * 1e-3)
     e2e_val = world * BATCH * K / e2e_s
