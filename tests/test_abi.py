@@ -59,3 +59,23 @@ def test_struct_layouts_match_reference_types():
     assert _lib.KP_DTYPE.itemsize == 24 and _lib.MATCH_DTYPE.itemsize == 12 and _lib.BOX_DTYPE.itemsize == 24
     assert _lib.KP_DTYPE.names == ("x", "y", "size", "angle", "response", "octave")
     assert C.sizeof(_lib.OrbParams) == 40
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary must bind from any FFI: include/aslam_b200.h compiles as strict C99 on its own, and a C
+    program that only calls the no-device entry points links against the library."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "aslam_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { aslam_orb_params p; aslam_ctx *c = 0; int rc;\n'
+                   '  aslam_orb_default_params(&p);\n'
+                   '  rc = aslam_ctx_create(0, 0, &c);\n'
+                   '  printf("%d %d %s\\n", p.nfeatures, rc, aslam_version());\n'
+                   '  if (c) aslam_ctx_destroy(c);\n  return 0; }\n')
+    exe = tmp_path / "use"
+    libdir = os.path.join(ROOT, "aria_slam_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                        "-L" + libdir, "-laslam_b200", "-Wl,-rpath," + libdir, "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.split()
+    assert out[0] == "1000"                     # FactoryConfig::max_features (include/factory/PipelineFactory.hpp:25)
