@@ -35,6 +35,11 @@ static_assert(31 * ((FT_OUT_H + 1) / 2) <= FT_CAP, "candidate slots per tile");
 #endif
 constexpr int BL_W = ASLAM_BL_W, BL_H = ASLAM_BL_H, BL_ROWS = BL_H + 6;
 static_assert(BL_W % 8 == 0 && BL_ROWS % 2 == 0 && BL_W * BL_ROWS * 4 <= 48 * 1024, "blur tile");
+// describe CTA = 8 warps x DESC_KPW keypoints handled one after another (the per-lane tables live in registers)
+#ifndef ASLAM_DESC_KPW
+#define ASLAM_DESC_KPW 8
+#endif
+constexpr int DESC_KPW = ASLAM_DESC_KPW;
 constexpr int SEL_TIE_ROOM = 64;   // extra output rows per level for tied Harris responses
 
 struct LevelGeom {

@@ -878,7 +878,6 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 constexpr int DP_ROWS = 39, DP_WORDS = 12;      // blurred patch: +-19 rows of 12 aligned words
 constexpr int OP_ROWS = 31;                     // unblurred patch for the moments: +-15 rows, same row format
-constexpr int DESC_KPW = 8;                     // keypoints per warp (the per-lane tables live in registers)
 
 // Stage `rows` rows of 12 aligned words starting at `src` (row 0, word 0) into smem: lanes 0..23 take two
 // rows per step, one 64-bit pointer bump per step, stores at compile-time offsets.
