@@ -127,3 +127,29 @@ def test_merge_top2_is_shard_invariant(oracle):
             parts.append((np.where(i >= 0, i + a, -1), d))
         midx, mdist = oracle.merge_top2(parts)
         assert (midx == ridx).all() and (mdist == rdist).all()
+
+
+def test_fast_quick_reject_is_a_necessary_condition():
+    """The GPU FAST kernel scores a pixel only if a cheap test passes: a 9-arc of the 16-pixel ring contains one
+    pixel of every opposite pair (i, i+8), so a bright (dark) corner needs max (min) of each pair above c + t
+    (below c - t).  Checked here on the four pairs the kernel uses, against every corner cv2 finds without NMS."""
+    import cv2
+    from aria_slam_b200 import synth
+    offs = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3), (-2, -2), (-3, -1),
+            (-3, 0), (-3, 1), (-2, 2), (-1, 3)]                  # (dx, dy), the kernel's ring order
+    t = 20
+    for seed, (w, h) in ((1, (320, 240)), (2, (411, 303)), (3, (752, 480))):
+        img = synth.frame(w, h, seed)
+        kps = cv2.FastFeatureDetector_create(t, False).detect(img, None)
+        assert len(kps) > 1000
+        i16 = img.astype(np.int16)
+        c = i16[3:h - 3, 3:w - 3]
+        ring = [i16[3 + dy:h - 3 + dy, 3 + dx:w - 3 + dx] for dx, dy in offs]
+        pairs = (0, 4, 2, 6)
+        mb = np.min([np.maximum(ring[i], ring[i + 8]) for i in pairs], axis=0)
+        md = np.max([np.minimum(ring[i], ring[i + 8]) for i in pairs], axis=0)
+        passed = (mb > c + t) | (md < c - t)
+        xs = np.array([int(k.pt[0]) for k in kps]) - 3
+        ys = np.array([int(k.pt[1]) for k in kps]) - 3
+        assert passed[ys, xs].all()
+        assert passed.mean() < 0.5                                # and it does reject most pixels
