@@ -45,7 +45,19 @@ def main():
     r75 = np.array([i for i in range(len(q)) if np.float32(dist[i, 0]) < np.float32(0.75) * np.float32(dist[i, 1])], np.int32)
     r70 = np.array([i for i in range(len(q)) if float(dist[i, 0]) < 0.7 * float(dist[i, 1])], np.int32)
     np.savez_compressed(os.path.join(HERE, "knn_ties.npz"), query=q, train=t, idx=idx, dist=dist, pass_075=r75, pass_070=r70)
-    print("wrote orb_320x240.npz (%d kp, %d masked) and knn_ties.npz" % (len(kps), len(kpm)))
+    # The BASELINE.json configurations at their real sizes: the frames come from the seeded generator (their
+    # CRC32 is stored to catch generator drift), only cv2's keypoints and descriptors are committed.
+    import zlib
+    out = {}
+    for name, (w, h, n, seed) in {"c1": (752, 480, 1000, 1), "c2": (752, 480, 2000, 1000), "c4": (640, 480, 1000, 4000)}.items():
+        f = synth.frame(w, h, seed)
+        k, d = O.cv2_orb(f, n)
+        o = np.lexsort((k["x"], k["y"], k["octave"]))
+        out[name + "_spec"] = np.array([w, h, n, seed, zlib.crc32(f.tobytes())], np.int64)
+        out[name + "_keypoints"] = k[o]
+        out[name + "_descriptors"] = d[o]
+    np.savez_compressed(os.path.join(HERE, "orb_configs.npz"), cv2_version=np.array(cv2.__version__), **out)
+    print("wrote orb_320x240.npz (%d kp, %d masked), knn_ties.npz and orb_configs.npz" % (len(kps), len(kpm)))
 
 
 if __name__ == "__main__":

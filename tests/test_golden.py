@@ -59,3 +59,31 @@ def test_gpu_reproduces_golden_knn(ctx):
     m = []
     mt.match(Frame(descriptors=g["query"].reshape(-1)), Frame(descriptors=g["train"].reshape(-1)), m, 0.75)
     assert [int(x["query_idx"]) for x in m] == g["pass_075"].tolist()
+
+
+def _config_frames():
+    import zlib
+    from aria_slam_b200 import synth
+    g = np.load(os.path.join(G, "orb_configs.npz"))
+    for name in ("c1", "c2", "c4"):
+        w, h, n, seed, crc = (int(v) for v in g[name + "_spec"])
+        img = synth.frame(w, h, seed)
+        assert zlib.crc32(img.tobytes()) == crc, "the synthetic frame generator drifted"
+        yield name, img, w, h, n, g[name + "_keypoints"], g[name + "_descriptors"]
+
+
+def test_oracle_reproduces_golden_configs(oracle):
+    """cv2's answers for the BASELINE configurations C1, C2 and C4 at their real sizes."""
+    for name, img, w, h, n, gk, gd in _config_frames():
+        k, d = oracle.orb(img, n)
+        assert _orb_check(k, d, gk, gd) == 1.0, name
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_configs(ctx):
+    from aria_slam_b200.frontend import OrbB200Extractor, Frame
+    for name, img, w, h, n, gk, gd in _config_frames():
+        ex = OrbB200Extractor(n, ctx)
+        f = Frame(); ex.extract(img, w, h, f)
+        assert _orb_check(f.keypoints, f.descriptors, gk, gd) >= 0.99, name
+        ex.close()
