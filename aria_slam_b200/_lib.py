@@ -24,7 +24,7 @@ class OrbParams(C.Structure):
     _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
                 ("edge_threshold", C.c_int32), ("first_level", C.c_int32), ("wta_k", C.c_int32),
                 ("score_type", C.c_int32), ("patch_size", C.c_int32), ("fast_threshold", C.c_int32),
-                ("blur_mode", C.c_int32)]
+                ("blur_mode", C.c_int32), ("grid_cell", C.c_int32)]
 
 
 class AslamError(RuntimeError):

@@ -29,11 +29,21 @@ void OrbB200Extractor::ensure(int width, int height)
     aslam_orb_params p;
     aslam_orb_default_params(&p);          // == cv::ORB::create(n,1.2f,8,31,0,2,HARRIS,31,20), OrbCudaExtractor.cpp:35-45
     p.nfeatures = max_features_;
+    p.grid_cell = grid_cell_;
     check(aslam_orb_create(ctx_->get(), &p, width, height, 1, &orb_));
     width_ = width; height_ = height;
     const size_t cap = (size_t)aslam_orb_capacity(orb_);
     kp_buf_.resize(cap);
     desc_buf_.resize(cap * 32);
+}
+
+void OrbB200Extractor::setGridBucketing(int cell_pixels)
+{
+    if (pending_frame_) throw std::runtime_error("aslam_b200: setGridBucketing with an extract pending");
+    if (cell_pixels == grid_cell_) return;
+    grid_cell_ = cell_pixels;
+    aslam_orb_destroy(orb_);      // re-created with the new parameter by the next extract
+    orb_ = nullptr;
 }
 
 void OrbB200Extractor::setDynamicBoxes(const std::vector<core::Detection>& detections)

@@ -51,11 +51,14 @@ public:
     // SlamPipeline::filterDynamicKeypoints (SlamPipeline.hpp:96-99) folded into the extraction:
     // detections given here drop keypoints inside dynamic-class boxes of the NEXT extract call.
     void setDynamicBoxes(const std::vector<core::Detection>& detections);
+    // Per-level grid bucketing of the Harris cull (aslam_orb_params::grid_cell; 0 = off = cv::ORB's behaviour).
+    // An extension: the reference never buckets.  Takes effect from the next extract call.
+    void setGridBucketing(int cell_pixels);
 private:
     void ensure(int width, int height);
     std::shared_ptr<Context> ctx_;
     aslam_orb* orb_ = nullptr;
-    int max_features_, width_ = 0, height_ = 0;
+    int max_features_, width_ = 0, height_ = 0, grid_cell_ = 0;
     core::Frame* pending_frame_ = nullptr;     // like OrbCudaExtractor::pending_frame_
     std::vector<aslam_box> boxes_;
     std::vector<aslam_keypoint> kp_buf_;

@@ -43,7 +43,7 @@ struct aslam_orb {
 static void orb_free_buffers(aslam_orb *o)
 {
     cudaFree(o->b.pyr); cudaFree(o->b.blur); cudaFree(o->b.mask); cudaFree(o->b.cand); cudaFree(o->b.cand_cnt);
-    cudaFree(o->b.tile_base); cudaFree(o->b.surv); cudaFree(o->b.hresp); cudaFree(o->b.sel_xy);
+    cudaFree(o->b.tile_base); cudaFree(o->b.surv); cudaFree(o->b.hresp); cudaFree(o->b.rank); cudaFree(o->b.sel_xy);
     cudaFree(o->b.sel_resp); cudaFree(o->b.sel_cnt); cudaFree(o->b.kps); cudaFree(o->b.desc);
     cudaFree(o->b.counts); cudaFree(o->b.overflow); cudaFree(o->d_tabs);
     cudaFree(o->d_matches); cudaFree(o->d_match_counts); cudaFree(o->d_probs); cudaFree(o->d_partial);
@@ -76,6 +76,7 @@ static int orb_plan(aslam_orb *o)
     std::vector<uint32_t> tabs;
     build_orb_geometry(o->width, o->height, o->prm.nfeatures, o->prm.scale_factor, o->prm.nlevels,
                        o->prm.edge_threshold, o->prm.fast_threshold, o->prm.blur_mode, o->g, tabs);
+    o->g.grid_cell = o->prm.grid_cell;
     const OrbGeom &g = o->g;
     const size_t B = (size_t)o->max_batch;
     const size_t tiles = (size_t)(g.tiles_per_frame > 0 ? g.tiles_per_frame : 1);
@@ -87,6 +88,7 @@ static int orb_plan(aslam_orb *o)
     ASLAM_CUDA(cudaMalloc(&b.tile_base, sizeof(uint32_t) * B * tiles));
     ASLAM_CUDA(cudaMalloc(&b.surv, sizeof(uint32_t) * B * tiles * FT_CAP));
     ASLAM_CUDA(cudaMalloc(&b.hresp, sizeof(float) * B * tiles * FT_CAP));
+    if (g.grid_cell > 0) ASLAM_CUDA(cudaMalloc(&b.rank, sizeof(uint32_t) * B * tiles * FT_CAP));
     ASLAM_CUDA(cudaMalloc(&b.sel_xy, sizeof(uint32_t) * B * g.kp_cap));
     ASLAM_CUDA(cudaMalloc(&b.sel_resp, sizeof(float) * B * g.kp_cap));
     ASLAM_CUDA(cudaMalloc(&b.sel_cnt, sizeof(int32_t) * B * ORB_MAX_LEVELS));
@@ -125,6 +127,7 @@ void aslam_orb_default_params(aslam_orb_params *p)
     p->nfeatures = 1000; p->scale_factor = 1.2f; p->nlevels = 8; p->edge_threshold = 31;
     p->first_level = 0; p->wta_k = 2; p->score_type = 0; p->patch_size = 31; p->fast_threshold = 20;
     p->blur_mode = 2;
+    p->grid_cell = 0;
 }
 
 static int check_params(const aslam_orb_params *p, int width, int height, int max_batch)
@@ -137,6 +140,7 @@ static int check_params(const aslam_orb_params *p, int width, int height, int ma
                   "only first_level 0, WTA_K 2, HARRIS_SCORE, patch 31 are implemented (the reference's values)");
     ASLAM_REQUIRE(p->fast_threshold >= 1 && p->fast_threshold <= 254, "fast_threshold must be 1..254");
     ASLAM_REQUIRE(p->blur_mode >= 0 && p->blur_mode <= 2, "blur_mode must be 0..2");
+    ASLAM_REQUIRE(p->grid_cell == 0 || (p->grid_cell >= 8 && p->grid_cell <= 4096), "grid_cell must be 0 (off) or 8..4096");
     ASLAM_REQUIRE(width >= 1 && height >= 1 && width <= 4095 && height <= 4095, "frame size must be 1..4095 per side");
     ASLAM_REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch must be 1..4096");
     return ASLAM_OK;
@@ -201,10 +205,12 @@ int aslam_orb_set_max_features(aslam_orb *o, int nfeatures)
     ASLAM_CUDA(cudaSetDevice(o->ctx->device));
     ASLAM_CUDA(cudaStreamSynchronize(o->ctx->stream));
     // OrbCudaExtractor.cpp:212-216 re-creates the detector with only nfeatures set: defaults elsewhere.
-    const int blur_mode = o->prm.blur_mode;
+    // blur_mode and grid_cell are this library's own knobs, not cv::ORB::create arguments: they stay.
+    const int blur_mode = o->prm.blur_mode, grid_cell = o->prm.grid_cell;
     aslam_orb_default_params(&o->prm);
     o->prm.nfeatures = nfeatures;
     o->prm.blur_mode = blur_mode;
+    o->prm.grid_cell = grid_cell;
     orb_free_buffers(o);
     return orb_plan(o);
 }

@@ -63,6 +63,7 @@ struct OrbGeom {
     int nlevels;             // as requested (quotas are spread over all of them)
     int nbuilt;              // levels 0..nbuilt-1 exist in memory (those that can hold keypoints, chained)
     int width, height, edge, fast_thr;
+    int grid_cell;           // 0 = cv::ORB's retainBest; > 0 = grid-bucketed second cull with cells of that many level pixels
     int tiles_per_frame;
     int blur_tiles_per_frame;
     int desc_blocks_per_frame;

@@ -696,6 +696,45 @@ __device__ __forceinline__ int warp_kth_bin_from_top(const int *hist, int k, int
     return __shfl_sync(0xffffffffu, bin, owner);
 }
 
+// K-th largest of the 32-bit keys key_of(i, key) (false = element i does not take part), i in [0, M), by
+// 4 x 8-bit radix passes; at least K >= 1 elements must take part.  Called by the whole CTA.  Returns that key;
+// k_left = how many of the elements equal to it are needed to reach K (>= 1).
+template <class KeyFn>
+__device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of, int *hist, uint32_t *s_prefix, int *s_k,
+                                                      int &k_left)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { *s_prefix = 0; *s_k = K; }
+    uint32_t maskbits = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = *s_prefix;
+        for (int i = tid; i < M; i += SEL_THREADS) {
+            uint32_t key;
+            if (key_of(i, key) && (key & maskbits) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 0xffu], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int above;
+            const int bin = warp_kth_bin_from_top(hist, *s_k, above);     // exists: the prefix class holds >= s_k keys
+            if (lane == 0) {
+                *s_k -= above;
+                *s_prefix = prefix | ((uint32_t)bin << (8 * pass));
+            }
+        }
+        maskbits |= 0xffu << (8 * pass);
+        __syncthreads();
+    }
+    const uint32_t kth = *s_prefix;
+    k_left = *s_k;
+    __syncthreads();          // the next call re-arms s_prefix / s_k
+    return kth;
+}
+
+// BUCKET = the grid-bucketed second cull (g.grid_cell > 0), an extension cv::ORB does not have; its definition is
+// in include/aslam_b200.h (aslam_orb_params::grid_cell) and DESIGN.md section 4a.
+template <bool BUCKET>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(OrbGeom g, OrbBuffers b)
 {
@@ -786,33 +825,47 @@ select_kernel(OrbGeom g, OrbBuffers b)
     }
     __syncthreads();
 
-    // --- retainBest(N): K-th largest response by 4 x 8-bit radix passes over the ordered key
+    // --- retainBest(N): K-th largest response by a radix select over the ordered key
     uint32_t cut = 0;   // keep keys >= cut
     const int K2 = L.quota;
-    if (M1 > K2) {
-        if (tid == 0) { s_prefix = 0; s_k = K2; }
-        uint32_t maskbits = 0;
-        for (int pass = 3; pass >= 0; --pass) {
-            for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-            __syncthreads();
-            const uint32_t prefix = s_prefix;
-            for (int i = tid; i < M1; i += SEL_THREADS) {
-                const uint32_t key = float_order_key(hresp[i]);
-                if ((key & maskbits) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 0xffu], 1);
-            }
-            __syncthreads();
-            if (warp == 0) {
-                int above;
-                const int bin = warp_kth_bin_from_top(hist, s_k, above);     // exists: the prefix class holds >= s_k keys
-                if (lane == 0) {
-                    s_k -= above;
-                    s_prefix = prefix | ((uint32_t)bin << (8 * pass));
+    int k_left;
+    [[maybe_unused]] uint32_t rank_cut = 0xffffffffu;     // BUCKET: keep ranks < rank_cut, and rank == rank_cut with key >= cut
+    [[maybe_unused]] uint32_t *rank = nullptr;
+    if constexpr (!BUCKET) {
+        if (M1 > K2)
+            cut = block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return true; },
+                                    hist, &s_prefix, &s_k, k_left);
+    } else {
+        // Grid-bucketed cull: rank of a survivor = how many survivors of its cell have a greater response; order by
+        // (rank ascending, response descending), keep the first K2 and everything tied with the K2-th.
+        rank = b.rank + tile0 * FT_CAP;
+        if (M1 > K2) {
+            __shared__ uint32_t s_cell[SEL_THREADS], s_key[SEL_THREADS];
+            const int cell = g.grid_cell;
+            auto cell_of = [&](uint32_t e) { return ((e & 0xfffu) / (uint32_t)cell) | ((((e >> 12) & 0xfffu) / (uint32_t)cell) << 12); };
+            for (int i0 = 0; i0 < M1; i0 += SEL_THREADS) {
+                const int i = i0 + tid;
+                const uint32_t mycell = i < M1 ? cell_of(surv[i]) : 0xfffffffeu;
+                const uint32_t mykey = i < M1 ? float_order_key(hresp[i]) : 0u;
+                uint32_t r = 0;
+                for (int j0 = 0; j0 < M1; j0 += SEL_THREADS) {
+                    __syncthreads();
+                    const int j = j0 + tid;
+                    s_cell[tid] = j < M1 ? cell_of(surv[j]) : 0xffffffffu;
+                    s_key[tid] = j < M1 ? float_order_key(hresp[j]) : 0u;
+                    __syncthreads();
+                    const int n = min(SEL_THREADS, M1 - j0);
+                    for (int k = 0; k < n; ++k) r += (s_cell[k] == mycell) & (s_key[k] > mykey);
                 }
+                if (i < M1) rank[i] = r;
             }
-            maskbits |= 0xffu << (8 * pass);
             __syncthreads();
+            rank_cut = ~block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = ~rank[i]; return true; },
+                                          hist, &s_prefix, &s_k, k_left);
+            const uint32_t R = rank_cut;
+            cut = block_kth_largest(M1, k_left, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return rank[i] == R; },
+                                    hist, &s_prefix, &s_k, k_left);
         }
-        cut = s_prefix;
     }
 
     // --- ordered output
@@ -823,7 +876,12 @@ select_kernel(OrbGeom g, OrbBuffers b)
         const int i = i0 + tid;
         float r = 0.f;
         bool pass = false;
-        if (i < M1) { r = hresp[i]; pass = float_order_key(r) >= cut; }
+        if (i < M1) {
+            r = hresp[i];
+            pass = float_order_key(r) >= cut;
+            if constexpr (BUCKET)
+                if (M1 > K2) pass = rank[i] < rank_cut || (rank[i] == rank_cut && pass);
+        }
         int total;
         const int ex = block_excl_scan<SEL_THREADS>(pass ? 1 : 0, warp_sums, total);
         const int pos = written + ex;
@@ -844,7 +902,8 @@ int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfr
     if (g.nbuilt == 0) return ASLAM_OK;
     dim3 grid(g.nbuilt, nframes);
     ProfScope ps(ctx, PK_SELECT);
-    select_kernel<<<grid, SEL_THREADS, 0, ctx->stream>>>(g, b);
+    if (g.grid_cell > 0) select_kernel<true><<<grid, SEL_THREADS, 0, ctx->stream>>>(g, b);
+    else select_kernel<false><<<grid, SEL_THREADS, 0, ctx->stream>>>(g, b);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

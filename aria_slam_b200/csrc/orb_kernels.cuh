@@ -19,6 +19,7 @@ struct OrbBuffers {
     uint32_t *tile_base;   // [B][tiles_per_frame]  scratch of the selection kernel
     uint32_t *surv;        // [B][tiles_per_frame][FT_CAP] (only the head of each level's range is used)
     float *hresp;          // same shape as surv
+    uint32_t *rank;        // same shape as surv; in-cell ranks of the grid-bucketed cull (NULL when grid_cell == 0)
     uint32_t *sel_xy;      // [B][kp_cap]  y<<12 | x, level ranges at LevelGeom::sel_off
     float *sel_resp;       // [B][kp_cap]
     int32_t *sel_cnt;      // [B][ORB_MAX_LEVELS]

@@ -71,11 +71,12 @@ class OrbB200Extractor:
     """IFeatureExtractor over aslam_orb_* -- drop-in for OrbCudaExtractor
     (src/adapters/gpu/OrbCudaExtractor.cpp).  Results follow the reference's CPU path."""
 
-    def __init__(self, max_features=1000, ctx: Optional[Context] = None, blur_mode=2):
+    def __init__(self, max_features=1000, ctx: Optional[Context] = None, blur_mode=2, grid_cell=0):
         self.ctx = ctx or Context(0)
         self._owns_ctx = ctx is None
         self._n = int(max_features)
         self._blur_mode = blur_mode
+        self._grid_cell = int(grid_cell)      # aslam_orb_params::grid_cell; 0 = cv::ORB's plain retainBest
         self._h = None
         self._size = None
         self._pending = None
@@ -85,6 +86,7 @@ class OrbB200Extractor:
         lib().aslam_orb_default_params(C.byref(p))
         p.nfeatures = self._n
         p.blur_mode = self._blur_mode
+        p.grid_cell = self._grid_cell
         return p
 
     def _handle(self, width, height):
@@ -135,6 +137,16 @@ class OrbB200Extractor:
 
     def getMaxFeatures(self):
         return self._n
+
+    def setGridBucketing(self, cell_pixels):
+        """Per-level grid bucketing of the Harris cull (extension, 0 = off); applies from the next extract."""
+        if self._pending is not None:
+            raise RuntimeError("setGridBucketing with an extract pending")
+        if int(cell_pixels) != self._grid_cell:
+            self._grid_cell = int(cell_pixels)
+            if self._h:
+                lib().aslam_orb_destroy(self._h)
+                self._h, self._size = None, None
 
     def close(self):
         if self._h:
@@ -346,11 +358,12 @@ class OrbBatchTracker:
     predecessor in one stream.  This is the high-throughput form of processFrame's
     extract -> match that the frames/s metric is measured on."""
 
-    def __init__(self, width, height, max_features=2000, max_batch=256, ctx: Optional[Context] = None, blur_mode=2):
+    def __init__(self, width, height, max_features=2000, max_batch=256, ctx: Optional[Context] = None, blur_mode=2,
+                 grid_cell=0):
         self.ctx = ctx or Context(0)
         p = _lib.OrbParams()
         lib().aslam_orb_default_params(C.byref(p))
-        p.nfeatures = int(max_features); p.blur_mode = blur_mode
+        p.nfeatures = int(max_features); p.blur_mode = blur_mode; p.grid_cell = int(grid_cell)
         h = C.c_void_p()
         check(lib().aslam_orb_create(self.ctx.h, C.byref(p), width, height, max_batch, C.byref(h)))
         self.h = h

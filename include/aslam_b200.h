@@ -76,6 +76,11 @@ typedef struct {
     int32_t patch_size;      /* 31 */
     int32_t fast_threshold;  /* 20 */
     int32_t blur_mode;       /* 2 = cv2-wheel hybrid FMA split, 1 = always fused, 0 = never */
+    int32_t grid_cell;       /* 0 = off: cv::ORB's plain retainBest (the parity mode, the default).  8..4096 = per-level
+                              * grid bucketing of the second cull with square cells of that many level pixels: within
+                              * a level every cell gives its best corner (by Harris response) before any cell gives
+                              * its second best, until the level's quota is full (ties kept).  An extension named by
+                              * BASELINE.json; neither cv::ORB nor the reference buckets. */
 } aslam_orb_params;
 
 /* ------------------------------------------------------------------ context

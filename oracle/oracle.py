@@ -19,7 +19,7 @@ _SO = os.path.join(_HERE, "liborb_oracle.so")
 
 class OrcParams(C.Structure):
     _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
-                ("edge_threshold", C.c_int), ("fast_threshold", C.c_int)]
+                ("edge_threshold", C.c_int), ("fast_threshold", C.c_int), ("grid_cell", C.c_int)]
 
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
@@ -122,6 +122,15 @@ def fast_nms(score):
     return out[:n]
 
 
+def grid_bucket_keep(xs, ys, resp, quota, cell):
+    """Grid-bucketed second cull (extension, orb_oracle.c): boolean keep mask over the corners."""
+    cs = np.zeros(len(xs), CORNER_DTYPE); cs["x"] = xs; cs["y"] = ys
+    resp = np.ascontiguousarray(resp, np.float32)
+    keep = np.zeros(len(xs) + 1, np.uint8)
+    lib().orc_grid_bucket_keep(_p(cs), _p(resp), len(xs), int(quota), int(cell), _p(keep))
+    return keep[:len(xs)].astype(bool)
+
+
 def harris(img, x, y):
     img = _u8(img)
     return np.float32(lib().orc_harris(_p(img), img.shape[1], int(x), int(y)))
@@ -151,14 +160,16 @@ def brief(blurred, xi, yi, angle):
     return d
 
 
-def orb(img, nfeatures=1000, mask=None, nlevels=8, scale=1.2, edge=31, fast_thr=20, blur_mode=None, cap=None):
-    """Whole ORB; returns (keypoints[KP_DTYPE], descriptors[n,32]) ordered by (level, y, x)."""
+def orb(img, nfeatures=1000, mask=None, nlevels=8, scale=1.2, edge=31, fast_thr=20, blur_mode=None, cap=None,
+        grid_cell=0):
+    """Whole ORB; returns (keypoints[KP_DTYPE], descriptors[n,32]) ordered by (level, y, x).
+    grid_cell > 0 switches the second cull to the grid-bucketed extension (orb_oracle.c; not cv::ORB)."""
     img = _u8(img)
     if mask is not None:
         mask = _u8(mask)
     cap = cap or (4 * nfeatures + 4096)
     kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
-    prm = OrcParams(nfeatures, scale, nlevels, edge, fast_thr)
+    prm = OrcParams(nfeatures, scale, nlevels, edge, fast_thr, int(grid_cell))
     n = lib().orc_orb_detect_and_compute(_p(img), img.shape[1], img.shape[0], img.shape[1],
                                          _p(mask) if mask is not None else None, C.byref(prm),
                                          BLUR_MODE if blur_mode is None else blur_mode,

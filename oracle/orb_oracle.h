@@ -26,6 +26,9 @@ typedef struct {
     int nlevels;         /* 8 */
     int edge_threshold;  /* 31 */
     int fast_threshold;  /* 20 */
+    int grid_cell;       /* 0 = cv::ORB's plain retainBest; > 0 = per-level grid bucketing of the second cull with
+                          * square cells of that many level pixels (an extension named by BASELINE.json's
+                          * north_star; cv::ORB and the reference have nothing like it, see .c) */
 } orc_params;
 
 typedef struct {
@@ -48,6 +51,8 @@ void orc_mask_level(uint8_t *m, int w, int h, int stride);   /* threshold(254, T
 /* A3: FAST-9/16 score map (0 where not a corner) and 3x3 strict NMS */
 void orc_fast_score_map(const uint8_t *img, int w, int h, int stride, int thr, uint8_t *score);
 int orc_fast_nms(const uint8_t *score, int w, int h, orc_corner *out, int cap);
+/* Grid-bucketed variant of the second cull (extension, see .c): keep[i] = 1 for the survivors. */
+int orc_grid_bucket_keep(const orc_corner *cs, const float *resp, int n, int quota, int cell, uint8_t *keep);
 /* A5 / A6 */
 float orc_harris(const uint8_t *img, int stride, int x, int y);
 float orc_fast_atan2(float y, float x);

@@ -58,7 +58,7 @@ def test_struct_layouts_match_reference_types():
     from aria_slam_b200 import _lib
     assert _lib.KP_DTYPE.itemsize == 24 and _lib.MATCH_DTYPE.itemsize == 12 and _lib.BOX_DTYPE.itemsize == 24
     assert _lib.KP_DTYPE.names == ("x", "y", "size", "angle", "response", "octave")
-    assert C.sizeof(_lib.OrbParams) == 40
+    assert C.sizeof(_lib.OrbParams) == 44      # 11 x 4 bytes, aslam_orb_params
 
 
 def test_header_is_plain_c99(tmp_path):
