@@ -74,8 +74,10 @@ static int orb_plan(aslam_orb *o)
 {
     aslam_ctx *ctx = o->ctx;
     std::vector<uint32_t> tabs;
-    build_orb_geometry(o->width, o->height, o->prm.nfeatures, o->prm.scale_factor, o->prm.nlevels,
-                       o->prm.edge_threshold, o->prm.fast_threshold, o->prm.blur_mode, o->g, tabs);
+    if (!build_orb_geometry(o->width, o->height, o->prm.nfeatures, o->prm.scale_factor, o->prm.nlevels,
+                            o->prm.edge_threshold, o->prm.fast_threshold, o->prm.blur_mode, o->g, tabs))
+        return fail(ASLAM_E_INVALID, "scale_factor %.3f on a %dx%d frame puts two levels more than a factor 2 apart",
+                    (double)o->prm.scale_factor, o->width, o->height);
     o->g.grid_cell = o->prm.grid_cell;
     const OrbGeom &g = o->g;
     const size_t B = (size_t)o->max_batch;

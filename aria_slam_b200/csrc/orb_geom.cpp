@@ -41,7 +41,9 @@ static void resize_row_table(int src, int dst, uint32_t *tab)
 //   [0] aligned source word of the window, [1] funnel shift in bits, [2] PRMT selectors of outputs 0,1,
 //   [3] selectors of outputs 2,3, [4..7] weight words (255-c1) | c1 << 8 | 1 << 16.
 // Outputs past the level width repeat the last real column (their bytes land in row padding).
-static void resize_col_table(int src, int dst, uint32_t *tab)
+// Returns false when a group's window does not fit the 8 bytes the kernel's PRMT selectors can address (taps up
+// to 7 bytes past the first one): an effective scale above 2 between two levels.
+static bool resize_col_table(int src, int dst, uint32_t *tab)
 {
     for (int g = 0; g * 4 < dst; ++g) {
         int ofs[4], c1[4];
@@ -52,16 +54,18 @@ static void resize_col_table(int src, int dst, uint32_t *tab)
         t[1] = (uint32_t)(o0 & 3) * 8u;
         uint32_t sel[4];
         for (int i = 0; i < 4; ++i) {
-            const uint32_t k = (uint32_t)(ofs[i] - o0);           // 0..4, so k+1 <= 5 < 8
+            const uint32_t k = (uint32_t)(ofs[i] - o0);           // 0..4 at scale 1.2, 0..6 at scale 2
+            if (k + 1 > 7) return false;
             sel[i] = k | ((k + 1) << 4) | (k << 8) | (k << 12);
             t[4 + i] = (uint32_t)(255 - c1[i]) | ((uint32_t)c1[i] << 8) | (1u << 16);
         }
         t[2] = sel[0] | (sel[1] << 16);
         t[3] = sel[2] | (sel[3] << 16);
     }
+    return true;
 }
 
-void build_orb_geometry(int width, int height, int nfeatures, float scale_factor, int nlevels,
+bool build_orb_geometry(int width, int height, int nfeatures, float scale_factor, int nlevels,
                         int edge, int fast_thr, int blur_mode, OrbGeom &g, std::vector<uint32_t> &tables)
 {
     g = OrbGeom();
@@ -117,7 +121,7 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
             const LevelGeom &P = g.lv[l - 1];
             L.xtab_off = (int)tables.size();
             tables.resize(tables.size() + (size_t)(L.w + 3) / 4 * 8, 0);
-            resize_col_table(P.w, L.w, tables.data() + L.xtab_off);
+            if (!resize_col_table(P.w, L.w, tables.data() + L.xtab_off)) return false;
             L.ytab_off = (int)tables.size();
             tables.resize(tables.size() + (size_t)(L.h + 3) / 4 * 4, 0);
             resize_row_table(P.h, L.h, tables.data() + L.ytab_off);
@@ -128,6 +132,7 @@ void build_orb_geometry(int width, int height, int nfeatures, float scale_factor
     g.blur_tiles_per_frame = blur_off;
     g.desc_blocks_per_frame = desc_off;
     g.kp_cap = (sel_off + 63) / 64 * 64;
+    return true;
 }
 
 }  // namespace aslam

@@ -72,8 +72,10 @@ struct OrbGeom {
     LevelGeom lv[ORB_MAX_LEVELS];
 };
 
-// Fills g and the resize tables (entry = ofs | c1 << 16; c0 = 256 - c1 applies to p[ofs]).
-void build_orb_geometry(int width, int height, int nfeatures, float scale_factor, int nlevels,
+// Fills g and the resize tables (entry = ofs | c1 << 16; c0 = 256 - c1 applies to p[ofs]).  False: two
+// consecutive levels are more than a factor 2 apart in width after rounding (scale_factor 2 on an odd width),
+// which the resize kernel's column window cannot express.
+bool build_orb_geometry(int width, int height, int nfeatures, float scale_factor, int nlevels,
                         int edge, int fast_thr, int blur_mode, OrbGeom &g, std::vector<uint32_t> &tables);
 
 }  // namespace aslam

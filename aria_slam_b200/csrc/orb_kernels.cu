@@ -34,8 +34,10 @@ __device__ __forceinline__ HRow resize_hrow(uint32_t w0, uint32_t w1, uint32_t w
 // One thread = 4 consecutive output columns of a strip of RS_ROWS output rows, marched top to bottom:
 // the column tables stay in registers, every source row of the strip goes through the horizontal pass
 // exactly once (the two latest results are kept), and the raw words of the next source row are
-// fetched one step ahead.  Source rows advance by 1 or 2 per output row (any scale in (1, 2]); the
-// advance depends on y only, so the control flow is uniform over the CTA.
+// fetched one step ahead.  Source rows advance by 0, 1, 2 (or more) per output row -- the march emits whatever
+// output rows have the current source row as lower tap -- and the advance depends on y only, so the control
+// flow is uniform over the CTA.  Columns are windowed: the taps of a group of 4 outputs must lie within 8 bytes
+// of the first one, i.e. a level-to-level factor <= 2 (build_orb_geometry refuses anything else).
 #ifndef ASLAM_RS_ROWS
 #define ASLAM_RS_ROWS 16
 #endif

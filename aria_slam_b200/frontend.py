@@ -359,11 +359,15 @@ class OrbBatchTracker:
     extract -> match that the frames/s metric is measured on."""
 
     def __init__(self, width, height, max_features=2000, max_batch=256, ctx: Optional[Context] = None, blur_mode=2,
-                 grid_cell=0):
+                 grid_cell=0, params: Optional[dict] = None):
         self.ctx = ctx or Context(0)
         p = _lib.OrbParams()
         lib().aslam_orb_default_params(C.byref(p))
         p.nfeatures = int(max_features); p.blur_mode = blur_mode; p.grid_cell = int(grid_cell)
+        for name, value in (params or {}).items():      # any other cv::ORB::create argument (aslam_orb_params field)
+            if name not in dict(_lib.OrbParams._fields_):
+                raise ValueError("unknown ORB parameter %r" % name)
+            setattr(p, name, value)
         h = C.c_void_p()
         check(lib().aslam_orb_create(self.ctx.h, C.byref(p), width, height, max_batch, C.byref(h)))
         self.h = h

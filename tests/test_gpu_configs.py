@@ -137,3 +137,33 @@ def test_structured_frames_with_ties_match_oracle(ctx, oracle, kind):
         assert (f.keypoints["response"][og] == ko["response"][oo]).all() and (f.keypoints["angle"][og] == ko["angle"][oo]).all()
         assert (f.descriptors.reshape(-1, 32)[og] == do[oo]).all(1).mean() >= 0.99
     ex.close()
+
+
+@pytest.mark.parametrize("n,scale,nlevels,edge,thr", [(800, 1.5, 4, 31, 20), (1000, 2.0, 3, 31, 10), (600, 1.1, 8, 25, 40),
+                                                      (1000, 1.2, 5, 40, 20), (500, 1.3, 6, 19, 7)])
+def test_other_create_arguments_match_oracle(ctx, oracle, n, scale, nlevels, edge, thr):
+    """cv::ORB::create arguments the reference never uses but the C ABI accepts: other scale factors (resize tables),
+    level counts (quotas), edge and FAST thresholds.  Levels bit-exact, keypoints and descriptors as the oracle
+    (which tests/test_oracle_cv2.py pins to cv2 at the same arguments)."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import OrbBatchTracker
+    w, h = 752, 480
+    img = synth.frame(w, h, 5)
+    tr = OrbBatchTracker(w, h, n, 1, ctx, params=dict(scale_factor=scale, nlevels=nlevels, edge_threshold=edge,
+                                                      fast_threshold=thr))
+    tr.extract_async(img[None])
+    kps, desc, cnt, _, _ = tr.results()
+    Wl, Hl, _ = oracle.level_geometry(w, h, nlevels, scale)
+    lev = img
+    for l in range(1, nlevels):
+        lev = oracle.resize_exact(lev, int(Wl[l]), int(Hl[l]))
+        if Wl[l] > 2 * edge and Hl[l] > 2 * edge:
+            assert (tr.read_level(0, l) == lev).all(), "level %d" % l
+    ko, do = oracle.orb(img, n, nlevels=nlevels, scale=scale, edge=edge, fast_thr=thr)
+    k, d = kps[0, :cnt[0]], desc[0, :cnt[0]]
+    assert sorted(kp_keys(k)) == sorted(kp_keys(ko))
+    o1, o2 = np.lexsort((k["x"], k["y"], k["octave"])), np.lexsort((ko["x"], ko["y"], ko["octave"]))
+    for name in ("size", "angle", "response"):
+        assert (k[name][o1] == ko[name][o2]).all(), name
+    assert (d[o1] == do[o2]).all(1).mean() >= 0.99
+    tr.close()

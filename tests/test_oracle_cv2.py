@@ -78,6 +78,26 @@ def test_whole_orb_equals_cv2(oracle, w, h, n, seed):
     assert _same(ko, do, kc, dc) >= 0.999
 
 
+@pytest.mark.parametrize("n,scale,nlevels,edge,thr", [(800, 1.5, 4, 31, 20), (1000, 2.0, 3, 31, 10), (600, 1.1, 8, 25, 40),
+                                                      (1000, 1.2, 5, 40, 20), (500, 1.3, 6, 19, 7)])
+def test_whole_orb_equals_cv2_at_other_create_arguments(oracle, n, scale, nlevels, edge, thr):
+    """The reference only ever calls cv::ORB::create(n,1.2f,8,31,0,2,HARRIS_SCORE,31,20); the C ABI also accepts other
+    scale factors, level counts, edge and FAST thresholds, so the restatement is pinned there too."""
+    import cv2
+    from aria_slam_b200 import synth
+    img = synth.frame(752, 480, 5)
+    k, d = cv2.ORB_create(n, scale, nlevels, edge, 0, 2, cv2.ORB_HARRIS_SCORE, 31, thr).detectAndCompute(img, None)
+    kc = np.zeros(len(k), oracle.KP_DTYPE)
+    for i, p in enumerate(k):
+        kc[i] = (p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave)
+    ko, do = oracle.orb(img, n, nlevels=nlevels, scale=scale, edge=edge, fast_thr=thr)
+    assert len(ko) == len(kc) == n
+    oc, oo = np.lexsort((kc["x"], kc["y"], kc["octave"])), np.lexsort((ko["x"], ko["y"], ko["octave"]))
+    for name in ("x", "y", "octave", "size", "angle", "response"):
+        assert (kc[name][oc] == ko[name][oo]).all(), name
+    assert (d[oc] == do[oo]).all()
+
+
 def test_whole_orb_with_mask_equals_cv2(oracle):
     from aria_slam_b200 import synth
     img = synth.frame(700, 500, 3000)
