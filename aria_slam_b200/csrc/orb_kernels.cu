@@ -842,7 +842,7 @@ select_kernel(OrbGeom g, OrbBuffers b)
         // (rank ascending, response descending), keep the first K2 and everything tied with the K2-th.
         rank = b.rank + tile0 * FT_CAP;
         if (M1 > K2) {
-            __shared__ uint32_t s_cell[SEL_THREADS], s_key[SEL_THREADS];
+            __shared__ uint2 s_ck[SEL_THREADS];        // (cell id, ordered response key) of a block of survivors
             const int cell = g.grid_cell;
             auto cell_of = [&](uint32_t e) { return ((e & 0xfffu) / (uint32_t)cell) | ((((e >> 12) & 0xfffu) / (uint32_t)cell) << 12); };
             for (int i0 = 0; i0 < M1; i0 += SEL_THREADS) {
@@ -853,11 +853,14 @@ select_kernel(OrbGeom g, OrbBuffers b)
                 for (int j0 = 0; j0 < M1; j0 += SEL_THREADS) {
                     __syncthreads();
                     const int j = j0 + tid;
-                    s_cell[tid] = j < M1 ? cell_of(surv[j]) : 0xffffffffu;
-                    s_key[tid] = j < M1 ? float_order_key(hresp[j]) : 0u;
+                    s_ck[tid] = j < M1 ? make_uint2(cell_of(surv[j]), float_order_key(hresp[j])) : make_uint2(0xffffffffu, 0u);
                     __syncthreads();
-                    const int n = min(SEL_THREADS, M1 - j0);
-                    for (int k = 0; k < n; ++k) r += (s_cell[k] == mycell) & (s_key[k] > mykey);
+                    const int n = min(SEL_THREADS, M1 - j0);        // padding entries match no cell: whole groups of 4 are safe
+#pragma unroll 4
+                    for (int k = 0; k < ((n + 3) & ~3); ++k) {
+                        const uint2 o = s_ck[k];                    // one broadcast 64-bit load
+                        r += (o.x == mycell) & (o.y > mykey);
+                    }
                 }
                 if (i < M1) rank[i] = r;
             }

@@ -22,6 +22,24 @@ def frame(w=752, h=480, seed=1):
     return np.ascontiguousarray(img)
 
 
+def natural_frame(w=752, h=480, seed=1, slope=1.6):
+    """A second image family for the parity tests: noise with a 1/f^slope amplitude spectrum (the statistics of
+    natural scenes -- large smooth regions, few strong corners, levels that do not reach their quota) plus a few
+    dark/bright polygons' worth of sharp edges."""
+    rs = np.random.RandomState(seed)
+    fy = np.fft.fftfreq(h)[:, None]; fx = np.fft.rfftfreq(w)[None, :]
+    amp = 1.0 / np.maximum(np.hypot(fx, fy), 1.0 / max(w, h)) ** slope
+    spec = amp * np.exp(2j * np.pi * rs.rand(h, fx.shape[1]))
+    a = np.fft.irfft2(spec, s=(h, w))
+    lo, hi = np.percentile(a, (1, 99))
+    img = np.clip((a - lo) / max(hi - lo, 1e-9) * 255.0, 0, 255).astype(np.uint8)
+    for _ in range(12):
+        rw, rh = rs.randint(20, 120, 2)
+        x0 = rs.randint(0, max(1, w - rw)); y0 = rs.randint(0, max(1, h - rh))
+        img[y0:y0 + rh, x0:x0 + rw] = np.clip(img[y0:y0 + rh, x0:x0 + rw].astype(np.int32) + rs.randint(-90, 91), 0, 255)
+    return np.ascontiguousarray(img)
+
+
 def shifted(img, dx=3, dy=2, sigma=2.0, seed=2):
     """Second frame of a pair: integer translation (REFLECT_101 fill) plus Gaussian noise."""
     h, w = img.shape

@@ -21,6 +21,7 @@ def _params(**kw):
     (dict(nfeatures=-1), 640, 480, 1), (dict(nlevels=9), 640, 480, 1), (dict(nlevels=0), 640, 480, 1),
     (dict(scale_factor=1.0), 640, 480, 1), (dict(scale_factor=2.5), 640, 480, 1), (dict(edge_threshold=10), 640, 480, 1),
     (dict(wta_k=3), 640, 480, 1), (dict(patch_size=15), 640, 480, 1), (dict(fast_threshold=0), 640, 480, 1),
+    (dict(grid_cell=7), 640, 480, 1), (dict(scale_factor=2.0, nlevels=3), 753, 480, 1),     # 753 -> 376: a factor above 2
     (dict(), 0, 480, 1), (dict(), 640, 5000, 1), (dict(), 640, 480, 0)])
 def test_orb_create_rejects_bad_arguments(ctx, kw, w, h, batch):
     from aria_slam_b200 import _lib

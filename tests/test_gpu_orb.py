@@ -111,6 +111,23 @@ def test_orb_end_to_end_vs_oracle_and_cv2(ctx, oracle, w, h, n, seed):
     assert (np.diff(f.keypoints["octave"]) >= 0).all()
 
 
+@pytest.mark.parametrize("w,h,n,seed,slope", [(752, 480, 1000, 1, 1.6), (752, 480, 2000, 2, 1.0), (640, 480, 1000, 3, 1.3),
+                                              (1408, 1408, 4000, 4, 1.6)])
+def test_orb_on_natural_statistics_vs_oracle_and_cv2(ctx, oracle, w, h, n, seed, slope):
+    """1/f^slope noise: few strong corners, most levels below quota, long flat stretches where the FAST quick-reject
+    discards whole warps -- the regime of real camera frames, unlike synth.frame."""
+    from aria_slam_b200 import synth
+    img = synth.natural_frame(w, h, seed, slope)
+    f = _extract(ctx, img, n)
+    ko, do = oracle.orb(img, n)
+    eq, frac, sdesc, sang, sresp, ssize = _compare(f.keypoints, f.descriptors, ko, do)
+    assert eq and frac == 1.0 and len(ko) > 50
+    assert sresp == 1.0 and sang == 1.0 and ssize == 1.0 and sdesc >= 0.99
+    kc, dc = oracle.cv2_orb(img, n)
+    eq, frac, sdesc, sang, sresp, ssize = _compare(f.keypoints, f.descriptors, kc, dc)
+    assert frac >= 0.99 and sdesc >= 0.99 and sang >= 0.99
+
+
 def test_orb_with_mask_matches_cv2(ctx, oracle):
     from aria_slam_b200 import synth
     w = h = 1408

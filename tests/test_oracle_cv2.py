@@ -98,6 +98,21 @@ def test_whole_orb_equals_cv2_at_other_create_arguments(oracle, n, scale, nlevel
     assert (d[oc] == do[oo]).all()
 
 
+@pytest.mark.parametrize("w,h,n,seed,slope", [(752, 480, 1000, 1, 1.6), (752, 480, 2000, 2, 1.0), (640, 480, 1000, 3, 1.3)])
+def test_whole_orb_equals_cv2_on_natural_statistics(oracle, w, h, n, seed, slope):
+    """1/f^slope noise: smooth regions, few strong corners, most levels below their quota (a different regime
+    from synth.frame, whose levels all saturate)."""
+    from aria_slam_b200 import synth
+    img = synth.natural_frame(w, h, seed, slope)
+    ko, do = oracle.orb(img, n)
+    kc, dc = oracle.cv2_orb(img, n)
+    assert len(ko) == len(kc) > 50
+    oo, oc = np.lexsort((ko["x"], ko["y"], ko["octave"])), np.lexsort((kc["x"], kc["y"], kc["octave"]))
+    for name in ("x", "y", "octave", "size", "angle", "response"):
+        assert (ko[name][oo] == kc[name][oc]).all(), name
+    assert (do[oo] == dc[oc]).all()
+
+
 def test_whole_orb_with_mask_equals_cv2(oracle):
     from aria_slam_b200 import synth
     img = synth.frame(700, 500, 3000)

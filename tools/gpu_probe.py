@@ -10,12 +10,16 @@ ctx = Context(0)
 out = {"sm_count": ctx.sm_count}
 for which, name in enumerate(["popc", "lop3", "iadd3", "vimnmx3_u16x2", "hmnmx2", "vimnmx3+hmnmx2", "imad", "prmt"]):
     out["gops_" + name] = ctx.microbench(which)
-frames = synth.frame_stream(32, 752, 480, 1000)
+if os.environ.get("ASLAM_PROBE_FRAMES", "") == "natural":       # 1/f noise: the FAST quick-reject discards most pixel pairs
+    frames = np.stack([synth.natural_frame(752, 480, 1000 + i) if i % 2 == 0 else synth.shifted(synth.natural_frame(752, 480, 999 + i), seed=i)
+                       for i in range(32)])
+else:
+    frames = synth.frame_stream(32, 752, 480, 1000)
 B = 256
 batch = np.ascontiguousarray(np.concatenate([frames] * (B // 32)))
 import torch
 d = torch.from_numpy(batch).cuda()
-tr = OrbBatchTracker(752, 480, 2000, B, ctx)
+tr = OrbBatchTracker(752, 480, 2000, B, ctx, grid_cell=int(os.environ.get("ASLAM_PROBE_GRID_CELL", "0")))
 ctx.prof_enable(True)
 for it in range(3):
     tr.track_async(d, 0.75, on_device=True); tr.device_results()
