@@ -234,6 +234,17 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*A)[FA_PITCH
     return __viaddmax_s16x2_relu(__vmaxu2(a, bq), neg_thr, 0u);
 }
 
+// NMS rows without a single positive score are skipped by the whole warp (one vote per row): on camera-like
+// frames most rows of a tile are such rows; on the dense synthetic frames almost none are.
+#ifndef ASLAM_FAST_NMS_SKIP
+#define ASLAM_FAST_NMS_SKIP 1
+#endif
+#if ASLAM_FAST_NMS_SKIP
+#define NMS_ROW_HAS_SCORES(word) __any_sync(0xffffffffu, (word) != 0u)
+#else
+#define NMS_ROW_HAS_SCORES(word) true
+#endif
+
 __global__ void __launch_bounds__(256, ASLAM_FAST_MINB)
 fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
 {
@@ -357,7 +368,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     for (int k = 0; k < RPW; ++k) {
         const int r = 1 + RPW * warp + k;
         uint32_t e = 0;
-        if (r <= FT_OUT_H && sy0 + r < L.h - g.edge) {
+        if (r <= FT_OUT_H && sy0 + r < L.h - g.edge && NMS_ROW_HAS_SCORES(S[r][p])) {
             const uint32_t up = S[r - 1][p], cur = S[r][p], dn = S[r + 1][p];
             const uint32_t V = __vmaxu2(up, dn), C3 = max3(up, cur, dn);
             const uint32_t Lw = __shfl_up_sync(0xffffffffu, C3, 1), Rw = __shfl_down_sync(0xffffffffu, C3, 1);
