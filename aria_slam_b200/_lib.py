@@ -67,6 +67,8 @@ SYMBOLS = {
     "aslam_orb_read_level": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "aslam_orb_read_corners": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int)]),
     "aslam_match_knn2": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_float, _P, C.POINTER(C.c_int)]),
+    "aslam_match_knn2_dynamic": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_float, _P, C.c_int, C.c_int, _P,
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "aslam_knn2_raw": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "aslam_match_multi": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P]),
     "aslam_match_knn2_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_float, _P, _P]),

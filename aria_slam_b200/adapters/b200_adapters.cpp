@@ -117,6 +117,34 @@ void B200Matcher::match(const core::Frame& query, const core::Frame& train, std:
     }
 }
 
+int B200Matcher::matchDynamic(const core::Frame& query, const core::Frame& train,
+                              const std::vector<core::Detection>& detections, std::vector<core::Match>& matches,
+                              float ratio_threshold)
+{
+    if (query.descriptors.empty() || train.descriptors.empty()) return 0;
+    const int nq = (int)(query.descriptors.size() / 32), nt = (int)(train.descriptors.size() / 32);
+    if ((int)query.keypoints.size() != nq || (int)train.keypoints.size() != nt)
+        throw std::runtime_error("aslam_b200: matchDynamic needs one keypoint per descriptor row");
+    auto pack = [](const std::vector<core::KeyPoint>& src) {
+        std::vector<aslam_keypoint> out(src.size());
+        for (size_t i = 0; i < src.size(); ++i) out[i] = {src[i].x, src[i].y, src[i].size, src[i].angle, src[i].response, src[i].octave};
+        return out;
+    };
+    const std::vector<aslam_keypoint> qk = pack(query.keypoints), tk = pack(train.keypoints);
+    std::vector<aslam_box> boxes;
+    for (const auto& d : detections) boxes.push_back({d.x1, d.y1, d.x2, d.y2, d.confidence, d.class_id});
+    buf_.resize((size_t)nq);
+    int n = 0, filtered = 0;
+    check(aslam_match_knn2_dynamic(ctx_->get(), query.descriptors.data(), qk.data(), nq, train.descriptors.data(), tk.data(), nt,
+                                   ratio_threshold, boxes.data(), (int)boxes.size(), /*half_open=*/0, buf_.data(), &n, &filtered));
+    for (int i = 0; i < n; ++i) {
+        core::Match m;
+        m.query_idx = buf_[(size_t)i].query_idx; m.train_idx = buf_[(size_t)i].train_idx; m.distance = buf_[(size_t)i].distance;
+        matches.push_back(m);
+    }
+    return filtered;
+}
+
 void B200Matcher::matchMultiple(const core::Frame& query, const std::vector<core::Frame>& candidates,
                                 std::vector<std::vector<core::Match>>& all_matches, float ratio_threshold)
 {

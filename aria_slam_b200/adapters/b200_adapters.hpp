@@ -72,6 +72,10 @@ public:
                float ratio_threshold = 0.75f) override;
     void matchMultiple(const core::Frame& query, const std::vector<core::Frame>& candidates,
                        std::vector<std::vector<core::Match>>& all_matches, float ratio_threshold = 0.75f) override;
+    // The legacy tracking loop's form (src/main.cpp:158-175): match(), then drop matches whose query or train keypoint
+    // lies inside a detection of a dynamic class (core::Detection::contains).  Returns main.cpp's filtered_count.
+    int matchDynamic(const core::Frame& query, const core::Frame& train, const std::vector<core::Detection>& detections,
+                     std::vector<core::Match>& matches, float ratio_threshold = 0.75f);
 private:
     std::shared_ptr<Context> ctx_;
     std::vector<aslam_match> buf_;

@@ -52,6 +52,25 @@ struct ProfScope {
     ~ProfScope();
 };
 
+#ifdef __CUDACC__
+// DYNAMIC_CLASSES of the reference (src/main.cpp:29-41): person, bicycle, car, motorcycle, bus, train, truck, bird, cat, dog
+__device__ __forceinline__ bool is_dynamic_class(int c)
+{
+    return c == 0 || c == 1 || c == 2 || c == 3 || c == 5 || c == 6 || c == 7 || c == 14 || c == 15 || c == 16;
+}
+
+// isInDynamicObject (src/main.cpp:43-50).  half_open: cv::Rect::contains (x1 <= x < x2); else Detection::contains (closed).
+__device__ __forceinline__ bool in_dynamic_box(float x, float y, const aslam_box *__restrict__ boxes, int nboxes, int half_open)
+{
+    for (int j = 0; j < nboxes; ++j) {
+        const aslam_box bx = boxes[j];
+        if (!is_dynamic_class(bx.class_id) || x < bx.x1 || y < bx.y1) continue;
+        if (half_open ? (x < bx.x2 && y < bx.y2) : (x <= bx.x2 && y <= bx.y2)) return true;
+    }
+    return false;
+}
+#endif
+
 }  // namespace aslam
 
 #define ASLAM_CUDA(expr)                                                                      \

@@ -226,9 +226,12 @@ __global__ void __launch_bounds__(FIN_THREADS)
 knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__restrict__ partial,
                            int splits, int q_stride, RatioTest rt,
                            aslam_match *__restrict__ out, int out_stride, int32_t *__restrict__ nout,
-                           int32_t *__restrict__ raw_idx, int32_t *__restrict__ raw_dist)
+                           int32_t *__restrict__ raw_idx, int32_t *__restrict__ raw_dist, const DynFilter F)
 {
     __shared__ int warp_sums[FIN_THREADS / 32];
+    __shared__ int s_filtered;
+    if (threadIdx.x == 0) s_filtered = 0;
+    __syncthreads();
     const int g = blockIdx.x;
     const KnnProblem P = probs[g * splits];
     const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
@@ -244,7 +247,14 @@ knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__
             raw_idx[o] = k1 == KEY_EMPTY ? -1 : i0;      raw_dist[o] = k1 == KEY_EMPTY ? -1 : (int)d0;
             raw_idx[o + 1] = k2 == KEY_EMPTY ? -1 : i1;  raw_dist[o + 1] = k2 == KEY_EMPTY ? -1 : (int)d1;
         }
-        const int pass = (q < nq && k2 != KEY_EMPTY && ratio_pass(d0, d1, rt)) ? 1 : 0;
+        int pass = (q < nq && k2 != KEY_EMPTY && ratio_pass(d0, d1, rt)) ? 1 : 0;
+        if (pass && F.boxes) {          // src/main.cpp:166-173: either endpoint on a dynamic object drops the match
+            const aslam_keypoint a = F.q_kps[q], b = F.t_kps[i0];
+            if (in_dynamic_box(a.x, a.y, F.boxes, F.nboxes, F.half_open) || in_dynamic_box(b.x, b.y, F.boxes, F.nboxes, F.half_open)) {
+                pass = 0;
+                atomicAdd(&s_filtered, 1);
+            }
+        }
         int total;
         const int pos = block_exclusive_scan(pass, warp_sums, total);
         if (pass && out) {
@@ -255,6 +265,7 @@ knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__
         written += total;
     }
     if (threadIdx.x == 0 && nout) nout[g] = written;
+    if (threadIdx.x == 0 && F.nfiltered) F.nfiltered[g] = s_filtered;      // ordered after the loop's last barrier
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -445,12 +456,12 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
 int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
                                int ngroups, int splits, int q_stride, RatioTest rt,
                                aslam_match *d_out, int out_stride, int32_t *d_nout,
-                               int32_t *d_raw_idx, int32_t *d_raw_dist)
+                               int32_t *d_raw_idx, int32_t *d_raw_dist, const DynFilter &filter)
 {
     if (ngroups <= 0) return ASLAM_OK;
     ProfScope ps(ctx, PK_KNN_FINISH);
     knn2_finish_matches_kernel<<<ngroups, FIN_THREADS, 0, ctx->stream>>>(
-        d_probs, d_partial, splits, q_stride, rt, d_out, out_stride, d_nout, d_raw_idx, d_raw_dist);
+        d_probs, d_partial, splits, q_stride, rt, d_out, out_stride, d_nout, d_raw_idx, d_raw_dist, filter);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
@@ -546,9 +557,17 @@ using namespace aslam;
 
 // ------------------------------------------------------------------ host-buffer entry points
 // Scratch layout (device): [problems][q rows][t rows][partial][matches][nout][raw idx][raw dist]
+struct HostDynFilter {          // host buffers of aslam_match_knn2_dynamic
+    const aslam_keypoint *q_kps, *t_kps;
+    const aslam_box *boxes;
+    int nboxes, half_open;
+    int *nfiltered;
+};
+
 static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
                       bool inputs_on_device, RatioTest rt, aslam_match *out, int *nout,
-                      int32_t *raw_idx, int32_t *raw_dist, aslam_match *d_out_user, int32_t *d_nout_user)
+                      int32_t *raw_idx, int32_t *raw_dist, aslam_match *d_out_user, int32_t *d_nout_user,
+                      const HostDynFilter *hf = nullptr)
 {
     ASLAM_CUDA(cudaSetDevice(ctx->device));
     if (nt > KNN_MAX_ROWS) return fail(ASLAM_E_INVALID, "train set has %d rows; at most %d per call", nt, KNN_MAX_ROWS);
@@ -562,7 +581,10 @@ static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t
     const size_t o_nout = align_up(o_match + sizeof(aslam_match) * (size_t)nq, 256);
     const size_t o_ridx = align_up(o_nout + 256, 256);
     const size_t o_rdist = align_up(o_ridx + sizeof(int32_t) * 2 * (size_t)q_stride, 256);
-    const size_t total = align_up(o_rdist + sizeof(int32_t) * 2 * (size_t)q_stride, 256);
+    const size_t o_qkp = align_up(o_rdist + sizeof(int32_t) * 2 * (size_t)q_stride, 256);
+    const size_t o_tkp = align_up(o_qkp + (hf ? sizeof(aslam_keypoint) * (size_t)nq : 0), 256);
+    const size_t o_box = align_up(o_tkp + (hf ? sizeof(aslam_keypoint) * (size_t)nt : 0), 256);
+    const size_t total = align_up(o_box + (hf ? sizeof(aslam_box) * (size_t)hf->nboxes : 0), 256);
     const size_t h_need = 256;
     int rc = ensure_scratch(ctx, total, h_need);
     if (rc) return rc;
@@ -583,7 +605,16 @@ static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t
     int32_t *dn = d_nout_user ? d_nout_user : (int32_t *)(base + o_nout);
     int32_t *dri = raw_idx ? (int32_t *)(base + o_ridx) : nullptr;
     int32_t *drd = raw_idx ? (int32_t *)(base + o_rdist) : nullptr;
-    rc = launch_knn2_finish_matches(ctx, dp, dpart, 1, splits, q_stride, rt, dm, nq, dn, dri, drd);
+    DynFilter F;
+    if (hf) {
+        ASLAM_CUDA(cudaMemcpyAsync(base + o_qkp, hf->q_kps, sizeof(aslam_keypoint) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
+        ASLAM_CUDA(cudaMemcpyAsync(base + o_tkp, hf->t_kps, sizeof(aslam_keypoint) * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+        ASLAM_CUDA(cudaMemcpyAsync(base + o_box, hf->boxes, sizeof(aslam_box) * (size_t)hf->nboxes, cudaMemcpyHostToDevice, ctx->stream));
+        F.q_kps = (const aslam_keypoint *)(base + o_qkp); F.t_kps = (const aslam_keypoint *)(base + o_tkp);
+        F.boxes = (const aslam_box *)(base + o_box); F.nboxes = hf->nboxes; F.half_open = hf->half_open;
+        F.nfiltered = dn + 1;           // second word of the 256-byte count slot
+    }
+    rc = launch_knn2_finish_matches(ctx, dp, dpart, 1, splits, q_stride, rt, dm, nq, dn, dri, drd, F);
     if (rc) return rc;
     if (d_out_user) return ASLAM_OK;     // fully asynchronous device form
     if (raw_idx) {
@@ -591,9 +622,10 @@ static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t
         ASLAM_CUDA(cudaMemcpyAsync(raw_dist, drd, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
     }
     int32_t *hn = (int32_t *)ctx->h_scratch;
-    ASLAM_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ASLAM_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int32_t) * (hf ? 2 : 1), cudaMemcpyDeviceToHost, ctx->stream));
     ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (nout) *nout = *hn;
+    if (hf && hf->nfiltered) *hf->nfiltered = hn[1];
     if (out && *hn > 0)
         ASLAM_CUDA(cudaMemcpy(out, dm, sizeof(aslam_match) * (size_t)*hn, cudaMemcpyDeviceToHost));
     return ASLAM_OK;
@@ -609,6 +641,24 @@ extern "C" int aslam_match_knn2(aslam_ctx *ctx, const uint8_t *q, int nq, const 
     if (nq == 0 || nt < 2) return ASLAM_OK;
     ASLAM_REQUIRE(q && t && out, "NULL descriptor or output pointer");
     return run_single(ctx, q, nq, t, nt, false, make_ratio((double)ratio, 0), out, nout, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int aslam_match_knn2_dynamic(aslam_ctx *ctx, const uint8_t *q, const aslam_keypoint *q_kps, int nq,
+                                        const uint8_t *t, const aslam_keypoint *t_kps, int nt, float ratio,
+                                        const aslam_box *boxes, int nboxes, int half_open,
+                                        aslam_match *out, int *nout, int *nfiltered)
+{
+    ASLAM_REQUIRE(ctx && nout, "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nt >= 0 && nboxes >= 0, "negative count");
+    *nout = 0;
+    if (nfiltered) *nfiltered = 0;
+    if (nq == 0 || nt < 2) return ASLAM_OK;
+    ASLAM_REQUIRE(q && t && out, "NULL descriptor or output pointer");
+    if (nboxes == 0)
+        return run_single(ctx, q, nq, t, nt, false, make_ratio((double)ratio, 0), out, nout, nullptr, nullptr, nullptr, nullptr);
+    ASLAM_REQUIRE(q_kps && t_kps && boxes, "NULL keypoints or boxes");
+    const HostDynFilter hf{q_kps, t_kps, boxes, nboxes, half_open ? 1 : 0, nfiltered};
+    return run_single(ctx, q, nq, t, nt, false, make_ratio((double)ratio, 0), out, nout, nullptr, nullptr, nullptr, nullptr, &hf);
 }
 
 extern "C" int aslam_knn2_raw(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,

@@ -31,6 +31,17 @@ struct RatioTest {
     int disabled;    // ratio < 0: keep every query that has two neighbours (extension)
 };
 
+// The legacy tracking loop's match filter (src/main.cpp:164-175 of the reference): a match is dropped when its query
+// keypoint OR its train keypoint lies inside a detection box of a dynamic class (src/main.cpp:29-50).  boxes == NULL
+// switches it off.  half_open: 1 = cv::Rect::contains as main.cpp uses it (x1 <= x < x2), 0 = core::Detection::contains
+// (x1 <= x <= x2, include/core/Types.hpp:109-111).  nfiltered[group] receives main.cpp's filtered_count.
+struct DynFilter {
+    const aslam_keypoint *q_kps = nullptr, *t_kps = nullptr;
+    const aslam_box *boxes = nullptr;
+    int nboxes = 0, half_open = 0;
+    int32_t *nfiltered = nullptr;
+};
+
 // Number of row ranges to cut a train set into so the grid covers the GPU a few times.
 int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets);
 // d_probs[0..splits) = the pair (q, t) cut into equal row ranges (device-side table build).
@@ -51,7 +62,7 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
 int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
                                int ngroups, int splits, int q_stride, RatioTest rt,
                                aslam_match *d_out, int out_stride, int32_t *d_nout,
-                               int32_t *d_raw_idx, int32_t *d_raw_dist);
+                               int32_t *d_raw_idx, int32_t *d_raw_dist, const DynFilter &filter = DynFilter());
 
 // One count per slot: queries passing the ratio test within that slot alone.
 int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,

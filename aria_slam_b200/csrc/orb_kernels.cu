@@ -1153,12 +1153,7 @@ int launch_describe(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int n
 
 // ------------------------------------------------------------------ dynamic-object filter (a4)
 // src/main.cpp:29-50 DYNAMIC_CLASSES {0,1,2,3,5,6,7,14,15,16}; Detection::contains is closed on
-// floats (include/core/Types.hpp:109-111).  One CTA compacts one frame's keypoints in order.
-__device__ __forceinline__ bool is_dynamic_class(int c)
-{
-    return c == 0 || c == 1 || c == 2 || c == 3 || c == 5 || c == 6 || c == 7 || c == 14 || c == 15 || c == 16;
-}
-
+// floats (include/core/Types.hpp:109-111): in_dynamic_box of common.cuh.  One CTA compacts one frame's keypoints in order.
 __global__ void __launch_bounds__(256)
 box_filter_kernel(aslam_keypoint *kps, uint8_t *desc, int32_t *count, int cap,
                   const aslam_box *__restrict__ boxes, int nboxes, aslam_keypoint *tmp_kps, uint8_t *tmp_desc)
@@ -1172,11 +1167,7 @@ box_filter_kernel(aslam_keypoint *kps, uint8_t *desc, int32_t *count, int cap,
         aslam_keypoint k;
         if (i < n) {
             k = kps[i];
-            keep = true;
-            for (int j = 0; j < nboxes; ++j) {
-                const aslam_box bx = boxes[j];
-                if (is_dynamic_class(bx.class_id) && k.x >= bx.x1 && k.x <= bx.x2 && k.y >= bx.y1 && k.y <= bx.y2) { keep = false; break; }
-            }
+            keep = !in_dynamic_box(k.x, k.y, boxes, nboxes, 0);
         }
         int total;
         const int ex = block_excl_scan<256>(keep ? 1 : 0, warp_sums, total);

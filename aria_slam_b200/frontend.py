@@ -174,6 +174,22 @@ class B200Matcher:
         check(lib().aslam_match_knn2(self.ctx.h, ptr(q), len(q), ptr(t), len(t), C.c_float(ratio_threshold), ptr(out), C.byref(n)))
         matches.extend(out[:n.value])
 
+    # The legacy tracking loop's form (src/main.cpp:158-175): ratio test, then drop matches with an endpoint on a
+    # dynamic object.  Appends like match(); returns main.cpp's filtered_count.
+    def matchDynamic(self, query: Frame, train: Frame, detections, matches: list, ratio_threshold=0.75, half_open=True):
+        if len(query.descriptors) == 0 or len(train.descriptors) == 0:
+            return 0
+        q = np.ascontiguousarray(query.descriptors, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train.descriptors, np.uint8).reshape(-1, 32)
+        qk = np.ascontiguousarray(query.keypoints, KP_DTYPE); tk = np.ascontiguousarray(train.keypoints, KP_DTYPE)
+        b = None if detections is None or len(detections) == 0 else as_boxes(detections)
+        out = np.zeros(len(q), MATCH_DTYPE); n = C.c_int(0); nf = C.c_int(0)
+        check(lib().aslam_match_knn2_dynamic(self.ctx.h, ptr(q), ptr(qk), len(q), ptr(t), ptr(tk), len(t),
+                                             C.c_float(ratio_threshold), ptr(b), 0 if b is None else len(b),
+                                             1 if half_open else 0, ptr(out), C.byref(n), C.byref(nf)))
+        matches.extend(out[:n.value])
+        return nf.value
+
     # IMatcher::matchMultiple (IMatcher.hpp:27-37) as one batched launch
     def matchMultiple(self, query: Frame, candidates: List[Frame], all_matches: list, ratio_threshold=0.75):
         while len(all_matches) < len(candidates):

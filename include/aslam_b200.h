@@ -184,6 +184,17 @@ ASLAM_API int aslam_orb_read_corners(aslam_orb *orb, int frame, int level, uint3
  * yields *nout = 0 (the reference emits a match only when both neighbours exist). */
 ASLAM_API int aslam_match_knn2(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
                                float ratio, aslam_match *out, int *nout);
+/* The legacy tracking loop's form (src/main.cpp:158-175): as aslam_match_knn2, and a surviving match is dropped when
+ * its query keypoint OR its train keypoint lies inside a detection box of a dynamic class (isInDynamicObject,
+ * src/main.cpp:29-50).  q_kps[nq] / t_kps[nt] are the keypoints the descriptor rows belong to.
+ * half_open = 1: cv::Rect::contains as main.cpp calls it on TRTInference's Detection::box, with x1 = box.x,
+ * x2 = box.x + box.width (x1 <= x < x2); half_open = 0: aria::core::Detection::contains (x1 <= x <= x2,
+ * include/core/Types.hpp:109-111).  *nfiltered (may be NULL) = matches removed, main.cpp's filtered_count.
+ * The predicate runs inside the match compaction kernel; nboxes == 0 is aslam_match_knn2. */
+ASLAM_API int aslam_match_knn2_dynamic(aslam_ctx *ctx, const uint8_t *q, const aslam_keypoint *q_kps, int nq,
+                                       const uint8_t *t, const aslam_keypoint *t_kps, int nt, float ratio,
+                                       const aslam_box *boxes, int nboxes, int half_open,
+                                       aslam_match *out, int *nout, int *nfiltered);
 /* Raw neighbours: idx[nq][2], dist[nq][2]; -1 where fewer than two train rows exist. */
 ASLAM_API int aslam_knn2_raw(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
                              int32_t *idx, int32_t *dist);

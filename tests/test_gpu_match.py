@@ -75,6 +75,74 @@ def test_match_appends_and_empty_sides(ctx):
     assert len(sentinel) == before
 
 
+DYNAMIC = {0, 1, 2, 3, 5, 6, 7, 14, 15, 16}          # src/main.cpp:29-41
+
+
+def _in_dynamic(x, y, boxes, half_open):
+    """isInDynamicObject (src/main.cpp:43-50) on float32 values, with cv::Rect::contains (half-open) or
+    core::Detection::contains (closed, include/core/Types.hpp:109-111)."""
+    for x1, y1, x2, y2, _, cls in boxes:
+        if int(cls) in DYNAMIC and x >= x1 and y >= y1 and ((x < x2 and y < y2) if half_open else (x <= x2 and y <= y2)):
+            return True
+    return False
+
+
+@pytest.mark.parametrize("half_open", [True, False])
+def test_match_dynamic_follows_the_legacy_tracking_loop(ctx, oracle, half_open):
+    """src/main.cpp:158-175: knnMatch(k=2) + 0.75 ratio, then a match is kept only if neither its query keypoint nor
+    its train keypoint lies in a dynamic-class detection; filtered_count counts the rest.  Real extracted frames, boxes
+    whose edges pass exactly through keypoint coordinates (the half-open / closed difference) and a static class."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import OrbB200Extractor, B200Matcher, Frame
+    a = synth.frame(640, 480, 51); b = synth.shifted(a, seed=52)
+    ex = OrbB200Extractor(1000, ctx)
+    fa, fb = Frame(), Frame()
+    ex.extract(a, 640, 480, fa); ex.extract(b, 640, 480, fb)
+    ex.close()
+    _, boxes = synth.mask_and_boxes(640, 480, 53)
+    boxes[1, 5] = 9                                       # traffic light: static, must not filter anything
+    k = fb.keypoints[np.argsort(fb.keypoints["x"])[len(fb.keypoints) // 2]]
+    boxes[2, :4] = (k["x"] - 40, k["y"] - 30, k["x"], k["y"])          # a keypoint exactly on the far corner
+    k = fa.keypoints[7]
+    boxes[3, :4] = (k["x"], k["y"], k["x"] + 25, k["y"] + 35)          # and one exactly on the near corner
+    mt = B200Matcher(ctx)
+    got = []
+    nf = mt.matchDynamic(fb, fa, boxes, got, 0.75, half_open=half_open)
+    idx, dist = oracle.knn2(fb.descriptors.reshape(-1, 32), fa.descriptors.reshape(-1, 32))
+    survivors = oracle.ratio_matches(idx, dist, 3, 4)
+    keep, dropped = [], 0
+    for qi, ti, d in survivors.tolist():
+        p1, p2 = fb.keypoints[qi], fa.keypoints[ti]
+        if _in_dynamic(p1["x"], p1["y"], boxes, half_open) or _in_dynamic(p2["x"], p2["y"], boxes, half_open):
+            dropped += 1
+        else:
+            keep.append((qi, ti, d))
+    assert [(int(m["query_idx"]), int(m["train_idx"]), int(m["distance"])) for m in got] == keep
+    assert nf == dropped and dropped > 20 and len(keep) > 100
+    # no boxes = IMatcher::match
+    plain, same = [], []
+    mt.match(fb, fa, plain, 0.75)
+    assert mt.matchDynamic(fb, fa, None, same, 0.75) == 0
+    assert [tuple(x) for x in same] == [tuple(x) for x in plain] and len(plain) == len(keep) + dropped
+
+
+def test_match_dynamic_half_open_and_closed_differ_only_on_the_far_edge(ctx):
+    from aria_slam_b200.frontend import B200Matcher, Frame
+    from aria_slam_b200._lib import KP_DTYPE
+    d = _rand_desc(64, 77)
+    kps = np.zeros(64, KP_DTYPE)
+    kps["x"] = np.arange(64, dtype=np.float32) * 2.5; kps["y"] = 10.0
+    q = Frame(keypoints=kps, descriptors=d.reshape(-1)); t = Frame(keypoints=kps.copy(), descriptors=d.reshape(-1).copy())
+    box = np.array([[25.0, 10.0, 50.0, 10.0, 0.9, 0]], np.float32)            # zero-height box on the keypoint row
+    mt = B200Matcher(ctx)
+    closed, half = [], []
+    nf_closed = mt.matchDynamic(q, t, box, closed, 0.99, half_open=False)
+    nf_half = mt.matchDynamic(q, t, box, half, 0.99, half_open=True)
+    on_closed = int(((kps["x"] >= 25) & (kps["x"] <= 50)).sum())
+    assert nf_closed == on_closed == 11 and len(closed) == 64 - 11
+    assert nf_half == 0 and len(half) == 64                                    # y < y2 never holds for a zero-height rect
+
+
 def test_match_multiple_equals_looped_match(ctx):
     from aria_slam_b200.frontend import B200Matcher, Frame
     mt = B200Matcher(ctx)
