@@ -49,6 +49,27 @@ int main(int argc, char** argv)
         std::vector<std::vector<core::Match>> all;
         matcher->matchMultiple(f1, {f0, core::Frame(), f1}, all, 0.75f);
         if (all.size() != 3 || all[0].size() != (size_t)nm || !all[1].empty()) throw std::runtime_error("matchMultiple disagrees with match");
+        // legacy loop's dynamic filter (src/main.cpp:164-175): no detections = match(); a static class filters nothing;
+        // a person box over the left half drops exactly the matches with an endpoint in it (closed Detection::contains)
+        {
+            auto* bm = static_cast<adapters::b200::B200Matcher*>(matcher.get());
+            std::vector<core::Match> none, stat, dyn;
+            if (bm->matchDynamic(f1, f0, {}, none, 0.75f) != 0 || none.size() != (size_t)nm) throw std::runtime_error("matchDynamic without boxes");
+            core::Detection box{0.f, 0.f, (float)w / 2, (float)h, 0.9f, 9};
+            if (bm->matchDynamic(f1, f0, {box}, stat, 0.75f) != 0 || stat.size() != (size_t)nm) throw std::runtime_error("matchDynamic with a static class");
+            box.class_id = 0;
+            const int filtered = bm->matchDynamic(f1, f0, {box}, dyn, 0.75f);
+            size_t expect = 0;
+            for (size_t i = 1; i < m.size(); ++i) {
+                const core::KeyPoint &a = f1.keypoints[(size_t)m[i].query_idx], &b = f0.keypoints[(size_t)m[i].train_idx];
+                if (!box.contains(a.x, a.y) && !box.contains(b.x, b.y)) {
+                    if (expect >= dyn.size() || dyn[expect].query_idx != m[i].query_idx || dyn[expect].train_idx != m[i].train_idx)
+                        throw std::runtime_error("matchDynamic kept the wrong matches");
+                    ++expect;
+                }
+            }
+            if (expect != dyn.size() || filtered != nm - (int)expect || filtered == 0) throw std::runtime_error("matchDynamic count");
+        }
         // loop detector: 12 keyframes, number 3 is frame 0; the query (frame 1) must find it
         std::unique_ptr<interfaces::ILoopDetector> loop = std::make_unique<adapters::b200::B200LoopDetector>(ctx, 5, 0.2, 20, 50, 50 * 4096);
         for (int i = 0; i < 12; ++i) {
