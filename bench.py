@@ -452,6 +452,10 @@ def run_ours(args):
             ach = 8.0 * pairs_per_step * K / (tot_ms * 1e-3) / 1e9
             ent.update(bound="int_pipe(popc)", achieved=ach, peak=popc_peak, unit="Gpopc32/s", frac=ach / popc_peak,
                        executed_popc_per_pair=4, frac_executed=0.5 * ach / popc_peak)
+            # the same launch seen as HBM traffic (each descriptor row read once: 32 B per query and per train row) --
+            # far below the HBM roofline, which is why the bound above is the POPC pipe
+            kb = 32.0 * float(np.sum(cnt_np[1:].astype(np.float64) + cnt_np[:-1])) * K / (tot_ms * 1e-3) / 1e9
+            ent["hbm_view"] = {"bound": "hbm", "achieved": kb, "peak": hbm_peak, "unit": "GB/s", "frac": kb / hbm_peak}
         if name == "fast_nms":
             # why FAST is not HBM-bound: >= 40 three-input u16x2 min/max per pixel, issued on the ALU pipe
             ops = 40.0 * BYTES_PER_FRAME["fast_nms"] * frames_total / (tot_ms * 1e-3) / 1e9
