@@ -5,6 +5,7 @@ properties, the GPU tests compare the CUDA path with the C restatement.  With gr
 cv::ORB (all other test files)."""
 import numpy as np
 import pytest
+from hypothesis import given, settings, strategies as st, HealthCheck
 
 from conftest import kp_keys
 
@@ -111,6 +112,26 @@ def test_gpu_bucketed_orb_matches_the_restatement(ctx, oracle, w, h, n, seed, ce
     kc, dc = oracle.orb(img, n)
     _same(f.keypoints, f.descriptors, kc, dc)
     ex.close()
+
+
+@pytest.mark.gpu
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(w=st.integers(120, 520), h=st.integers(120, 420), n=st.integers(200, 1500), cell=st.integers(8, 120),
+       seed=st.integers(0, 1000), natural=st.booleans())
+def test_gpu_bucketed_random_sizes_and_cells(ctx, oracle, w, h, n, cell, seed, natural):
+    """Ragged frame sizes, quotas and cell sizes, dense and sparse frames: levels over and under quota, cells cut by
+    the level border, one or many cells per level."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import OrbBatchTracker
+    img = synth.natural_frame(w, h, seed, 1.2) if natural else synth.frame(w, h, seed)
+    tr = OrbBatchTracker(w, h, n, 1, ctx, grid_cell=cell)
+    tr.extract_async(img[None])
+    kps, desc, cnt, _, _ = tr.results()
+    tr.close()
+    ko, do = oracle.orb(img, n, grid_cell=cell)
+    assert cnt[0] == len(ko)
+    if len(ko):
+        _same(kps[0, :cnt[0]], desc[0, :cnt[0]], ko, do)
 
 
 @pytest.mark.gpu
