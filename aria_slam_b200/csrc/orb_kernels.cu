@@ -239,6 +239,14 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*A)[FA_PITCH
 #ifndef ASLAM_FAST_NMS_SKIP
 #define ASLAM_FAST_NMS_SKIP 1
 #endif
+// ASLAM_FAST_NMS_QUEUE: the NMS runs only on the pixel pairs that hold a positive score (a second, in-place
+// compaction of the phase-B queue), on dense warps, instead of on every pair of every row.
+#ifndef ASLAM_FAST_NMS_QUEUE
+#define ASLAM_FAST_NMS_QUEUE 1
+#endif
+#if ASLAM_FAST_NMS_QUEUE && !ASLAM_FAST_COMPACT
+#error "ASLAM_FAST_NMS_QUEUE needs the two-phase score (ASLAM_FAST_COMPACT)"
+#endif
 #if ASLAM_FAST_NMS_SKIP
 #define NMS_ROW_HAS_SCORES(word) __any_sync(0xffffffffu, (word) != 0u)
 #else
@@ -306,6 +314,9 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     const int px_x = sx0 + 2 * p;
     const uint32_t neg_thr = ((uint32_t)(px_x < L.w - 3 ? -g.fast_thr - 256 : -30000) & 0xffffu) |
                              ((uint32_t)(px_x + 1 < L.w - 3 ? -g.fast_thr - 256 : -30000) << 16);     // incl. the bias below
+#if ASLAM_FAST_NMS_QUEUE
+    int n2 = 0;                 // pairs of this warp's rows with a positive score (queued in Q[warp] after phase B)
+#endif
 #if ASLAM_FAST_COMPACT
     // Two phases per warp.  A: a cheap necessary test -- a 9-arc contains one pixel of every opposite ring pair,
     // so a bright (dark) corner needs max (min) of each pair above c + t (below c - t); four of the eight
@@ -317,8 +328,15 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
         const uint32_t kq = (uint32_t)(32767 - g.fast_thr) * 0x00010001u;
         const uint32_t colbits = (px_x < L.w - 3 ? 0x8000u : 0u) | (px_x + 1 < L.w - 3 ? 0x80000000u : 0u);
         int nq = 0;
+#if ASLAM_FAST_NMS_QUEUE
+        // a warp owns FT_SCORE_H / 8 consecutive rows, so its queue -- and with it the emitted order -- is row-major
+        const int r_last = min(r_end, (warp + 1) * (FT_SCORE_H / 8));
+#pragma unroll 1
+        for (int r = warp * (FT_SCORE_H / 8); r < r_last; ++r) {
+#else
 #pragma unroll 1
         for (int r = warp; r < r_end; r += 8) {
+#endif
             const uint32_t c = ring_pair<0, 0>(A, Bc, r, gp);
             const uint32_t p0 = ring_pair<0, 3>(A, Bc, r, gp), p8 = ring_pair<0, -3>(A, Bc, r, gp);
             const uint32_t p4 = ring_pair<3, 0>(A, Bc, r, gp), p12 = ring_pair<-3, 0>(A, Bc, r, gp);
@@ -336,6 +354,9 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             nq += __popc(bal);
         }
         __syncwarp();
+#if ASLAM_FAST_NMS_QUEUE
+        n2 = 0;
+#endif
 #pragma unroll 1
         for (int i0 = 0; i0 < nq; i0 += 32) {
             const int i = i0 + p;
@@ -344,6 +365,14 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             const uint32_t thr = __shfl_sync(0xffffffffu, neg_thr, pp);
             const uint32_t sc = fast_score_pair(A, Bc, rr, g0 / 2 + pp, thr, M);
             if (i < nq) S[rr][pp] = sc;
+#if ASLAM_FAST_NMS_QUEUE
+            // keep the pairs with a positive score, in place: n2 <= i0, so a slot written here was read already
+            const bool nz = i < nq && sc != 0u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+            __syncwarp();
+            if (nz) queue[n2 + __popc(bal & ((1u << p) - 1u))] = (uint16_t)id;
+            n2 += __popc(bal);
+#endif
         }
     }
 #else
@@ -357,6 +386,58 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     // For a column x: C3 = max of the three rows (centre row included), V = max of rows above/below.
     // neighbours(x) = max(V[x], C3[x-1], C3[x+1]); columns x-1 / x+1 of a pair come from the lanes beside it.
     const uint8_t *mrow = b.mask ? b.mask + (size_t)frame * g.pyr_stride + L.off : nullptr;
+#if ASLAM_FAST_NMS_QUEUE
+    // One lane = one queued pair (row rr, pair column pp): the 3x3 block of score words around it comes straight from
+    // S (no shuffles), the arithmetic is the row-wise form's.  Results are parked per warp in the pixel tile's memory
+    // (dead after the barrier above) in queue order = row-major, then copied out behind the warps before.
+    uint32_t *stage = reinterpret_cast<uint32_t *>(&A[0][0]) + warp * (FT_SCORE_H / 8 * 32);
+    static_assert(sizeof(uint32_t) * FT_SCORE_H * 32 <= sizeof(uint16_t) * FT_PIX_H * FA_PITCH, "candidate staging fits the pixel tile");
+    const uint32_t resp_bias = (uint32_t)(g.fast_thr - 1);
+    int local = 0;
+    {
+        const uint16_t *queue = Q[warp];
+#pragma unroll 1
+        for (int i0 = 0; i0 < n2; i0 += 32) {
+            const int i = i0 + p;
+            const int id = queue[min(i, n2 - 1)];
+            const int r = id >> 5, pp = id & 31;
+            uint32_t e = 0;
+            if (i < n2 && r >= 1 && r <= FT_OUT_H && sy0 + r < L.h - g.edge) {
+                const int pl = max(pp - 1, 0), pr = min(pp + 1, FT_SCORE_W / 2 - 1);     // clamped words feed masked lanes only
+                const uint32_t up = S[r - 1][pp], cur = S[r][pp], dn = S[r + 1][pp];
+                const uint32_t V = __vmaxu2(up, dn), C3 = max3(up, cur, dn);
+                const uint32_t Lw = max3(S[r - 1][pl], S[r][pl], S[r + 1][pl]), Rw = max3(S[r - 1][pr], S[r][pr], S[r + 1][pr]);
+                const uint32_t nb = max3(V, __byte_perm(Lw, C3, 0x5432), __byte_perm(C3, Rw, 0x5432));
+                const int x0 = sx0 + 2 * pp, y = sy0 + r;
+                const uint32_t ok = ((pp >= 1 && x0 >= g.edge && x0 < L.w - g.edge) ? 0xffffu : 0u) |
+                                    ((pp <= 30 && x0 + 1 >= g.edge && x0 + 1 < L.w - g.edge) ? 0xffff0000u : 0u);
+                const uint32_t d = __vimax_s16x2_relu(__vsub2(cur, nb), 0u) & ok;
+                if (d) {
+                    const bool second = (d & 0xffffu) == 0;
+                    const int x = x0 + (second ? 1 : 0);
+                    const uint32_t sc = second ? cur >> 16 : cur & 0xffffu;
+                    if (!(mrow && __ldg(mrow + (size_t)y * L.pitch + x) == 0))
+                        e = ((sc + resp_bias) << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, e != 0);
+            if (e) stage[local + __popc(bal & ((1u << p) - 1u))] = e;
+            local += __popc(bal);
+        }
+    }
+    if (p == 0) warp_tot[warp] = local;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = warp_tot[i];
+        if (i < warp) base += t;
+        total += t;
+    }
+    uint32_t *out = b.cand + ((size_t)frame * g.tiles_per_frame + tile) * FT_CAP;
+    for (int i = p; i < local; i += 32) out[base + i] = stage[i];
+    if (tid == 0) b.cand_cnt[(size_t)frame * g.tiles_per_frame + tile] = (uint32_t)total;
+#else
     constexpr int RPW = FT_SCORE_H / 8;
     uint32_t found[RPW];
     int off[RPW];
@@ -403,6 +484,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     for (int k = 0; k < RPW; ++k)
         if (found[k]) out[base + off[k]] = found[k];
     if (tid == 0) b.cand_cnt[(size_t)frame * g.tiles_per_frame + tile] = (uint32_t)total;
+#endif
 }
 
 int launch_fast(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
