@@ -36,6 +36,7 @@ class AslamError(RuntimeError):
 # name -> (restype, argtypes); every symbol declared in include/aslam_b200.h
 _P = C.c_void_p
 SYMBOLS = {
+    "aslam_device_count": (C.c_int, []),
     "aslam_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "aslam_ctx_destroy": (None, [_P]),
     "aslam_ctx_sync": (C.c_int, [_P]),
@@ -71,6 +72,8 @@ SYMBOLS = {
                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "aslam_knn2_raw": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "aslam_match_multi": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P]),
+    "aslam_match_knn2_resident": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_float, _P, C.POINTER(C.c_int)]),
+    "aslam_orb_retain_descriptors": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int32)]),
     "aslam_match_knn2_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_float, _P, _P]),
     "aslam_loopdb_create": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(_P)]),
     "aslam_loopdb_destroy": (None, [_P]),
@@ -87,6 +90,26 @@ SYMBOLS = {
     "aslam_loopdb_query_global_device": (C.c_int, [_P, _P, C.c_int, _P]),
     "aslam_loopdb_query_global_push_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int]),
     "aslam_loopdb_query_global_exchange_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_uint64, _P]),
+    "aslam_loopdb_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), _P, C.c_int]),
+    "aslam_loopdb_capacity_rows": (C.c_int64, [_P]),
+    "aslam_loopdb_query_segmented_device": (C.c_int, [_P, _P, C.c_int, C.c_double, _P]),
+    "aslam_loopdb_match_keyframe": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_double, _P, C.POINTER(C.c_int)]),
+    "aslam_loopdb_shard_handle_bytes": (C.c_size_t, []),
+    "aslam_loopdb_shard_export": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "aslam_loopdb_shard_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "aslam_loopdb_query_global_sharded_device": (C.c_int, [_P, _P, C.c_int, _P]),
+    "aslam_loopdb_shard_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "aslam_loopdb_shard_group_destroy": (None, [_P]),
+    "aslam_loopdb_shard_group_num_shards": (C.c_int, [_P]),
+    "aslam_loopdb_shard_group_add": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
+    "aslam_loopdb_shard_group_clear": (C.c_int, [_P]),
+    "aslam_loopdb_shard_group_num_keyframes": (C.c_int, [_P]),
+    "aslam_loopdb_shard_group_num_rows": (C.c_int64, [_P]),
+    "aslam_loopdb_shard_group_keyframes": (C.c_int, [_P, _P, _P, _P]),
+    "aslam_loopdb_shard_group_query_segmented": (C.c_int, [_P, _P, C.c_int, C.c_double, _P]),
+    "aslam_loopdb_shard_group_query_global": (C.c_int, [_P, _P, C.c_int, _P]),
+    "aslam_loopdb_shard_group_read_result": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "aslam_loopdb_shard_group_match_keyframe": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_double, _P, C.POINTER(C.c_int)]),
     "aslam_loop_exchange_buffer_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "aslam_loopdb_query_global": (C.c_int, [_P, _P, C.c_int, _P]),
     "aslam_loop_merge_top2_device": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),

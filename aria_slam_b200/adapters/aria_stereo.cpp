@@ -78,10 +78,11 @@ bool AriaStereoFrontend::onImage(const interfaces::AriaImage& im)
     const size_t npx = (size_t)width_ * height_;
     if (have_[side]) ++dropped_;                               // its partner never came
     if (have_[other] && half_ts_[other] == im.timestamp_ns) {
-        // pair complete: slot layout [right, left] so that the tracker matches left (query) against right (train)
+        // pair complete: slot layout [left, right] -- the tracker matches a frame's predecessor (query) against the
+        // frame (train), so the odd slot carries left (query) vs right (train)
         uint8_t* slot = images_ + (size_t)staged_ * 2 * npx;
-        uint8_t* dst_new = slot + (side == 0 ? npx : 0);
-        uint8_t* dst_old = slot + (other == 0 ? npx : 0);
+        uint8_t* dst_new = slot + (side == 0 ? 0 : npx);
+        uint8_t* dst_old = slot + (other == 0 ? 0 : npx);
         to_grey(im.data, im.channels, npx, dst_new);
         memcpy(dst_old, half_[other].data(), npx);
         have_[0] = have_[1] = false;
@@ -122,8 +123,8 @@ void AriaStereoFrontend::run()
         StereoResult r;
         r.timestamp_ns = stamps_[(size_t)p];
         r.left.timestamp = r.right.timestamp = (double)r.timestamp_ns * 1e-9;
-        fill(2 * p, r.right);
-        fill(2 * p + 1, r.left);
+        fill(2 * p, r.left);
+        fill(2 * p + 1, r.right);
         const int nm = mcounts_[2 * p + 1];                    // the odd slot is left-vs-right; the even one is a by-product
         r.matches.resize((size_t)nm);
         for (int i = 0; i < nm; ++i) {

@@ -3,7 +3,7 @@
 // device port (include/interfaces/IAriaDevice.hpp:17-61, docs/milestones/H15_META_ARIA.md:300-330):
 //
 //   AriaStereoFrontend  takes AriaImage callbacks, pairs SLAM_LEFT / SLAM_RIGHT frames by timestamp and
-//                       runs pairs through ONE batched call of the C ABI: the batch [right, left] of
+//                       runs pairs through ONE batched call of the C ABI: the batch [left, right] of
 //                       aslam_orb_track_batch_async extracts both images and matches the left frame
 //                       (query) against the right one (train) on the GPU; results come back per pair.
 //   ReplayAriaDevice    an IAriaDevice that replays stored stereo frames (spinOnce = next timestamp).
@@ -47,7 +47,7 @@ private:
     int max_features_, pairs_per_batch_, width_ = 0, height_ = 0, staged_ = 0;
     float ratio_;
     size_t cap_ = 0, processed_ = 0, dropped_ = 0;
-    uint8_t* images_ = nullptr;                 // pinned: [pairs][right, left][h][w]
+    uint8_t* images_ = nullptr;                 // pinned: [pairs][left, right][h][w]
     aslam_keypoint* kps_ = nullptr;             // pinned result staging
     uint8_t* desc_ = nullptr;
     aslam_match* matches_ = nullptr;

@@ -39,6 +39,12 @@ private:
     aslam_ctx* ctx_ = nullptr;
 };
 
+// Descriptor rows resident in HBM (the cv::cuda::GpuMat of CudaMatcher::matchGpu, include/adapters/gpu/CudaMatcher.hpp:22-28).
+struct DeviceDescriptors {
+    const uint8_t* data = nullptr;     // device pointer, 32 bytes per row
+    int rows = 0;
+};
+
 class OrbB200Extractor : public interfaces::IFeatureExtractor {
 public:
     explicit OrbB200Extractor(std::shared_ptr<Context> ctx, int max_features = 1000);
@@ -54,6 +60,12 @@ public:
     // Per-level grid bucketing of the Harris cull (aslam_orb_params::grid_cell; 0 = off = cv::ORB's behaviour).
     // An extension: the reference never buckets.  Takes effect from the next extract call.
     void setGridBucketing(int cell_pixels);
+    // The descriptors of the frame just extracted, kept on the device beyond the next extract (two ring slots owned by
+    // the handle): retain...() after extract()/sync() returns the new frame's rows, previous...() those of the frame
+    // retained before it.  With B200Matcher::matchGpu this is the reference's OrbCudaExtractor + CudaMatcher::matchGpu
+    // chain: no descriptor crosses PCIe between extraction and matching.
+    DeviceDescriptors retainDeviceDescriptors();
+    DeviceDescriptors previousDeviceDescriptors() const { return retained_[1]; }
 private:
     void ensure(int width, int height);
     std::shared_ptr<Context> ctx_;
@@ -63,6 +75,7 @@ private:
     std::vector<aslam_box> boxes_;
     std::vector<aslam_keypoint> kp_buf_;
     std::vector<uint8_t> desc_buf_;
+    DeviceDescriptors retained_[2];            // [0] newest, [1] the one before
 };
 
 class B200Matcher : public interfaces::IMatcher {
@@ -76,6 +89,9 @@ public:
     // lies inside a detection of a dynamic class (core::Detection::contains).  Returns main.cpp's filtered_count.
     int matchDynamic(const core::Frame& query, const core::Frame& train, const std::vector<core::Detection>& detections,
                      std::vector<core::Match>& matches, float ratio_threshold = 0.75f);
+    // CudaMatcher::matchGpu (CudaMatcher.hpp:22-28): both descriptor sets already on the device; appends like match().
+    void matchGpu(const DeviceDescriptors& query_desc, const DeviceDescriptors& train_desc, std::vector<core::Match>& matches,
+                  float ratio_threshold = 0.75f);
 private:
     std::shared_ptr<Context> ctx_;
     std::vector<aslam_match> buf_;
@@ -83,9 +99,15 @@ private:
 
 class B200LoopDetector : public interfaces::ILoopDetector {
 public:
-    // defaults of LoopClosureDetector (include/legacy/LoopClosure.hpp): 30 frames, 0.3 score, 30 matches
+    // defaults of LoopClosureDetector (include/legacy/LoopClosure.hpp): 30 frames, 0.3 score, 30 matches; FIFO of 500
+    // keyframes (LoopClosure.cpp:27-30).  max_features sizes the first allocation (max_keyframes * (max_features + tie
+    // room) rows); the store grows on demand, so no keyframe is ever refused.
     explicit B200LoopDetector(std::shared_ptr<Context> ctx, int min_frames_between = 30, double min_score = 0.3,
-                              int min_matches = 30, int max_keyframes = 500, int64_t capacity_rows = 500 * 2600);
+                              int min_matches = 30, int max_keyframes = 500, int max_features = 2000);
+    // The same detector with its keyframe database sharded over several GPUs of this process
+    // (aslam_loopdb_shard_group: keyframe k on device k % n, counts exchanged, candidates re-matched on the owning GPU).
+    explicit B200LoopDetector(const std::vector<int>& cuda_devices, int min_frames_between = 30, double min_score = 0.3,
+                              int min_matches = 30, int max_keyframes = 500, int max_features = 2000);
     ~B200LoopDetector() override;
     void addKeyFrame(const core::KeyFrame& kf) override;
     std::optional<core::LoopCandidate> detect(const core::KeyFrame& query) override;
@@ -95,13 +117,15 @@ public:
     void setMinMatches(int n) override { min_matches_ = n; }
     // LoopClosure.cpp:72-114: (keyframe index in the store, score), best first, at most 5
     std::vector<std::pair<int, double>> findCandidates(const core::KeyFrame& query);
+    int numKeyFrames() const;
+    int numShards() const;
 private:
-    std::shared_ptr<Context> ctx_;
+    std::shared_ptr<Context> ctx_;             // single-GPU form
     aslam_loopdb* db_ = nullptr;
-    B200Matcher matcher_;
-    std::deque<std::pair<uint64_t, std::vector<uint8_t>>> store_;   // host copy for the candidate re-match
+    aslam_loopdb_group* group_ = nullptr;      // sharded form
     int min_frames_between_, min_matches_, max_keyframes_, loops_ = 0;
     double min_score_;
+    std::vector<aslam_match> buf_;
 };
 
 }  // namespace aria::adapters::b200

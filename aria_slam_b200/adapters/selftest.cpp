@@ -1,7 +1,9 @@
 // Exercises the C++ adapters through the reference's interface types on a GPU box.
 //   adapter_selftest <in.raw> <width> <height> <nfeatures> <out.bin>
 // in.raw holds two frames back to back.  out.bin: for each frame [int32 n][n x KeyPoint 24 B][n x 32 B],
-// then [int32 m][m x Match 12 B] for match(frame1, frame0, 0.75f), then the loop detector's verdict.
+// then [int32 m][m x Match 12 B] for match(frame1, frame0, 0.75f), then the loop detector's verdict
+// [int32 found, match_id, matches] (the same from a detector sharded over two GPUs is compared here when a second
+// device exists).
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -28,9 +30,15 @@ int main(int argc, char** argv)
         if (extractor->getMaxFeatures() != nf) throw std::runtime_error("getMaxFeatures");
         core::Frame f0, f1;
         f0.id = 7; f0.timestamp = 1.5;
+        auto* bex = static_cast<adapters::b200::OrbB200Extractor*>(extractor.get());
         extractor->extract(px.data(), w, h, f0);
+        const adapters::b200::DeviceDescriptors dev0 = bex->retainDeviceDescriptors();
         extractor->extractAsync(px.data() + (size_t)w * h, w, h, f1);
         extractor->sync();
+        const adapters::b200::DeviceDescriptors dev1 = bex->retainDeviceDescriptors();
+        if (dev0.rows != (int)f0.keypoints.size() || dev1.rows != (int)f1.keypoints.size() || dev0.data == dev1.data ||
+            bex->previousDeviceDescriptors().data != dev0.data)
+            throw std::runtime_error("retainDeviceDescriptors");
         if (f0.id != 7 || f0.timestamp != 1.5) throw std::runtime_error("extract touched id/timestamp");
         FILE* out = fopen(argv[5], "wb");
         for (const core::Frame* f : {&f0, &f1}) {
@@ -46,6 +54,19 @@ int main(int argc, char** argv)
         int32_t nm = (int32_t)m.size() - 1;
         put(out, &nm, 4);
         put(out, m.data() + 1, (size_t)nm * sizeof(core::Match));
+        // CudaMatcher::matchGpu: the descriptors both frames left on the device give the same matches, appended
+        {
+            auto* bm = static_cast<adapters::b200::B200Matcher*>(matcher.get());
+            std::vector<core::Match> g;
+            g.push_back({-2, -2, -2.f});
+            bm->matchGpu(dev1, dev0, g, 0.75f);
+            if (g.size() != m.size() || g[0].query_idx != -2) throw std::runtime_error("matchGpu count");
+            for (size_t i = 1; i < g.size(); ++i)
+                if (g[i].query_idx != m[i].query_idx || g[i].train_idx != m[i].train_idx || g[i].distance != m[i].distance)
+                    throw std::runtime_error("matchGpu disagrees with match");
+            bm->matchGpu(adapters::b200::DeviceDescriptors{}, dev0, g, 0.75f);
+            if (g.size() != m.size()) throw std::runtime_error("matchGpu with an empty side");
+        }
         std::vector<std::vector<core::Match>> all;
         matcher->matchMultiple(f1, {f0, core::Frame(), f1}, all, 0.75f);
         if (all.size() != 3 || all[0].size() != (size_t)nm || !all[1].empty()) throw std::runtime_error("matchMultiple disagrees with match");
@@ -70,8 +91,12 @@ int main(int argc, char** argv)
             }
             if (expect != dyn.size() || filtered != nm - (int)expect || filtered == 0) throw std::runtime_error("matchDynamic count");
         }
-        // loop detector: 12 keyframes, number 3 is frame 0; the query (frame 1) must find it
-        std::unique_ptr<interfaces::ILoopDetector> loop = std::make_unique<adapters::b200::B200LoopDetector>(ctx, 5, 0.2, 20, 50, 50 * 4096);
+        // loop detector: 12 keyframes into a FIFO of 10 (keyframes 2..11 stay), number 3 is frame 0; the query (frame 1) must
+        // find it.  max_features 64 makes the first allocation far too small for these keyframes: the store has to grow.
+        std::unique_ptr<interfaces::ILoopDetector> loop = std::make_unique<adapters::b200::B200LoopDetector>(ctx, 5, 0.2, 20, 10, 64);
+        std::unique_ptr<adapters::b200::B200LoopDetector> sharded;
+        if (aslam_device_count() >= 2)
+            sharded = std::make_unique<adapters::b200::B200LoopDetector>(std::vector<int>{0, 1}, 5, 0.2, 20, 10, 64);
         for (int i = 0; i < 12; ++i) {
             core::KeyFrame kf;
             kf.id = (uint64_t)i;
@@ -83,6 +108,7 @@ int main(int argc, char** argv)
                 kf.frame.keypoints.resize(f0.keypoints.size());
             }
             loop->addKeyFrame(kf);
+            if (sharded) sharded->addKeyFrame(kf);
         }
         core::KeyFrame q;
         q.id = 20; q.frame = f1;
@@ -90,6 +116,17 @@ int main(int argc, char** argv)
         int32_t verdict[3] = {hit ? 1 : 0, hit ? (int32_t)hit->match_id : -1, hit ? (int32_t)hit->matches.size() : 0};
         put(out, verdict, sizeof(verdict));
         if (loop->getLoopCount() != (hit ? 1 : 0)) throw std::runtime_error("getLoopCount");
+        if (static_cast<adapters::b200::B200LoopDetector*>(loop.get())->numKeyFrames() != 10) throw std::runtime_error("FIFO cap");
+        if (sharded) {
+            auto hit2 = sharded->detect(q);
+            if (sharded->numShards() != 2 || sharded->numKeyFrames() != 10 || bool(hit2) != bool(hit) ||
+                (hit && (hit2->match_id != hit->match_id || hit2->score != hit->score || hit2->matches.size() != hit->matches.size())))
+                throw std::runtime_error("the detector sharded over two GPUs disagrees with the single-GPU one");
+            for (size_t i = 0; hit && i < hit->matches.size(); ++i)
+                if (hit2->matches[i].query_idx != hit->matches[i].query_idx || hit2->matches[i].train_idx != hit->matches[i].train_idx)
+                    throw std::runtime_error("sharded re-match differs");
+            printf("sharded loop detector (2 GPUs) agrees\n");
+        }
         fclose(out);
         printf("selftest ok: %zu + %zu keypoints, %d matches, loop %d -> kf %d\n", f0.keypoints.size(), f1.keypoints.size(), nm, verdict[0], verdict[1]);
     } catch (const std::exception& e) {

@@ -101,7 +101,22 @@ core::Pose SlamPipeline::processFrame(const uint8_t* image_data, int width, int 
 
     // previous frame is the query, the new one the train set (src/main.cpp:158-163)
     std::vector<core::Match> matches;
-    if (prev_frame_ && !prev_frame_->descriptors.empty() && !frame.descriptors.empty())
+    // With the B200 ports and nothing dropped on the host, the two descriptor sets are matched where they already are
+    // (CudaMatcher::matchGpu, include/adapters/gpu/CudaMatcher.hpp:22-28): the extractor keeps the last two frames'
+    // rows on the device, so no descriptor crosses PCIe between extraction and matching.
+    auto* b200_extractor = dynamic_cast<adapters::b200::OrbB200Extractor*>(extractor_.get());
+    auto* b200_matcher = dynamic_cast<adapters::b200::B200Matcher*>(matcher_.get());
+    const bool dropped_on_host = config_.filter_dynamic_objects && !detections.empty();
+    bool matched_on_device = false;
+    if (b200_extractor && b200_matcher) {
+        const adapters::b200::DeviceDescriptors cur = b200_extractor->retainDeviceDescriptors();
+        const adapters::b200::DeviceDescriptors prev = b200_extractor->previousDeviceDescriptors();
+        if (!dropped_on_host && prev_frame_ && prev.rows == (int)prev_frame_->keypoints.size() && cur.rows == (int)frame.keypoints.size()) {
+            b200_matcher->matchGpu(prev, cur, matches, 0.75f);
+            matched_on_device = true;
+        }
+    }
+    if (!matched_on_device && prev_frame_ && !prev_frame_->descriptors.empty() && !frame.descriptors.empty())
         matcher_->match(*prev_frame_, frame, matches, 0.75f);
 
     const core::Pose before = current_pose_;
@@ -163,7 +178,7 @@ std::unique_ptr<pipeline::SlamPipeline> PipelineFactory::create(const FactoryCon
         auto ctx = std::make_shared<Context>(config.cuda_device);
         return std::make_unique<pipeline::SlamPipeline>(
             std::make_unique<OrbB200Extractor>(ctx, config.max_features), std::make_unique<B200Matcher>(ctx),
-            std::make_unique<B200LoopDetector>(ctx), std::make_unique<NullObjectDetector>(),
+            std::make_unique<B200LoopDetector>(ctx, 30, 0.3, 30, 500, config.max_features), std::make_unique<NullObjectDetector>(),
             std::make_unique<PassThroughFusion>(), std::make_unique<NullMapper>(), config.pipeline_config);
     }
     case ExecutionMode::MOCK:

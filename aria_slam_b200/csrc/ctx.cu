@@ -92,7 +92,14 @@ int aslam_prof_read(aslam_ctx *ctx, int kind, double *total_ms, int64_t *launche
 }
 
 const char *aslam_last_error(void) { return aslam::g_err; }
-const char *aslam_version(void) { return "aslam_b200 0.1 (sm_100a)"; }
+const char *aslam_version(void) { return "aslam_b200 0.2 (sm_100a)"; }
+
+int aslam_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 uint64_t aslam_kernel_launches(void) { return aslam::g_launches.load(); }
 
 int aslam_ctx_create(int device, void *stream, aslam_ctx **out)

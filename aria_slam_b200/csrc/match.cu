@@ -78,12 +78,50 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t t0)
     return k16 == 0xffffu ? KEY_EMPTY : ((k16 >> 7) << KEY_IDX_BITS) + t0 + (k16 & 127u);
 }
 
+// ---- peer-memory primitives of the fused exchange
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// 32-bit shard key (distance << 23 | local row) -> 64-bit global key (distance << 40 | global row)
+__device__ __forceinline__ unsigned long long global_key(uint32_t k, const RowMap &m)
+{
+    if (k == KEY_EMPTY) return ~0ull;
+    const int local = (int)(k & (KNN_MAX_ROWS - 1));
+    long long row;
+    if (m.nseg == 0) {
+        row = m.row_base + local;
+    } else {
+        int lo = 0, hi = m.nseg - 1;              // last keyframe whose first local row is <= local
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (m.lstart[mid] <= local) lo = mid; else hi = mid - 1;
+        }
+        row = m.gbase[lo] + (local - m.lstart[lo]);
+    }
+    return ((unsigned long long)(k >> KEY_IDX_BITS) << 40) | (unsigned long long)row;
+}
+
 #ifndef ASLAM_KNN_MINB
 #define ASLAM_KNN_MINB 1
 #endif
-template <bool POPC4>
+template <bool POPC4, bool FUSED>
 __global__ void __launch_bounds__(KNN_THREADS, ASLAM_KNN_MINB)
-knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__ partial, int q_stride, const KnnMul M, int merge_div)
+knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *partial, int q_stride, const KnnMul M, int merge_div,
+                       const ExchangeArgs X)
 {
     static_assert(KNN_TILE == KNN_THREADS && KNN_TILE == 128 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
     __shared__ uint4 tile[2][KNN_TILE * 3];
@@ -92,7 +130,7 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__
     const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
     const int nt = P.nt_dev ? min(*P.nt_dev, P.nt) : P.nt;
     const int qbase = blockIdx.x * KNN_QBLOCK;
-    if (qbase >= nq) return;
+    if (!FUSED && qbase >= nq) return;
     const int t_lo = P.t_lo, t_hi = min(P.t_hi, nt);
     const int tid = threadIdx.x;
 
@@ -166,10 +204,10 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__
     for (int j = 0; j < KNN_RQ; ++j) {
         const int qi = qbase + j * KNN_THREADS + tid;
         if (qi >= nq) continue;
-        if (merge_div <= 1) {
+        if (!FUSED && merge_div <= 1) {
             partial[(size_t)blockIdx.y * q_stride + qi] = make_uint2(b1[j], b2[j]);
         } else {
-            unsigned int *slot = reinterpret_cast<unsigned int *>(partial + (size_t)(blockIdx.y / merge_div) * q_stride + qi);
+            unsigned int *slot = reinterpret_cast<unsigned int *>(partial + (size_t)(FUSED ? 0 : blockIdx.y / merge_div) * q_stride + qi);
             if (b1[j] != KEY_EMPTY) {
                 const uint32_t old = atomicMin(slot, b1[j]);
                 const uint32_t lost = max(old, b1[j]);
@@ -177,6 +215,68 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *__restrict__
                 if (b2[j] != KEY_EMPTY) atomicMin(slot + 1, b2[j]);
             }
         }
+    }
+    if (!FUSED) return;
+
+    // ---- fused exchange (one shard of a sharded database; every problem of the launch is a row range of the same pair).
+    // The last CTA to arrive for this block of queries owns the block from here on.
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(X.arrive + blockIdx.x, 1u);
+        s_last = prev == gridDim.y - 1;
+        if (s_last) X.arrive[blockIdx.x] = 0;               // ready for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int half = (int)(X.round & 1ull);
+    const int nqb = gridDim.x;
+    const size_t flags_off = (size_t)2 * X.nparts * X.nq * 2;                 // per peer buffer, after the data
+    // phase 1: this shard's top-2 of the block's queries, as global keys, into every peer's gather buffer (NVLink stores)
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        const int qi = qbase + j * KNN_THREADS + tid;
+        if (qi >= nq) continue;
+        const uint2 p = __ldcg(partial + qi);
+        partial[qi] = make_uint2(KEY_EMPTY, KEY_EMPTY);     // the merged slot is ready for the next scan
+        ulonglong2 v;
+        v.x = global_key(p.x, X.map);
+        v.y = global_key(p.y, X.map);
+        const size_t at = (((size_t)half * X.nparts + X.my_part) * X.nq + qi) * 2;
+        for (int pr = 0; pr < X.nparts; ++pr) *reinterpret_cast<ulonglong2 *>(X.peer_bufs[pr] + at) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // publish: this shard's flag of this block and round, on every peer
+    for (int pr = tid; pr < X.nparts; pr += KNN_THREADS)
+        st_release_sys(X.peer_bufs[pr] + flags_off + ((size_t)half * X.nparts + X.my_part) * nqb + blockIdx.x, X.round);
+    const unsigned long long t_push = global_timer_ns();
+    // phase 2: wait for every shard's flag of this block, then merge the block's queries from the LOCAL buffer
+    unsigned long long *mine = X.peer_bufs[X.my_part];
+    for (int pr = tid; pr < X.nparts; pr += KNN_THREADS) {
+        const unsigned long long *f = mine + flags_off + ((size_t)half * X.nparts + pr) * nqb + blockIdx.x;
+        while (ld_acquire_sys(f) < X.round) {
+            __nanosleep(32);
+            if (global_timer_ns() - t_push > 4000000000ull) { atomicOr(X.status, 1u); break; }      // a peer never came: 4 s
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && X.stamps) { X.stamps[2 * blockIdx.x] = t_push; X.stamps[2 * blockIdx.x + 1] = global_timer_ns(); }
+#pragma unroll
+    for (int j = 0; j < KNN_RQ; ++j) {
+        const int qi = qbase + j * KNN_THREADS + tid;
+        if (qi >= nq) continue;
+        unsigned long long k1 = ~0ull, k2 = ~0ull;
+        for (int pr = 0; pr < X.nparts; ++pr) {
+            const ulonglong2 ab = __ldcg(reinterpret_cast<const ulonglong2 *>(mine + (((size_t)half * X.nparts + pr) * X.nq + qi) * 2));
+            const unsigned long long n2 = min(max(k1, ab.x), min(k2, ab.y));
+            k1 = min(k1, ab.x);
+            k2 = n2;
+        }
+        X.out[2 * (size_t)qi] = k1;
+        X.out[2 * (size_t)qi + 1] = k2;
     }
 }
 
@@ -294,25 +394,22 @@ knn2_finish_counts_kernel(const KnnProblem *__restrict__ probs, const uint2 *__r
 
 __global__ void __launch_bounds__(FIN_THREADS)
 knn2_finish_global_kernel(uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
-                          long long row_base, unsigned long long *__restrict__ top2, int rearm)
+                          const RowMap map, unsigned long long *__restrict__ top2, int rearm)
 {
     const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
     if (q >= nq) return;
     uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
     for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
     if (rearm && nslots) partial[q] = make_uint2(KEY_EMPTY, KEY_EMPTY);       // the merged slot is ready for the next scan
-    const unsigned long long e = ~0ull;
-    top2[2 * (size_t)q] = k1 == KEY_EMPTY ? e
-        : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
-    top2[2 * (size_t)q + 1] = k2 == KEY_EMPTY ? e
-        : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
+    top2[2 * (size_t)q] = global_key(k1, map);
+    top2[2 * (size_t)q + 1] = global_key(k2, map);
 }
 
 // Fused finish + all-gather: the merged keys of this shard go directly into every peer's gather buffer
 // with plain 16-byte stores to peer-mapped addresses (NVLink / NVSwitch); one thread = one query.
 __global__ void __launch_bounds__(FIN_THREADS)
 knn2_finish_global_push_kernel(uint2 *__restrict__ partial, int nslots, int nq, int q_stride,
-                               long long row_base, unsigned long long *const *__restrict__ peer_bufs,
+                               const RowMap map, unsigned long long *const *__restrict__ peer_bufs,
                                int nparts, int my_part, int rearm)
 {
     const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
@@ -320,77 +417,12 @@ knn2_finish_global_push_kernel(uint2 *__restrict__ partial, int nslots, int nq, 
     uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
     for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
     if (rearm && nslots) partial[q] = make_uint2(KEY_EMPTY, KEY_EMPTY);       // the merged slot is ready for the next scan
-    const unsigned long long e = ~0ull;
     ulonglong2 v;
-    v.x = k1 == KEY_EMPTY ? e : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
-    v.y = k2 == KEY_EMPTY ? e : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
+    v.x = global_key(k1, map);
+    v.y = global_key(k2, map);
     const size_t at = ((size_t)my_part * nq + q) * 2;
     for (int p = 0; p < nparts; ++p)
         *reinterpret_cast<ulonglong2 *>(peer_bufs[p] + at) = v;
-}
-
-// ---- one-kernel exchange: scan finish -> P2P stores -> release flags -> acquire peers' flags -> merge
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(FIN_THREADS)
-knn2_finish_exchange_kernel(uint2 *__restrict__ partial, int nslots, int nq, int q_stride, long long row_base,
-                            unsigned long long *const *__restrict__ peer_bufs, int nparts, int my_part,
-                            unsigned long long round, unsigned int *arrival, unsigned long long *__restrict__ out, int rearm)
-{
-    const int q = blockIdx.x * FIN_THREADS + threadIdx.x;
-    const int half = (int)(round & 1ull);
-    const size_t data_words = (size_t)2 * nparts * nq * 2;                    // per peer buffer, before the flags
-    const size_t slot = ((size_t)half * nparts + my_part) * nq;
-    // phase 1: this shard's top-2 per query into every peer's gather buffer (NVLink stores)
-    if (q < nq) {
-        uint32_t k1 = KEY_EMPTY, k2 = KEY_EMPTY;
-        for (int s = 0; s < nslots; ++s) merge_pair(k1, k2, partial[(size_t)s * q_stride + q]);
-        if (rearm && nslots) partial[q] = make_uint2(KEY_EMPTY, KEY_EMPTY);       // the merged slot is ready for the next scan
-        const unsigned long long e = ~0ull;
-        ulonglong2 v;
-        v.x = k1 == KEY_EMPTY ? e : ((unsigned long long)(k1 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k1 & (KNN_MAX_ROWS - 1)));
-        v.y = k2 == KEY_EMPTY ? e : ((unsigned long long)(k2 >> KEY_IDX_BITS) << 40) | (unsigned long long)(row_base + (long long)(k2 & (KNN_MAX_ROWS - 1)));
-        for (int p = 0; p < nparts; ++p)
-            *reinterpret_cast<ulonglong2 *>(peer_bufs[p] + (slot + q) * 2) = v;
-    }
-    // publish: the last CTA to arrive raises this shard's flag on every peer
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(arrival, 1u);
-        if (prev == gridDim.x - 1) {
-            *arrival = 0;                         // ready for the next launch (stream-ordered)
-            __threadfence_system();
-            for (int p = 0; p < nparts; ++p)
-                st_release_sys(peer_bufs[p] + data_words + (size_t)half * nparts + my_part, round);
-        }
-    }
-    // phase 2: wait for every shard of this round, then merge this CTA's queries from the LOCAL buffer
-    unsigned long long *mine = peer_bufs[my_part];
-    if (threadIdx.x < nparts) {
-        const unsigned long long *f = mine + data_words + (size_t)half * nparts + threadIdx.x;
-        while (ld_acquire_sys(f) < round) __nanosleep(64);
-    }
-    __syncthreads();
-    if (q >= nq) return;
-    unsigned long long k1 = ~0ull, k2 = ~0ull;
-    for (int p = 0; p < nparts; ++p) {
-        const ulonglong2 ab = __ldcg(reinterpret_cast<const ulonglong2 *>(mine + (((size_t)half * nparts + p) * nq + q) * 2));
-        const unsigned long long n2 = min(max(k1, ab.x), min(k2, ab.y));
-        k1 = min(k1, ab.x);
-        k2 = n2;
-    }
-    out[2 * (size_t)q] = k1;
-    out[2 * (size_t)q + 1] = k2;
 }
 
 // Merge of all-gathered shard results: parts[nparts][nq][2] packed 64-bit keys.
@@ -447,8 +479,30 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
         ASLAM_CUDA(cudaMemsetAsync(d_partial, 0xff, sizeof(uint2) * (size_t)(nprobs / merge_div) * q_stride, ctx->stream));
     const KnnMul M{2u, 4u, 65536u, 128u};
     ProfScope ps(ctx, PK_KNN_PARTIAL);
-    if (csa == 7) knn2_partial_v2_kernel<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div);
-    else knn2_partial_v2_kernel<true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div);
+    if (csa == 7) knn2_partial_v2_kernel<false, false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div, ExchangeArgs());
+    else knn2_partial_v2_kernel<true, false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div, ExchangeArgs());
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+
+int launch_knn2_scan_exchange(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int nq, uint2 *d_partial,
+                              int q_stride, const ExchangeArgs &X)
+{
+    if (nprobs <= 0 || nq <= 0) return fail(ASLAM_E_INVALID, "fused exchange needs at least one row range and one query");
+    const int nqb = (nq + KNN_QBLOCK - 1) / KNN_QBLOCK;
+    // One CTA per query block ends up waiting for the peers: they must never fill the GPU while CTAs of other
+    // blocks have not started (those would then never push, and the peers would wait for ever).
+    if (nqb > KNN_FUSED_MAX_QBLOCKS)
+        return fail(ASLAM_E_INVALID, "fused exchange takes at most %d queries per call (got %d); split the batch",
+                    KNN_FUSED_MAX_QBLOCKS * KNN_QBLOCK, nq);
+    if (X.nparts < 1 || X.nparts > 64 || X.my_part < 0 || X.my_part >= X.nparts || X.nq != nq || X.round < 1)
+        return fail(ASLAM_E_INVALID, "bad exchange arguments");
+    dim3 grid(nqb, nprobs);
+    static const int csa = [] { const char *e = getenv("ASLAM_KNN_CSA"); return e ? atoi(e) : ASLAM_KNN_CSA; }();
+    const KnnMul M{2u, 4u, 65536u, 128u};
+    ProfScope ps(ctx, PK_KNN_PARTIAL);
+    if (csa == 7) knn2_partial_v2_kernel<false, true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, nprobs, X);
+    else knn2_partial_v2_kernel<true, true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, nprobs, X);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
@@ -477,38 +531,24 @@ int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const u
 }
 
 int launch_knn2_finish_global(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
-                              int q_stride, int64_t row_base, uint64_t *d_top2, bool rearm)
+                              int q_stride, const RowMap &map, uint64_t *d_top2, bool rearm)
 {
     if (nq <= 0) return ASLAM_OK;
     ProfScope ps(ctx, PK_KNN_FINISH);
     knn2_finish_global_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
-        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *)d_top2, rearm ? 1 : 0);
+        d_partial, nslots, nq, q_stride, map, (unsigned long long *)d_top2, rearm ? 1 : 0);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
 
 int launch_knn2_finish_global_push(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
-                                   int q_stride, int64_t row_base, uint64_t *const *d_peer_bufs,
+                                   int q_stride, const RowMap &map, uint64_t *const *d_peer_bufs,
                                    int nparts, int my_part, bool rearm)
 {
     if (nq <= 0) return ASLAM_OK;
     ProfScope ps(ctx, PK_KNN_FINISH);
     knn2_finish_global_push_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
-        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part, rearm ? 1 : 0);
-    ASLAM_LAUNCH_CHECK();
-    return ASLAM_OK;
-}
-
-int launch_knn2_finish_exchange(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq, int q_stride,
-                                int64_t row_base, uint64_t *const *d_peer_bufs, int nparts, int my_part,
-                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out, bool rearm)
-{
-    if (nq <= 0) return ASLAM_OK;
-    if (nparts > FIN_THREADS) return fail(ASLAM_E_INVALID, "at most %d shards", FIN_THREADS);
-    ProfScope ps(ctx, PK_MERGE);
-    knn2_finish_exchange_kernel<<<(nq + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(
-        d_partial, nslots, nq, q_stride, (long long)row_base, (unsigned long long *const *)d_peer_bufs, nparts, my_part,
-        (unsigned long long)round, d_arrival, (unsigned long long *)d_out, rearm ? 1 : 0);
+        d_partial, nslots, nq, q_stride, map, (unsigned long long *const *)d_peer_bufs, nparts, my_part, rearm ? 1 : 0);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
@@ -529,7 +569,7 @@ int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets)
     const long long units = (long long)((nq + KNN_QBLOCK - 1) / KNN_QBLOCK) * nsets;      // CTAs per range
     static const int ctas_per_sm = [] {                // resident scan CTAs per SM, as the compiler's register count allows
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, knn2_partial_v2_kernel<true>, KNN_THREADS, 0) != cudaSuccess || n < 1) n = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, knn2_partial_v2_kernel<true, false>, KNN_THREADS, 0) != cudaSuccess || n < 1) n = 4;
         return n;
     }();
     const double slots = (double)ctas_per_sm * ctx->sm_count;
@@ -631,6 +671,13 @@ static int run_single(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t
     return ASLAM_OK;
 }
 
+// Device-resident rows on both sides, results to host buffers (the loop database's candidate re-match).
+int knn2_resident_to_host(aslam_ctx *ctx, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, double ratio, int as_double,
+                          aslam_match *out, int *nout)
+{
+    return run_single(ctx, d_q, nq, d_t, nt, true, make_ratio(ratio, as_double), out, nout, nullptr, nullptr, nullptr, nullptr);
+}
+
 extern "C" int aslam_match_knn2(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt,
                                 float ratio, aslam_match *out, int *nout)
 {
@@ -689,6 +736,17 @@ extern "C" int aslam_match_knn2_device(aslam_ctx *ctx, const uint8_t *d_q, int n
     return run_single(ctx, d_q, nq, d_t, nt, true, make_ratio((double)ratio, 0), nullptr, nullptr, nullptr, nullptr, d_out, d_nout);
 }
 
+extern "C" int aslam_match_knn2_resident(aslam_ctx *ctx, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
+                                         float ratio, aslam_match *out, int *nout)
+{
+    ASLAM_REQUIRE(ctx && nout, "NULL argument");
+    ASLAM_REQUIRE(nq >= 0 && nt >= 0, "negative row count");
+    *nout = 0;
+    if (nq == 0 || nt < 2) return ASLAM_OK;
+    ASLAM_REQUIRE(d_q && d_t && out, "NULL descriptor or output pointer");
+    return run_single(ctx, d_q, nq, d_t, nt, true, make_ratio((double)ratio, 0), out, nout, nullptr, nullptr, nullptr, nullptr);
+}
+
 extern "C" int aslam_match_multi(aslam_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t,
                                  const int32_t *t_start, int nsets, float ratio,
                                  aslam_match *out, int32_t *nout)
@@ -739,7 +797,9 @@ extern "C" int aslam_match_multi(aslam_ctx *ctx, const uint8_t *q, int nq, const
 
 extern "C" size_t aslam_loop_exchange_buffer_bytes(int nparts, int nq)
 {
-    return sizeof(uint64_t) * ((size_t)2 * nparts * nq * 2 + (size_t)2 * nparts);
+    if (nparts < 1 || nq < 0) return 0;
+    const size_t nqb = ((size_t)nq + KNN_QBLOCK - 1) / KNN_QBLOCK;
+    return sizeof(uint64_t) * ((size_t)2 * nparts * nq * 2 + (size_t)2 * nparts * nqb);
 }
 
 extern "C" int aslam_loop_merge_top2_device(aslam_ctx *ctx, const uint64_t *d_parts, int nparts, int nq, uint64_t *d_out)

@@ -42,6 +42,17 @@ struct DynFilter {
     int32_t *nfiltered = nullptr;
 };
 
+// Local row of a database shard -> global row.  nseg == 0: one contiguous range (row_base + local row).  Otherwise the
+// shard's keyframes are scattered over the global row space (round-robin placement of the single-process shard
+// group): keyframe i holds local rows [lstart[i], lstart[i+1]) = global rows gbase[i] + 0, 1, ...; local and global
+// order agree inside a shard, so ties still resolve to the lowest global row.
+struct RowMap {
+    long long row_base = 0;
+    const long long *gbase = nullptr;
+    const int *lstart = nullptr;      // nseg + 1 entries
+    int nseg = 0;
+};
+
 // Number of row ranges to cut a train set into so the grid covers the GPU a few times.
 int choose_splits(const aslam_ctx *ctx, int nq, long long nt, int nsets);
 // d_probs[0..splits) = the pair (q, t) cut into equal row ranges (device-side table build).
@@ -72,17 +83,34 @@ int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const u
 // + slot_row_offset), where slot rows are relative to the problem's t base and row_base is
 // added on top.
 int launch_knn2_finish_global(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
-                              int q_stride, int64_t row_base, uint64_t *d_top2, bool rearm = false);
+                              int q_stride, const RowMap &map, uint64_t *d_top2, bool rearm = false);
 
 // As launch_knn2_finish_global, with the result stored into slot `my_part` of every peer's
 // [nparts][nq][2] buffer (peer-mapped pointers in device memory): the all-gather is the epilogue.
 int launch_knn2_finish_global_push(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq,
-                                   int q_stride, int64_t row_base, uint64_t *const *d_peer_bufs,
+                                   int q_stride, const RowMap &map, uint64_t *const *d_peer_bufs,
                                    int nparts, int my_part, bool rearm = false);
 
-// Fused finish + push + flag exchange + merge (see aslam_loopdb_query_global_exchange_device).
-int launch_knn2_finish_exchange(aslam_ctx *ctx, uint2 *d_partial, int nslots, int nq, int q_stride,
-                                int64_t row_base, uint64_t *const *d_peer_bufs, int nparts, int my_part,
-                                uint64_t round, unsigned int *d_arrival, uint64_t *d_out, bool rearm = false);
+// The exchange step of the sharded flat query, run as the tail of the scan kernel itself
+// (aslam_loopdb_query_global_exchange_device).  Peer buffer layout, identical on all ranks:
+//     uint64 data[2][nparts][nq][2];  uint64 flags[2][nparts][qblocks];     qblocks = ceil(nq / KNN_QBLOCK)
+struct ExchangeArgs {
+    unsigned long long *const *peer_bufs = nullptr;   // device array of nparts peer-mapped buffer addresses
+    int nparts = 0, my_part = 0, nq = 0;
+    unsigned long long round = 0;
+    unsigned int *arrive = nullptr;        // [qblocks] CTA arrival counters, zero between launches
+    unsigned long long *out = nullptr;     // [nq][2] merged keys
+    unsigned long long *stamps = nullptr;  // [qblocks][2] %globaltimer when the block was pushed / when all peers' flags were seen
+    unsigned int *status = nullptr;        // bit 0: a wait for a peer's flag timed out (the result is then invalid)
+    RowMap map;
+};
+constexpr int KNN_FUSED_MAX_QBLOCKS = 64;  // waiting CTAs (one per query block) must stay far below the resident CTA slots
+
+// Shard scan + exchange in ONE launch: every CTA merges its row range into the per-query slot (atomic minima); the
+// last CTA to arrive for a block of KNN_QBLOCK queries turns the merged slots into global keys, stores them into every
+// peer's buffer over NVLink, raises this shard's flag for that block on every peer, waits for the peers' flags of the
+// same block and round, merges and writes X.out.  The slots must hold KEY_EMPTY on entry and are left so.
+int launch_knn2_scan_exchange(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int nq, uint2 *d_partial,
+                              int q_stride, const ExchangeArgs &X);
 
 }  // namespace aslam

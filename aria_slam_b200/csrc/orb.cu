@@ -38,6 +38,10 @@ struct aslam_orb {
     bool pending_track = false;
     // pinned result staging
     int32_t *h_counts = nullptr;   // [B+1] counts, [B+1] overflow, [B] match counts
+    // aslam_orb_retain_descriptors: two ring slots of kp_cap rows, the first frame's count at the last sync
+    uint8_t *d_retained[2] = {nullptr, nullptr};
+    int retain_next = 0;
+    int last_count = -1;           // -1: nothing synced yet (or already retained)
 };
 
 static void orb_free_buffers(aslam_orb *o)
@@ -48,6 +52,8 @@ static void orb_free_buffers(aslam_orb *o)
     cudaFree(o->b.counts); cudaFree(o->b.overflow); cudaFree(o->d_tabs);
     cudaFree(o->d_matches); cudaFree(o->d_match_counts); cudaFree(o->d_probs); cudaFree(o->d_partial);
     cudaFree(o->d_tmp_kps); cudaFree(o->d_tmp_desc);
+    cudaFree(o->d_retained[0]); cudaFree(o->d_retained[1]);
+    o->d_retained[0] = o->d_retained[1] = nullptr; o->last_count = -1;
     if (o->h_counts) cudaFreeHost(o->h_counts);
     o->b = OrbBuffers();
     o->d_tabs = nullptr; o->d_matches = nullptr; o->d_match_counts = nullptr; o->d_probs = nullptr;
@@ -60,10 +66,12 @@ __global__ void fill_track_problems_kernel(KnnProblem *probs, const uint8_t *des
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * splits) return;
     const int f = i / splits, s = i - f * splits;
+    // src/main.cpp:158-161, src/euroc_eval.cpp:167-169: knnMatch(prev_frame, current_frame) -- query = the
+    // predecessor, train = the new frame, so query_idx indexes the previous frame's keypoints.
     KnnProblem P;
-    P.q = desc + (size_t)(f + 1) * kp_cap * 32;      // frame f of the batch lives in slot f+1
-    P.t = desc + (size_t)f * kp_cap * 32;            // its predecessor (slot 0 = carry)
-    P.nq_dev = counts + f + 1; P.nt_dev = counts + f;
+    P.q = desc + (size_t)f * kp_cap * 32;            // predecessor of frame f (slot 0 = carry of the last call)
+    P.t = desc + (size_t)(f + 1) * kp_cap * 32;      // frame f of the batch lives in slot f+1
+    P.nq_dev = counts + f; P.nt_dev = counts + f + 1;
     P.nq = kp_cap; P.nt = kp_cap;
     P.t_lo = min(s * rows_per, kp_cap);
     P.t_hi = min((s + 1) * rows_per, kp_cap);
@@ -208,13 +216,21 @@ int aslam_orb_set_max_features(aslam_orb *o, int nfeatures)
     ASLAM_CUDA(cudaStreamSynchronize(o->ctx->stream));
     // OrbCudaExtractor.cpp:212-216 re-creates the detector with only nfeatures set: defaults elsewhere.
     // blur_mode and grid_cell are this library's own knobs, not cv::ORB::create arguments: they stay.
-    const int blur_mode = o->prm.blur_mode, grid_cell = o->prm.grid_cell;
+    const aslam_orb_params before = o->prm;
     aslam_orb_default_params(&o->prm);
     o->prm.nfeatures = nfeatures;
-    o->prm.blur_mode = blur_mode;
-    o->prm.grid_cell = grid_cell;
+    o->prm.blur_mode = before.blur_mode;
+    o->prm.grid_cell = before.grid_cell;
     orb_free_buffers(o);
-    return orb_plan(o);
+    const int rc = orb_plan(o);
+    if (rc == ASLAM_OK) return rc;
+    // the new plan could not be allocated: go back to the previous one; if even that fails the handle refuses all work
+    char msg[512];
+    snprintf(msg, sizeof(msg), "%s", aslam_last_error());
+    orb_free_buffers(o);
+    o->prm = before;
+    if (orb_plan(o) != ASLAM_OK) { orb_free_buffers(o); o->max_batch = 0; }
+    return fail(rc, "%s", msg);
 }
 
 int aslam_orb_get_max_features(const aslam_orb *o) { return o ? o->prm.nfeatures : 0; }
@@ -280,6 +296,8 @@ static int orb_prepare_mask(aslam_orb *o)
     return ASLAM_OK;
 }
 
+static int orb_track_enqueue(aslam_orb *o, int n, float ratio);
+
 static int orb_extract_common(aslam_orb *o, const uint8_t *images, int n, size_t frame_stride, int row_stride,
                               const uint8_t *masks, cudaMemcpyKind kind)
 {
@@ -312,15 +330,18 @@ int aslam_orb_extract_async(aslam_orb *o, const uint8_t *image, int width, int h
     int rc = orb_extract_common(o, image, 1, 0, row_stride, mask, cudaMemcpyHostToDevice);
     if (rc) return rc;
     if (nboxes > 0) {
-        aslam_ctx *ctx = o->ctx;
-        if (nboxes > o->boxes_cap) {
-            if (o->d_boxes) ASLAM_CUDA(cudaFree(o->d_boxes));
-            o->d_boxes = nullptr;
-            ASLAM_CUDA(cudaMalloc(&o->d_boxes, sizeof(aslam_box) * (size_t)(nboxes + 64)));
-            o->boxes_cap = nboxes + 64;
-        }
-        ASLAM_CUDA(cudaMemcpyAsync(o->d_boxes, boxes, sizeof(aslam_box) * (size_t)nboxes, cudaMemcpyHostToDevice, ctx->stream));
-        rc = launch_box_filter(ctx, o->g, o->b, 1, o->d_boxes, nboxes, o->d_tmp_kps, o->d_tmp_desc);
+        rc = [&]() -> int {
+            aslam_ctx *ctx = o->ctx;
+            if (nboxes > o->boxes_cap) {
+                if (o->d_boxes) ASLAM_CUDA(cudaFree(o->d_boxes));
+                o->d_boxes = nullptr; o->boxes_cap = 0;
+                ASLAM_CUDA(cudaMalloc(&o->d_boxes, sizeof(aslam_box) * (size_t)(nboxes + 64)));
+                o->boxes_cap = nboxes + 64;
+            }
+            ASLAM_CUDA(cudaMemcpyAsync(o->d_boxes, boxes, sizeof(aslam_box) * (size_t)nboxes, cudaMemcpyHostToDevice, ctx->stream));
+            return launch_box_filter(ctx, o->g, o->b, 1, o->d_boxes, nboxes, o->d_tmp_kps, o->d_tmp_desc);
+        }();
+        if (rc) o->pending = 0;         // the call failed as a whole: nothing is pending
     }
     return rc;
 }
@@ -353,8 +374,12 @@ static int orb_collect(aslam_orb *o, aslam_keypoint *kps, uint8_t *desc, int32_t
     ASLAM_REQUIRE(o, "orb is NULL");
     if (!o->pending) return fail(ASLAM_E_STATE, "sync without a pending extract");
     aslam_ctx *ctx = o->ctx;
-    ASLAM_CUDA(cudaSetDevice(ctx->device));
     const int n = o->pending;
+    // Whatever happens below, the extract is no longer pending: a CUDA error here must not leave the handle refusing
+    // every later extract with "already pending" (the failed results are lost, the handle stays usable).
+    o->pending = 0;
+    o->last_count = -1;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
     const size_t cap = (size_t)o->g.kp_cap;
     const size_t B = (size_t)o->max_batch;
     int32_t *h_cnt = o->h_counts, *h_ovf = o->h_counts + (B + 1), *h_mc = o->h_counts + 2 * (B + 1);
@@ -392,7 +417,7 @@ static int orb_collect(aslam_orb *o, aslam_keypoint *kps, uint8_t *desc, int32_t
         }
         if (again) ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    o->pending = 0;
+    o->last_count = h_cnt[0];
     int ovf = 0;
     for (int i = 0; i < n; ++i) {
         if (counts) counts[i] = h_cnt[i];
@@ -415,6 +440,16 @@ int aslam_orb_track_batch_async(aslam_orb *o, const uint8_t *images, int n, size
     int rc = orb_extract_common(o, images, n, frame_stride, row_stride, nullptr,
                                 images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
     if (rc) return rc;
+    rc = orb_track_enqueue(o, n, ratio);
+    if (rc) o->pending = 0;             // the call failed as a whole: nothing is pending
+    return rc;
+}
+
+}  // extern "C"
+
+static int orb_track_enqueue(aslam_orb *o, int n, float ratio)
+{
+    int rc;
     aslam_ctx *ctx = o->ctx;
     const OrbGeom &g = o->g;
     const int cap = g.kp_cap, splits = o->track_splits;
@@ -436,6 +471,27 @@ int aslam_orb_track_batch_async(aslam_orb *o, const uint8_t *images, int n, size
     ASLAM_CUDA(cudaMemcpyAsync(o->b.counts, o->b.counts + n, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     o->have_carry = true;
     o->pending_track = true;
+    return ASLAM_OK;
+}
+
+extern "C" {
+
+int aslam_orb_retain_descriptors(aslam_orb *o, const uint8_t **d_desc, int32_t *rows)
+{
+    ASLAM_REQUIRE(o && d_desc && rows, "NULL argument");
+    if (o->pending) return fail(ASLAM_E_STATE, "retain_descriptors with an extract pending; call sync first");
+    if (o->last_count < 0) return fail(ASLAM_E_STATE, "retain_descriptors needs a synced extract whose descriptors were not retained yet");
+    aslam_ctx *ctx = o->ctx;
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    const int slot = o->retain_next;
+    if (!o->d_retained[slot]) ASLAM_CUDA(cudaMalloc(&o->d_retained[slot], (size_t)o->g.kp_cap * 32));
+    const int n = std::min(o->last_count, o->g.kp_cap);
+    if (n) ASLAM_CUDA(cudaMemcpyAsync(o->d_retained[slot], o->b.desc + (size_t)o->g.kp_cap * 32, (size_t)n * 32,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    *d_desc = o->d_retained[slot];
+    *rows = n;
+    o->retain_next = slot ^ 1;
+    o->last_count = -1;
     return ASLAM_OK;
 }
 

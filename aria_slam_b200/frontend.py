@@ -265,12 +265,47 @@ class LoopDB:
         check(lib().aslam_loopdb_query_segmented(self.h, ptr(q), len(q), C.c_double(ratio), ptr(good)))
         return good[:self.num_keyframes]
 
+    def query_segmented_device(self, d_q, nq, d_good, ratio=0.7):
+        """Queries and counts stay on the device (d_good[num_keyframes] int32); asynchronous."""
+        check(lib().aslam_loopdb_query_segmented_device(self.h, ptr(d_q), int(nq), C.c_double(ratio), ptr(d_good)))
+
+    def match_keyframe(self, kf_index, q, ratio=0.7):
+        """verifyGeometry's re-match (LoopClosure.cpp:116-130) against the resident rows of keyframe kf_index."""
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        out = np.zeros(max(len(q), 1), MATCH_DTYPE); n = C.c_int(0)
+        check(lib().aslam_loopdb_match_keyframe(self.h, int(kf_index), ptr(q), len(q), C.c_double(ratio), ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    @property
+    def capacity_rows(self):
+        return lib().aslam_loopdb_capacity_rows(self.h)
+
     def query_global(self, q):
         """(row[nq,2] int64 global rows, dist[nq,2]); -1 where empty."""
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
         top2 = np.zeros((len(q), 2), np.uint64)
         check(lib().aslam_loopdb_query_global(self.h, ptr(q), len(q), ptr(top2)))
         return unpack_top2(top2)
+
+    def exchange_status(self, nqblocks=0):
+        """(status word, stamps[nqblocks,2] of %globaltimer ns: pushed / all peers seen) of the last fused exchange."""
+        st = C.c_uint32(0)
+        stamps = np.zeros((max(nqblocks, 1), 2), np.uint64)
+        check(lib().aslam_loopdb_exchange_status(self.h, C.byref(st), ptr(stamps), int(nqblocks)))
+        return st.value, stamps[:nqblocks]
+
+    # one process per GPU: peers' exchange buffers through CUDA IPC (aslam_loopdb_shard_export / _init)
+    def shard_export(self, nranks, max_nq):
+        h = np.zeros(lib().aslam_loopdb_shard_handle_bytes(), np.uint8)
+        check(lib().aslam_loopdb_shard_export(self.h, int(nranks), int(max_nq), ptr(h)))
+        return h
+
+    def shard_init(self, rank, nranks, handles):
+        handles = np.ascontiguousarray(handles, np.uint8).reshape(nranks, -1)
+        check(lib().aslam_loopdb_shard_init(self.h, int(rank), int(nranks), ptr(handles)))
+
+    def query_global_sharded_device(self, d_q, nq, d_out):
+        check(lib().aslam_loopdb_query_global_sharded_device(self.h, ptr(d_q), int(nq), ptr(d_out)))
 
     def query_global_device(self, d_q, nq, d_top2):
         check(lib().aslam_loopdb_query_global_device(self.h, ptr(d_q), int(nq), ptr(d_top2)))
@@ -288,6 +323,70 @@ class LoopDB:
             self.h = None
 
 
+class LoopDBGroup:
+    """aslam_loopdb_shard_group: ONE process, one shard per listed GPU (peer access between them, keyframe k on shard
+    k % n).  Same calls and semantics as LoopDB; keyframes are indexed oldest first across the whole group."""
+
+    def __init__(self, devices, capacity_rows_per_shard, max_keyframes=500):
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(lib().aslam_loopdb_shard_group_create(dev, len(devices), int(capacity_rows_per_shard), int(max_keyframes), C.byref(h)))
+        self.h = h
+
+    def add(self, desc, keyframe_id):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        check(lib().aslam_loopdb_shard_group_add(self.h, ptr(d), len(d), int(keyframe_id)))
+
+    def clear(self):
+        check(lib().aslam_loopdb_shard_group_clear(self.h))
+
+    @property
+    def num_shards(self):
+        return lib().aslam_loopdb_shard_group_num_shards(self.h)
+
+    @property
+    def num_keyframes(self):
+        return lib().aslam_loopdb_shard_group_num_keyframes(self.h)
+
+    @property
+    def num_rows(self):
+        return lib().aslam_loopdb_shard_group_num_rows(self.h)
+
+    def keyframes(self, with_shards=False):
+        n = self.num_keyframes
+        ids = np.zeros(n, np.uint64); rows = np.zeros(n, np.int32); shards = np.zeros(n, np.int32)
+        check(lib().aslam_loopdb_shard_group_keyframes(self.h, ptr(ids), ptr(rows), ptr(shards)))
+        return (ids, rows, shards) if with_shards else (ids, rows)
+
+    def query_segmented(self, q, ratio=0.7):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        good = np.zeros(max(self.num_keyframes, 1), np.int32)
+        check(lib().aslam_loopdb_shard_group_query_segmented(self.h, ptr(q), len(q), C.c_double(ratio), ptr(good)))
+        return good[:self.num_keyframes]
+
+    def query_global(self, q, raw=False):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        top2 = np.zeros((len(q), 2), np.uint64)
+        check(lib().aslam_loopdb_shard_group_query_global(self.h, ptr(q), len(q), ptr(top2)))
+        return top2 if raw else unpack_top2(top2)
+
+    def read_result(self, shard, nq):
+        top2 = np.zeros((nq, 2), np.uint64)
+        check(lib().aslam_loopdb_shard_group_read_result(self.h, int(shard), int(nq), ptr(top2)))
+        return top2
+
+    def match_keyframe(self, kf_index, q, ratio=0.7):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        out = np.zeros(max(len(q), 1), MATCH_DTYPE); n = C.c_int(0)
+        check(lib().aslam_loopdb_shard_group_match_keyframe(self.h, int(kf_index), ptr(q), len(q), C.c_double(ratio), ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def close(self):
+        if self.h:
+            lib().aslam_loopdb_shard_group_destroy(self.h)
+            self.h = None
+
+
 def unpack_top2(top2):
     top2 = np.asarray(top2, np.uint64)
     empty = top2 == np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -299,16 +398,25 @@ def unpack_top2(top2):
 
 class B200LoopDetector:
     """ILoopDetector over aslam_loopdb_* -- the descriptor side of LoopClosureDetector
-    (src/legacy/LoopClosure.cpp:15-114).  detect() ranks keyframes exactly as findCandidates does
-    and returns the best one that clears min_score/min_matches; the CPU-side geometric
-    verification of the reference (:116-195, RANSAC + pose) is outside this path."""
+    (src/legacy/LoopClosure.cpp:15-130).  detect() ranks keyframes exactly as findCandidates does
+    and returns the best one that clears min_score/min_matches; the candidate re-match of verifyGeometry
+    (:116-130) runs against the rows already resident in the database (no host copy of the keyframes, no
+    upload of keyframe descriptors); the RANSAC check after it (:131-156) is host code outside this path.
+
+    devices = a list of CUDA devices: the database is sharded over them inside this one process
+    (aslam_loopdb_shard_group); None = one database on the context's device."""
 
     def __init__(self, ctx: Optional[Context] = None, min_frames_between=30, min_score=0.3, min_matches=30,
-                 capacity_rows=500 * 2600, max_keyframes=500):
-        self.ctx = ctx or Context(0)
-        self.db = LoopDB(self.ctx, capacity_rows, max_keyframes)
-        self.matcher = B200Matcher(self.ctx)
-        self._kf_desc = {}
+                 capacity_rows=None, max_keyframes=500, max_features=2000, devices=None):
+        if capacity_rows is None:                       # the store grows on demand; this is only the first allocation
+            capacity_rows = max_keyframes * (max_features + 64)
+        if devices is not None and len(devices) > 1:
+            self.ctx = None
+            per_shard = -(-capacity_rows // len(devices))
+            self.db = LoopDBGroup(devices, per_shard, max_keyframes)
+        else:
+            self.ctx = ctx or Context(devices[0] if devices else 0)
+            self.db = LoopDB(self.ctx, capacity_rows, max_keyframes)
         self.min_frames_between = min_frames_between
         self.min_score = min_score
         self.min_matches = min_matches
@@ -317,10 +425,6 @@ class B200LoopDetector:
     def addKeyFrame(self, kf: KeyFrame):
         d = np.ascontiguousarray(kf.frame.descriptors, np.uint8).reshape(-1, 32)
         self.db.add(d, kf.id)
-        self._kf_desc[kf.id] = d
-        live = set(int(i) for i in self.db.keyframes()[0])
-        for k in [k for k in self._kf_desc if k not in live]:
-            del self._kf_desc[k]
 
     def findCandidates(self, query: KeyFrame):
         """LoopClosure.cpp:72-114: [(keyframe index, score)], at most 5, best first."""
@@ -343,16 +447,15 @@ class B200LoopDetector:
         if self.db.num_keyframes < self.min_frames_between:     # LoopClosure.cpp:34-36
             return None
         ids, _ = self.db.keyframes()
+        q = np.ascontiguousarray(query.frame.descriptors, np.uint8).reshape(-1, 32)
         for i, score in self.findCandidates(query):
             if score < self.min_score:
                 continue
-            m = []
-            kf = Frame(descriptors=self._kf_desc[int(ids[i])].reshape(-1))
-            self.matcher.match(query.frame, kf, m, 0.7)          # verifyGeometry's re-match (:120-128)
+            m = self.db.match_keyframe(i, q, 0.7)                # verifyGeometry's re-match (:120-128) on resident rows
             if len(m) < self.min_matches:
                 continue
             self._loops += 1
-            return LoopCandidate(int(query.id), int(ids[i]), score, np.array(m, MATCH_DTYPE))
+            return LoopCandidate(int(query.id), int(ids[i]), score, m)
         return None
 
     def getLoopCount(self):
@@ -366,6 +469,9 @@ class B200LoopDetector:
 
     def setMinMatches(self, n):
         self.min_matches = int(n)
+
+    def close(self):
+        self.db.close()
 
 
 # ----------------------------------------------------------------------------- batched tracker

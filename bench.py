@@ -150,7 +150,7 @@ def cv2_extract_match(frames, nfeat, threads):
     for f in frames:
         _, d = orb.detectAndCompute(f, None)
         if prev is not None and d is not None and len(prev) >= 2:
-            for m in bf.knnMatch(d, prev, k=2):
+            for m in bf.knnMatch(prev, d, k=2):          # knnMatch(prev_frame, current_frame), main.cpp:158-161
                 if len(m) >= 2 and m[0].distance < 0.75 * m[1].distance:
                     good += 1
         prev = d

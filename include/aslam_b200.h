@@ -38,6 +38,7 @@ typedef enum {
 typedef struct aslam_ctx aslam_ctx;
 typedef struct aslam_orb aslam_orb;
 typedef struct aslam_loopdb aslam_loopdb;
+typedef struct aslam_loopdb_group aslam_loopdb_group;
 
 /* aria::core::KeyPoint, include/core/Types.hpp:9-15 (24 bytes, same field order) */
 typedef struct {
@@ -88,6 +89,7 @@ typedef struct {
  * (OrbCudaExtractor.cpp:21-33, CudaMatcher.cpp:7-19; FactoryConfig::cuda_device,
  * include/factory/PipelineFactory.hpp:21).  stream = a cudaStream_t to borrow, or NULL to
  * create (and later destroy) a private one. */
+ASLAM_API int aslam_device_count(void);      /* CUDA devices visible to this process (0 without a driver) */
 ASLAM_API int aslam_ctx_create(int device, void *stream, aslam_ctx **out);
 ASLAM_API void aslam_ctx_destroy(aslam_ctx *ctx);
 ASLAM_API int aslam_ctx_sync(aslam_ctx *ctx);
@@ -142,8 +144,8 @@ ASLAM_API int aslam_orb_extract_batch_async(aslam_orb *orb, const uint8_t *image
                                             size_t frame_stride, int row_stride,
                                             const uint8_t *masks);
 /* Waits, then copies out: kps[n][capacity], desc[n][capacity][32], counts[n].
- * ASLAM_E_OVERFLOW: a frame had more tied keypoints than capacity; the first capacity (in
- * level, y, x order) were returned. */
+ * ASLAM_E_OVERFLOW: a frame had more tied keypoints than capacity; the first capacity (by level, and
+ * within a level tile-major: 62x62-pixel tiles in row-major order, row-major inside a tile) were returned. */
 ASLAM_API int aslam_orb_sync(aslam_orb *orb, aslam_keypoint *kps, uint8_t *desc, int32_t *counts);
 
 /* Device-resident path (inputs already in HBM; results stay there). */
@@ -153,9 +155,19 @@ ASLAM_API int aslam_orb_extract_batch_device(aslam_orb *orb, const uint8_t *d_im
 ASLAM_API int aslam_orb_device_results(aslam_orb *orb, const aslam_keypoint **d_kps,
                                        const uint8_t **d_desc, const int32_t **d_counts);
 
-/* Extract n frames and match frame i (query) against frame i-1 (train) in the same stream;
- * frame 0 is matched against the last frame of the previous call on this handle (none on the
- * first call).  One call = the per-frame body of SlamPipeline::processFrame's
+/* Keeps the descriptors of the first frame of the extract just synced on the device beyond the next extract: they are
+ * copied (device to device, 64 KB) into one of two ring slots owned by the handle; *d_desc / *rows describe that slot,
+ * which stays valid until the second-next call of this function.  With aslam_match_knn2_resident this chains
+ * extract -> match of consecutive frames without a PCIe round trip of descriptors (the reference's
+ * OrbCudaExtractor + CudaMatcher::matchGpu pairing).  Once per synced extract. */
+ASLAM_API int aslam_orb_retain_descriptors(aslam_orb *orb, const uint8_t **d_desc, int32_t *rows);
+
+/* Extract n frames and match frame i-1 (query) against frame i (train) in the same stream, the
+ * direction of the reference's tracking loop, knnMatch(prev_frame, current_frame) (src/main.cpp:158-161,
+ * src/euroc_eval.cpp:167-169): matches[i] belongs to frame i, its query_idx indexes the keypoints of
+ * frame i-1 and its train_idx those of frame i, and it holds at most as many matches as frame i-1 has
+ * keypoints.  Frame 0 is matched against the last frame of the previous call on this handle (no
+ * matches on the first call).  One call = the per-frame body of SlamPipeline::processFrame's
  * extract -> match (docs H12:595-601 of the reference) for a whole batch.
  * ratio as in IMatcher::match (include/interfaces/IMatcher.hpp:19-24). */
 ASLAM_API int aslam_orb_track_batch_async(aslam_orb *orb, const uint8_t *images, int n,
@@ -210,6 +222,12 @@ ASLAM_API int aslam_match_knn2_device(aslam_ctx *ctx, const uint8_t *d_q, int nq
                                       const uint8_t *d_t, int nt, float ratio,
                                       aslam_match *d_out, int32_t *d_nout);
 
+/* CudaMatcher::matchGpu (include/adapters/gpu/CudaMatcher.hpp:22-28: "GPU-to-GPU matching, zero-copy when used with
+ * OrbCudaExtractor"): descriptor rows already on the device (aslam_orb_retain_descriptors, aslam_orb_device_results),
+ * matches to a host buffer -- the two 64 KB descriptor sets of a frame pair never cross PCIe again. */
+ASLAM_API int aslam_match_knn2_resident(aslam_ctx *ctx, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
+                                        float ratio, aslam_match *out, int *nout);
+
 /* ------------------------------------------------------------------ loop-closure database
  * Replaces the descriptor side of LoopClosureDetector (src/legacy/LoopClosure.cpp): the
  * keyframe store addKeyFrame (:24-31, FIFO cap 500) and findCandidates' per-keyframe
@@ -220,7 +238,12 @@ ASLAM_API int aslam_loopdb_create(aslam_ctx *ctx, int64_t capacity_rows, int max
                                   aslam_loopdb **out);
 ASLAM_API void aslam_loopdb_destroy(aslam_loopdb *db);
 /* Append one keyframe's descriptors (host rows).  Evicts oldest keyframes while more than
- * max_keyframes are stored (LoopClosure.cpp:27-30). */
+ * max_keyframes are stored (LoopClosure.cpp:27-30).  Like the reference's deque the store never refuses a
+ * keyframe: capacity_rows is the initial size and the array doubles when the live rows outgrow it
+ * (ASLAM_E_NOMEM only when the device is out of memory; a failed call changes nothing).
+ * The copy is asynchronous on the context's stream: pageable host rows are staged before the call returns and
+ * may be reused at once; PINNED host rows (aslam_host_alloc) must stay unchanged until the next query or
+ * aslam_ctx_sync. */
 ASLAM_API int aslam_loopdb_add(aslam_loopdb *db, const uint8_t *desc, int n, uint64_t keyframe_id);
 ASLAM_API int aslam_loopdb_add_device(aslam_loopdb *db, const uint8_t *d_desc, int n, uint64_t keyframe_id);
 ASLAM_API int aslam_loopdb_clear(aslam_loopdb *db);
@@ -231,6 +254,7 @@ ASLAM_API int aslam_loopdb_save(aslam_loopdb *db, const char *path);
 ASLAM_API int aslam_loopdb_load(aslam_loopdb *db, const char *path);
 ASLAM_API int aslam_loopdb_num_keyframes(const aslam_loopdb *db);
 ASLAM_API int64_t aslam_loopdb_num_rows(const aslam_loopdb *db);
+ASLAM_API int64_t aslam_loopdb_capacity_rows(const aslam_loopdb *db);
 ASLAM_API int aslam_loopdb_set_row_base(aslam_loopdb *db, int64_t row_base);
 /* ids[k], rows[k] of the stored keyframes, oldest first. */
 ASLAM_API int aslam_loopdb_keyframes(const aslam_loopdb *db, uint64_t *ids, int32_t *rows);
@@ -238,6 +262,16 @@ ASLAM_API int aslam_loopdb_keyframes(const aslam_loopdb *db, uint64_t *ids, int3
  * LoopClosure.cpp:92) against that keyframe's rows.  good[num_keyframes]. */
 ASLAM_API int aslam_loopdb_query_segmented(aslam_loopdb *db, const uint8_t *q, int nq, double ratio,
                                            int32_t *good);
+/* The same with the queries already on the device and the counts left there (d_good[num_keyframes]); asynchronous
+ * on the context's stream.  The sharded per-keyframe query is this call on every shard followed by an exchange of
+ * the counts alone. */
+ASLAM_API int aslam_loopdb_query_segmented_device(aslam_loopdb *db, const uint8_t *d_q, int nq, double ratio,
+                                                  int32_t *d_good);
+/* verifyGeometry's re-match of a loop candidate (LoopClosure.cpp:116-130): knnMatch(query, keyframe, 2) + the
+ * d0 < ratio*d1 test in double, against the RESIDENT rows of stored keyframe kf_index (oldest = 0) -- no keyframe
+ * descriptors cross PCIe.  out receives at most nq matches in query order (train_idx = row within the keyframe). */
+ASLAM_API int aslam_loopdb_match_keyframe(aslam_loopdb *db, int kf_index, const uint8_t *q, int nq, double ratio,
+                                          aslam_match *out, int *nout);
 /* Flat query: per query the two smallest (distance, global row) over the whole shard as
  * packed keys (distance << 40 | global row); empty slots are UINT64_MAX.  d_q, d_top2 are
  * device pointers (top2[nq][2]); asynchronous on the context's stream. */
@@ -250,16 +284,22 @@ ASLAM_API int aslam_loopdb_query_global_device(aslam_loopdb *db, const uint8_t *
  * before aslam_loop_merge_top2_device reads the local buffer.  Asynchronous on the context's stream. */
 ASLAM_API int aslam_loopdb_query_global_push_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
                                                     uint64_t *const *d_peer_bufs, int nparts, int my_part);
-/* The whole exchange in ONE kernel after the shard scan (no collective call, no separate barrier):
- * finish the scan, store the keys into every peer's buffer, publish a per-shard flag with release
- * semantics, wait (acquire) for all peers' flags of this round, merge, write d_out[nq][2].
- * Every peer buffer (peer-mapped, e.g. torch symmetric memory) is laid out as
- *     uint64 data[2][nparts][nq][2];  uint64 flags[2][nparts];        (zeroed before round 1)
- * `round` = 1, 2, 3, ... identical on all ranks; rounds alternate between the two halves.  Every rank
- * must call this once per round, each on its own GPU. */
+/* Shard scan AND exchange in ONE kernel launch (no collective call, no second launch): every CTA of the scan merges its
+ * row range into the per-query slots; the last CTA to arrive for a block of 512 queries stores that block's keys into every
+ * peer's buffer over NVLink, publishes a per-(shard, block) flag with release semantics, waits (acquire) for the
+ * peers' flags of the same block and round, merges, and writes d_out[nq][2].
+ * Every peer buffer (peer-mapped: CUDA IPC, cudaDeviceEnablePeerAccess or torch symmetric memory) is laid out as
+ *     uint64 data[2][nparts][nq][2];  uint64 flags[2][nparts][ceil(nq/512)];        (zeroed before round 1)
+ * `round` = 1, 2, 3, ... identical on all ranks; rounds alternate between the two halves.  Every rank must call this
+ * once per round, each on its own GPU, with the same nq <= 32768.  A rank that waits more than 4 s for a peer gives up
+ * and sets bit 0 of the status word (aslam_loopdb_exchange_status); its output is then invalid. */
 ASLAM_API int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
                                                         uint64_t *const *d_peer_bufs, int nparts, int my_part,
                                                         uint64_t round, uint64_t *d_out);
+/* Waits for the stream; *status = 0 when no exchange on this database ever timed out.  stamps (may be NULL):
+ * per query block of the last exchange, %globaltimer (ns) when the block was pushed to the peers and when all peers'
+ * flags had been seen -- the difference is how long this rank waited for the slowest peer. */
+ASLAM_API int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *stamps, int nqblocks);
 ASLAM_API size_t aslam_loop_exchange_buffer_bytes(int nparts, int nq);
 /* Host-buffer form of the flat query (copies in and out, synchronous). */
 ASLAM_API int aslam_loopdb_query_global(aslam_loopdb *db, const uint8_t *q, int nq, uint64_t *top2);
@@ -268,6 +308,48 @@ ASLAM_API int aslam_loopdb_query_global(aslam_loopdb *db, const uint8_t *q, int 
  * single-GPU answer.  Asynchronous on the context's stream. */
 ASLAM_API int aslam_loop_merge_top2_device(aslam_ctx *ctx, const uint64_t *d_parts, int nparts,
                                            int nq, uint64_t *d_out);
+
+/* ------------------------------------------------------------------ sharded loop database
+ * the keyframe database is sharded by keyframe over the GPUs of one node, the 64 KB query block is
+ * replicated, each GPU answers for its shard and one small exchange over NVLink follows (flat query: 2 keys per query;
+ * per-keyframe query: one int32 count per keyframe).
+ *
+ * (1) One process per GPU.  A plain aslam_loopdb is the rank's shard (row_base = global row of its first row).
+ *     aslam_loopdb_shard_export allocates the rank's exchange buffer and returns a CUDA IPC handle of
+ *     aslam_loopdb_shard_handle_bytes() bytes; the ranks all-gather the handles by any means (MPI, torch.distributed,
+ *     a file) and aslam_loopdb_shard_init opens the peers' buffers.  aslam_loopdb_query_global_sharded_device then is
+ *     aslam_loopdb_query_global_exchange_device with those peers and an internal round counter. */
+ASLAM_API size_t aslam_loopdb_shard_handle_bytes(void);
+ASLAM_API int aslam_loopdb_shard_export(aslam_loopdb *db, int nranks, int max_nq, void *handle_out);
+ASLAM_API int aslam_loopdb_shard_init(aslam_loopdb *db, int rank, int nranks, const void *handles /* [nranks][handle_bytes] */);
+ASLAM_API int aslam_loopdb_query_global_sharded_device(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_t *d_out);
+/* (2) One process, several GPUs -- the reference's shape: a single-process C++ program whose device knob is
+ *     FactoryConfig::cuda_device (include/factory/PipelineFactory.hpp:21) and whose LoopClosureDetector is called from
+ *     one thread (src/euroc_eval.cpp:224-242).  The group owns one context + one shard per listed device, enables peer
+ *     access between all of them (cudaDeviceEnablePeerAccess; exchange buffers are plain cudaMalloc memory) and
+ *     places keyframe k (insertion order) on shard k % ndevices, so the FIFO eviction of LoopClosure.cpp:27-30 keeps
+ *     the shards balanced.  Same semantics as the single aslam_loopdb calls of the same name: keyframes are indexed
+ *     oldest first across the whole group, global rows count from the group's creation. */
+ASLAM_API int aslam_loopdb_shard_group_create(const int *devices, int ndevices, int64_t capacity_rows_per_shard,
+                                              int max_keyframes, aslam_loopdb_group **out);
+ASLAM_API void aslam_loopdb_shard_group_destroy(aslam_loopdb_group *g);
+ASLAM_API int aslam_loopdb_shard_group_num_shards(const aslam_loopdb_group *g);
+ASLAM_API int aslam_loopdb_shard_group_add(aslam_loopdb_group *g, const uint8_t *desc, int n, uint64_t keyframe_id);
+ASLAM_API int aslam_loopdb_shard_group_clear(aslam_loopdb_group *g);
+ASLAM_API int aslam_loopdb_shard_group_num_keyframes(const aslam_loopdb_group *g);
+ASLAM_API int64_t aslam_loopdb_shard_group_num_rows(const aslam_loopdb_group *g);
+/* ids[k], rows[k], shards[k] (any may be NULL) of the stored keyframes, oldest first. */
+ASLAM_API int aslam_loopdb_shard_group_keyframes(const aslam_loopdb_group *g, uint64_t *ids, int32_t *rows, int32_t *shards);
+/* findCandidates' counts (LoopClosure.cpp:86-95) with every shard counting for its own keyframes; the exchange is
+ * the int32 count per keyframe.  good[num_keyframes], oldest first: equal to aslam_loopdb_query_segmented on one GPU. */
+ASLAM_API int aslam_loopdb_shard_group_query_segmented(aslam_loopdb_group *g, const uint8_t *q, int nq, double ratio,
+                                                       int32_t *good);
+/* Flat top-2 (host buffers): the fused scan + exchange kernel on every device; top2[nq][2] as aslam_loopdb_query_global. */
+ASLAM_API int aslam_loopdb_shard_group_query_global(aslam_loopdb_group *g, const uint8_t *q, int nq, uint64_t *top2);
+/* Device `shard`'s copy of the last flat query's merged keys (all copies are identical; for parity tests). */
+ASLAM_API int aslam_loopdb_shard_group_read_result(aslam_loopdb_group *g, int shard, int nq, uint64_t *top2);
+ASLAM_API int aslam_loopdb_shard_group_match_keyframe(aslam_loopdb_group *g, int kf_index, const uint8_t *q, int nq,
+                                                      double ratio, aslam_match *out, int *nout);
 
 /* ------------------------------------------------------------------ pipe micro-benchmarks
  * Measured integer-pipe ceilings used as roofline denominators for the matching kernel

@@ -159,4 +159,7 @@ def test_adapter_selftest_matches_oracle(tmp_path, oracle):
     ref = oracle.ratio_matches(idx, dist, 3, 4)
     got = np.stack([matches["q"], matches["t"], matches["d"].astype(np.int32)], 1)
     assert got.shape == ref.shape and (got == ref).all()
-    assert verdict[0] == 1 and verdict[1] == 3 and verdict[2] >= 20
+    # the loop detector's verdict: keyframe 3 (= frame 0) found, and its match list is verifyGeometry's re-match
+    # (LoopClosure.cpp:116-130: knnMatch(query, keyframe) + d0 < 0.7*d1 in double) computed on the resident rows
+    idx7, dist7 = oracle.knn2(frames[1][1], frames[0][1])
+    assert verdict[0] == 1 and verdict[1] == 3 and verdict[2] == len(oracle.ratio_matches(idx7, dist7, 7, 10)) >= 20

@@ -70,14 +70,32 @@ def test_matcher_argument_errors_and_degenerate_sizes(ctx):
     assert L.aslam_match_knn2(None, _lib.ptr(q), 10, _lib.ptr(t5), 5, C.c_float(0.75), _lib.ptr(out), C.byref(n)) == _lib.E_INVALID
 
 
-def test_loopdb_capacity_is_an_error_not_a_truncation(ctx):
+def test_loopdb_grows_instead_of_refusing_and_a_failed_add_changes_nothing(ctx, oracle):
+    """Like the reference's std::deque (LoopClosure.cpp:24-31) the store never refuses a keyframe: the array grows when the
+    live rows outgrow the initial capacity, with eviction, slide and growth interleaved; queries stay exact throughout.
+    A call that fails (bad argument) leaves the database as it was."""
     from aria_slam_b200 import _lib
     from aria_slam_b200.frontend import LoopDB
     rs = np.random.RandomState(4)
     db = LoopDB(ctx, 1000, 4)
-    db.add(rs.randint(0, 256, (600, 32), dtype=np.uint8), 0)
+    kfs = [rs.randint(0, 256, (n, 32), dtype=np.uint8) for n in (600, 1200, 300, 900, 2500, 40, 700)]
+    db.add(kfs[0], 0)
+    db.add(kfs[1], 1)                                  # one keyframe larger than the whole initial store
+    assert db.num_keyframes == 2 and db.num_rows == 1800 and db.capacity_rows >= 1800
+    for i in range(2, len(kfs)):
+        db.add(kfs[i], i)
+        live = kfs[max(0, i - 3):i + 1]                # FIFO cap 4
+        assert db.num_keyframes == len(live) and db.num_rows == sum(len(k) for k in live)
+        flat = np.concatenate(live)
+        q = np.concatenate([live[0][:30], live[-1][:30]])
+        start = np.concatenate([[0], np.cumsum([len(k) for k in live])]).astype(np.int32)
+        assert (db.query_segmented(q, 0.7) == oracle.loop_segment_counts(q, flat, start, 7, 10)).all()
+        rows, dist = db.query_global(q)
+        ridx, rdist = oracle.knn2(q, flat)
+        evicted = sum(len(k) for k in kfs[:max(0, i - 3)])          # global rows keep counting from creation
+        assert (rows - evicted == ridx).all() and (dist == rdist).all()
+    before = (db.num_keyframes, db.num_rows)
     with pytest.raises(_lib.AslamError) as e:
-        db.add(rs.randint(0, 256, (1200, 32), dtype=np.uint8), 1)      # one keyframe larger than the whole store
-    assert e.value.code in (_lib.E_INVALID, _lib.E_OVERFLOW, _lib.E_NOMEM)
-    assert db.num_keyframes == 1 and db.num_rows == 600
+        _lib.check(_lib.lib().aslam_loopdb_add(db.h, None, 5, 99))
+    assert e.value.code == _lib.E_INVALID and (db.num_keyframes, db.num_rows) == before
     db.close()

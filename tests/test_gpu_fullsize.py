@@ -62,7 +62,7 @@ def test_c2_full_batch_is_deterministic_split_invariant_and_matches_the_oracle_o
         og, oo = np.lexsort((kps[i, :N]["x"], kps[i, :N]["y"], kps[i, :N]["octave"])), np.lexsort((ko["x"], ko["y"], ko["octave"]))
         assert (desc[i, :N][og] == do[oo]).all(1).mean() >= 0.99      # the gate of north_star; 1.0 on every case so far
     for i in (1, 128, 255):
-        idx, dist = oracle.knn2(desc[i, :cnt[i]], desc[i - 1, :cnt[i - 1]])
+        idx, dist = oracle.knn2(desc[i - 1, :cnt[i - 1]], desc[i, :cnt[i]])      # query = previous frame (main.cpp:158-161)
         ref = oracle.ratio_matches(idx, dist, 3, 4)
         got = np.stack([m[i, :mc[i]]["query_idx"], m[i, :mc[i]]["train_idx"], m[i, :mc[i]]["distance"].astype(np.int32)], 1)
         assert got.shape == ref.shape and (got == ref).all()

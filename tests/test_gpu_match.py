@@ -315,9 +315,13 @@ def test_loopdb_save_load_round_trip(ctx, oracle, tmp_path):
     assert (a.query_segmented(q, 0.7) == b.query_segmented(q, 0.7)).all()
     (r1, d1), (r2, d2) = a.query_global(q), b.query_global(q)
     assert (r1 == r2).all() and (d1 == d2).all() and r1[:100, 0].min() >= 5000
-    small = LoopDB(ctx, 1000, 8)
+    grown = LoopDB(ctx, 1000, 8)
+    grown.load(path)                                   # more rows than its first allocation: the store grows
+    assert grown.num_rows == b.num_rows and (grown.query_segmented(q, 0.7) == a.query_segmented(q, 0.7)).all()
+    grown.close()
+    small = LoopDB(ctx, 4000, 3)
     with pytest.raises(_lib.AslamError):
-        small.load(path)                               # more rows than this database can hold
+        small.load(path)                               # more keyframes than this database's FIFO cap
     bad = tmp_path / "bad.db"
     bad.write_bytes(b"not a database")
     with pytest.raises(_lib.AslamError):
@@ -325,3 +329,95 @@ def test_loopdb_save_load_round_trip(ctx, oracle, tmp_path):
     assert b.num_keyframes == 5                        # a failed load leaves the database as it was
     for d in (a, b, small):
         d.close()
+
+
+def test_match_keyframe_on_resident_rows_equals_the_oracle(ctx, oracle):
+    """verifyGeometry's re-match (LoopClosure.cpp:116-130): knnMatch(query, keyframe) + d0 < 0.7*d1 in double against the
+    rows already stored in the database, for keyframes before and after an eviction + slide."""
+    from aria_slam_b200.frontend import LoopDB
+    kfs = _make_db(12, 250, 81)
+    db = LoopDB(ctx, 1500, 6)
+    for i, k in enumerate(kfs):
+        db.add(k, i)
+    live = kfs[6:]
+    rs = np.random.RandomState(82)
+    q = np.concatenate([live[2][:120], live[4][:50], rs.randint(0, 256, (80, 32), dtype=np.uint8)])
+    q[::4, 9] ^= 0x81
+    for i, k in enumerate(live):
+        m = db.match_keyframe(i, q, 0.7)
+        if len(k) < 2:
+            assert len(m) == 0
+            continue
+        idx, dist = oracle.knn2(q, k)
+        ref = oracle.ratio_matches(idx, dist, 7, 10)
+        got = np.stack([m["query_idx"], m["train_idx"], m["distance"].astype(np.int32)], 1)
+        assert got.shape == ref.shape and (got == ref).all(), "keyframe %d" % i
+    assert len(db.match_keyframe(2, q[:0], 0.7)) == 0
+    db.close()
+
+
+def test_fused_scan_exchange_with_one_shard_equals_the_plain_query(ctx, oracle):
+    """The fused scan + exchange kernel with nparts = 1 (this GPU is its only peer) goes through every step of the
+    protocol -- merged slots, push, flag, acquire, merge, re-arm -- and must give the plain flat query's keys, round
+    after round, also after a segmented query reused the scratch and for a ragged number of query blocks."""
+    import torch
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import LoopDB
+    from aria_slam_b200._lib import lib
+    from aria_slam_b200.sharded import pack_top2
+    rows = synth.descriptor_db(30_000, 31)
+    db = LoopDB(ctx, 40_000, 64)
+    for k in range(15):
+        db.add(rows[k * 2000:(k + 1) * 2000], k)
+    db.set_row_base(7_000_000)
+    for nq in (1300, 2000, 7):
+        q, _ = synth.loop_queries(rows, nq, 32 + nq)
+        ridx, rdist = oracle.knn2(q, rows)
+        ref = pack_top2(np.where(ridx >= 0, ridx.astype(np.int64) + 7_000_000, -1), rdist)
+        words = lib().aslam_loop_exchange_buffer_bytes(1, nq) // 8
+        buf = torch.zeros(words, dtype=torch.int64, device="cuda")
+        ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+        dq = torch.from_numpy(q).cuda()
+        out = torch.zeros((nq, 2), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        for rnd in (1, 2, 3):
+            out.zero_(); torch.cuda.synchronize()
+            db.query_global_exchange_device(dq, nq, ptrs, 1, 0, rnd, out)
+            ctx.sync()
+            assert (out.cpu().numpy().view(np.uint64) == ref).all(), (nq, rnd)
+            if rnd == 2:
+                db.query_segmented(q[:50], 0.7)            # overwrites the armed slots and the row-range table
+        st, stamps = db.exchange_status((nq + 511) // 512)
+        assert st == 0 and (stamps[:, 1] >= stamps[:, 0]).all() and (stamps[:, 0] > 0).all()
+    db.close()
+
+
+def test_shard_group_on_one_device_follows_the_single_database(ctx, oracle):
+    """aslam_loopdb_shard_group with a single device: FIFO eviction, per-keyframe counts, flat top-2 with global rows
+    that keep counting from creation, candidate re-match -- all equal to the plain aslam_loopdb and the oracle."""
+    from aria_slam_b200.frontend import LoopDB, LoopDBGroup
+    kfs = _make_db(25, 180, 91)
+    grp = LoopDBGroup([ctx.device], 800, 9)
+    one = LoopDB(ctx, 800, 9)
+    for i, k in enumerate(kfs):
+        grp.add(k, 500 + i)
+        one.add(k, 500 + i)
+    live = kfs[16:]
+    ids, rows, shards = grp.keyframes(with_shards=True)
+    assert list(ids) == [500 + i for i in range(16, 25)] and list(rows) == [len(k) for k in live] and (shards == 0).all()
+    assert grp.num_shards == 1 and grp.num_keyframes == 9 and grp.num_rows == sum(len(k) for k in live)
+    q = np.concatenate([live[1][:60], live[7][:60], kfs[2][:30]])
+    q[::5, 3] ^= 0x18
+    flat = np.concatenate(live)
+    start = np.concatenate([[0], np.cumsum([len(k) for k in live])]).astype(np.int32)
+    good = grp.query_segmented(q, 0.7)
+    assert (good == one.query_segmented(q, 0.7)).all() and (good == oracle.loop_segment_counts(q, flat, start, 7, 10)).all()
+    (r1, d1), (r2, d2) = grp.query_global(q), one.query_global(q)
+    assert (r1 == r2).all() and (d1 == d2).all()
+    ridx, rdist = oracle.knn2(q, flat)
+    assert (r1 - sum(len(k) for k in kfs[:16]) == ridx).all() and (d1 == rdist).all()
+    m1, m2 = grp.match_keyframe(7, q, 0.7), one.match_keyframe(7, q, 0.7)
+    assert len(m1) >= 50 and (m1 == m2).all()
+    grp.clear()
+    assert grp.num_keyframes == 0 and len(grp.query_segmented(q, 0.7)) == 0
+    grp.close(); one.close()

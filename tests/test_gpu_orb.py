@@ -211,7 +211,8 @@ def test_batch_equals_single_frames(ctx, oracle):
 
 
 def test_track_batch_matches_follow_oracle(ctx, oracle):
-    """extract + match of a stream: frame i vs i-1, with the carry across two calls."""
+    """extract + match of a stream: frame i-1 (query) vs frame i (train), the direction of the reference's tracking
+    loop (src/main.cpp:158-161), with the carry across two calls."""
     from aria_slam_b200 import synth
     frames = synth.frame_stream(8, 640, 480, 2000)
     tr = _tracker(ctx, 640, 480, 1000, batch=4)
@@ -223,9 +224,10 @@ def test_track_batch_matches_follow_oracle(ctx, oracle):
             got.append((kps[i, :cnt[i]].copy(), desc[i, :cnt[i]].copy(), m[i, :mc[i]].copy()))
     assert len(got[0][2]) == 0                         # first frame of the stream has no predecessor
     for i in range(1, 8):
-        idx, dist = oracle.knn2(got[i][1], got[i - 1][1])
+        idx, dist = oracle.knn2(got[i - 1][1], got[i][1])          # knnMatch(prev_frame, current_frame)
         ref = oracle.ratio_matches(idx, dist, 3, 4)
         m = got[i][2]
+        assert (m["query_idx"] < len(got[i - 1][0])).all() and (m["train_idx"] < len(got[i][0])).all()
         mine = np.stack([m["query_idx"], m["train_idx"], m["distance"].astype(np.int32)], 1)
         assert mine.shape == ref.shape and (mine == ref).all(), "frame %d" % i
     # odd frames are shifted copies of their predecessor: most keypoints find their partner

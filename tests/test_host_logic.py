@@ -54,6 +54,15 @@ def _gloo_worker(rank, world, port, tmp):
     merged = O.merge_top2([unpack_top2(parts[p]) for p in range(world)])
     ridx, rdist = O.knn2(q, db)
     ok = (merged[0] == ridx).all() and (merged[1] == rdist).all()
+    # the per-keyframe query's exchange: each rank counts for its own keyframes (13 keyframes over 2 ranks: 7 + 6,
+    # so the padded all-gather has to drop rank 1's padding), counts gathered in global keyframe order
+    from aria_slam_b200.sharded import all_gather_counts
+    ranges = plan_shards(len(starts) - 1, world)
+    per = max(b - a for a, b in ranges)
+    mine = np.zeros(per, np.int32)
+    mine[:hi - lo] = O.loop_segment_counts(q, db[r0:r1], (starts[lo:hi + 1] - r0).astype(np.int32), 7, 10)
+    good = all_gather_counts(torch.from_numpy(mine), ranges).numpy()
+    ok = ok and len(good) == len(starts) - 1 and (good == O.loop_segment_counts(q, db, starts.astype(np.int32), 7, 10)).all()
     open(os.path.join(tmp, "ok%d" % rank), "w").write("1" if ok else "0")
     dist.destroy_process_group()
 
