@@ -722,8 +722,8 @@ int aslam_loopdb_shard_group_create(const int *devices, int ndevices, int64_t ca
         if (rc) break;
         g->ctx.push_back(c);
         aslam_loopdb *db = nullptr;
-        // a shard keeps every max_keyframes/n-th keyframe; the group evicts explicitly, so the shard's own cap never bites
-        rc = aslam_loopdb_create(c, capacity_rows_per_shard, max_keyframes, &db);
+        // the group evicts explicitly (the globally oldest keyframe), so a shard's own FIFO cap must never bite
+        rc = aslam_loopdb_create(c, capacity_rows_per_shard, 0x7fffffff, &db);
         if (rc) break;
         db->scattered = true;
         g->shard.push_back(db);

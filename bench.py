@@ -31,7 +31,24 @@ METRIC = "orb_extract_match_frames_per_s_752x480"
 WORKLOAD = "C2: stream of 256 synthetic 752x480 frames per GPU, ORB 2000 kpts (8 levels) + frame-to-frame Hamming kNN2 ratio 0.75"
 # algorithmic bytes per 752x480 frame, each stage streaming its input once
 BYTES_PER_FRAME = {"resize": 1_845_634, "fast_nms": 1_117_367, "blur": 2_234_734}
-LOOP_DB_ROWS, LOOP_NQ = 1_000_000, 2000
+LOOP_DB_ROWS, LOOP_NQ, LOOP_KF_ROWS = 1_000_000, 2000, 2000
+
+
+def bench_config():
+    """The `config` object of both arms (ours and --impl reference): the same workload, the same 256 frames per GPU and step."""
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": BATCH,
+            "l2_policy": "working set per step (pyramid+blur+candidates ~1.4 GB) exceeds the 126 MB L2",
+            "multi_gpu": "replicas: independent frame streams per GPU, no collective"}
+
+
+def host_info():
+    info = {"cores": os.cpu_count() or 1, "cpu": cpu_model()}
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+    except OSError:
+        info["numa_nodes"] = None
+    return info
 
 
 def env_int(name, default):
@@ -157,19 +174,46 @@ def cv2_extract_match(frames, nfeat, threads):
     return good
 
 
-def cv2_stream_pool(frames, nfeat, workers, per_worker):
-    """The same CPU path run the way the GPU arm runs it: independent frame streams side by side, one host
-    thread each (cv::ORB parallelises only resize/FAST/blur internally and scales poorly with
-    cv2.setNumThreads; independent streams with one OpenCV thread each use the cores about 4x better).
-    Stream k handles frames [k*per_worker, (k+1)*per_worker] -- per_worker matched frames + their predecessor.
-    Returns the number of frames extracted and matched."""
-    import cv2
-    from concurrent.futures import ThreadPoolExecutor
-    cv2.setNumThreads(1)
-    chunks = [frames[k * per_worker:(k + 1) * per_worker + 1] for k in range(workers) if (k + 1) * per_worker < len(frames)]
-    with ThreadPoolExecutor(max(len(chunks), 1)) as ex:
-        list(ex.map(lambda c: cv2_extract_match(c, nfeat, 1), chunks))
-    return per_worker * len(chunks)
+class Cv2Streams:
+    """The same CPU path run the way the GPU arm runs it: the batch is cut into independent frame streams, one host
+    thread each with one OpenCV thread (cv::ORB parallelises only resize/FAST/blur internally and scales poorly with
+    cv2.setNumThreads; independent streams use the cores about 4x better).  Like the GPU arm's streams, a stream keeps
+    its last frame's descriptors between steps, so every frame of a step is extracted once and matched once."""
+
+    def __init__(self, frames, nfeat, workers):
+        import cv2
+        from concurrent.futures import ThreadPoolExecutor
+        cv2.setNumThreads(1)
+        self.cv2 = cv2
+        n = len(frames)
+        workers = max(1, min(workers, n))
+        cuts = [n * k // workers for k in range(workers + 1)]
+        self.chunks = [frames[cuts[k]:cuts[k + 1]] for k in range(workers)]
+        self.prev = [None] * workers
+        self.orbs = [cv2.ORB_create(nfeat, 1.2, 8, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20) for _ in range(workers)]
+        self.bfs = [cv2.BFMatcher(cv2.NORM_HAMMING) for _ in range(workers)]
+        self.pool = ThreadPoolExecutor(workers)
+        self.workers, self.frames_per_step = workers, n
+
+    def _run(self, k, limit):
+        orb, bf, prev, good = self.orbs[k], self.bfs[k], self.prev[k], 0
+        for f in self.chunks[k][:limit]:
+            _, d = orb.detectAndCompute(f, None)
+            if prev is not None and d is not None and len(prev) >= 2 and len(d) >= 2:
+                for m in bf.knnMatch(prev, d, k=2):          # knnMatch(prev_frame, current_frame), main.cpp:158-161
+                    if len(m) >= 2 and m[0].distance < 0.75 * m[1].distance:
+                        good += 1
+            prev = d
+        self.prev[k] = prev
+        return good
+
+    def step(self, limit=None):
+        """One pass over the batch (or over the first `limit` frames of every stream); returns frames processed."""
+        list(self.pool.map(lambda k: self._run(k, limit), range(self.workers)))
+        return sum(len(c[:limit]) for c in self.chunks)
+
+    def close(self):
+        self.pool.shutdown()
 
 
 def cpu_baseline_frames(frames, budget_s=12.0):
@@ -179,16 +223,16 @@ def cpu_baseline_frames(frames, budget_s=12.0):
     t0 = time.perf_counter()
     cv2_extract_match(frames[:9], NFEAT, cores)
     single = 8 / (time.perf_counter() - t0)
-    per_worker = 4
-    usable = min(cores, (len(frames) - 1) // per_worker)
-    cv2_stream_pool(frames, NFEAT, usable, 1)            # warm-up of the pool path
-    n, t0 = 0, time.perf_counter()
+    st = Cv2Streams(frames, NFEAT, cores)
+    st.step(1)                                           # warm-up of the pool path
+    per, n, t0 = 4, 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s:
-        n += cv2_stream_pool(frames, NFEAT, usable, per_worker)
+        n += st.step(per)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": usable, "kind": "reference",
-            "sample": "%d frames (%d independent streams of %d matched frames, repeated for %.0f s), cv2 %s ORB_create(2000)+BFMatcher "
-                      "knnMatch(k=2)+0.75 ratio, one OpenCV thread per stream, %s" % (n, usable, per_worker, dt, cv2.__version__, cpu_model()),
+    st.close()
+    return {"value": n / dt, "unit": "frames/s", "cores": st.workers, "kind": "reference",
+            "sample": "%d frames (%d independent streams x %d frames per pass, repeated for %.0f s), cv2 %s ORB_create(2000)+BFMatcher "
+                      "knnMatch(k=2)+0.75 ratio, one OpenCV thread per stream, %s" % (n, st.workers, per, dt, cv2.__version__, cpu_model()),
             "single_stream_all_cv2_threads": {"value": single, "unit": "frames/s", "threads": cores}}
 
 
@@ -227,30 +271,30 @@ def single_frame_latency(ctx, frames, reps=50):
 
 
 def run_reference(args):
+    """The reference's own CPU path (cv2 = the OpenCV the reference links) on this box's host cores, on OUR arm's config:
+    every step is the full 256-frame batch, cut into one frame stream per core."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     from aria_slam_b200 import synth
     cores = os.cpu_count() or 1
-    per_worker = 4                                          # bounded sample of the 256-frame batch per step
-    per_step = per_worker * cores
-    frames = synth.frame_stream(min(per_step, BATCH - 1) + 1, W, H, 1000)
-    workers = min(cores, (len(frames) - 1) // per_worker)
-    per_step = per_worker * workers
+    frames = synth.frame_stream(BATCH, W, H, 1000)
+    st = Cv2Streams(frames, NFEAT, cores)
     for _ in range(max(args.warmup, 1)):
-        cv2_stream_pool(frames, NFEAT, workers, 1)
+        st.step(1)                                          # one frame per stream: thread pool, caches, cv2 dispatch
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cv2_stream_pool(frames, NFEAT, workers, per_worker)
+        st.step()
     dt = time.perf_counter() - t0
-    val = per_step * args.steps / dt
-    sample = "%d frames per step of the 256-frame batch (%d independent streams of %d matched frames, one OpenCV thread each); cv2 %s ORB+BFMatcher, %s" % (
-        per_step, workers, per_worker, __import__("cv2").__version__, cpu_model())
+    val = BATCH * args.steps / dt
+    sample = "the full %d-frame batch per step (%d independent streams, one OpenCV thread each); cv2 %s ORB+BFMatcher, %s" % (
+        BATCH, st.workers, __import__("cv2").__version__, cpu_model())
+    st.close()
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": per_step},
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": workers, "kind": "reference", "sample": sample},
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": bench_config(), "host": host_info(),
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": st.workers, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
 
@@ -397,31 +441,162 @@ def run_ours(args):
     mc_np = np.concatenate([p[2]["mc"].numpy() for p in pipes])
     checks = {"frames_at_quota": int((cnt_np == NFEAT).sum()), "median_matches_shifted_pairs": float(np.median(mc_np[1::2]))}
 
+    # ---- copy-only probe: the step's H2D and D2H bytes with no kernels at all, every rank at once.  It separates "PCIe /
+    # host memory cannot carry more" from "the GPU is waiting for something else" when end-to-end scaling falls off.
+    def copy_only(reps=8):
+        d_in = torch.empty((BATCH, H, W), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty(d2h, dtype=torch.uint8, device="cuda")
+        h_out = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        res = {}
+        for name, up, down in (("h2d", True, False), ("d2h", False, True), ("both", True, True)):
+            for timed in (False, True):
+                barrier()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream); s_in.wait_event(c0); s_out.wait_event(c0)
+                for _ in range(reps if timed else 2):
+                    if up:
+                        with torch.cuda.stream(s_in):
+                            d_in.copy_(h_in, non_blocking=True)
+                    if down:
+                        with torch.cuda.stream(s_out):
+                            h_out.copy_(d_out, non_blocking=True)
+                for st_ in (s_in, s_out):
+                    ev = torch.cuda.Event(); ev.record(st_); stream.wait_event(ev)
+                c1.record(stream)
+                barrier()
+            sec = max_over_ranks(c0.elapsed_time(c1) * 1e-3) / reps
+            res[name] = {"ms_per_step_bytes": sec * 1e3, "GBps_per_gpu": ((h2d if up else 0) + (d2h if down else 0)) / sec / 1e9,
+                         "GBps_all_gpus": world * ((h2d if up else 0) + (d2h if down else 0)) / sec / 1e9}
+        res["frames_per_s_if_copies_were_the_only_cost"] = world * BATCH / (res["both"]["ms_per_step_bytes"] * 1e-3)
+        return res
+
+    copy_probe = copy_only()
+
     # ---- loop-closure query, database sharded over the ranks (strong scaling)
     db = synth.descriptor_db(LOOP_DB_ROWS, 5)
     q, src = synth.loop_queries(db, LOOP_NQ, 6)
-    with torch.cuda.stream(stream):
-        lq = ShardedLoopQuery(ctx, db, rank, world, keyframe_rows=2000)
-        d_q = torch.from_numpy(q).cuda()
+    nqb = (LOOP_NQ + 511) // 512
+
+    def timed_loop(fn, steps):
+        """K calls of fn() back to back on `stream`, CUDA events, max over ranks -> ms per call."""
         for _ in range(Wm):
-            top2 = lq.query(d_q, LOOP_NQ)
+            fn()
         barrier()
+        t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0_.record(stream)
+        for _ in range(steps):
+            fn()
+        t1_.record(stream)
+        barrier()
+        return max_over_ranks(t0_.elapsed_time(t1_)) / steps
+
+    with torch.cuda.stream(stream):
+        lq = ShardedLoopQuery(ctx, db, rank, world, keyframe_rows=LOOP_KF_ROWS)
+        d_q = torch.from_numpy(q).cuda()
+        h_q = torch.from_numpy(q).pin_memory()
+        h_top2 = torch.empty((LOOP_NQ, 2), dtype=torch.int64).pin_memory()
+        lq.query(d_q, LOOP_NQ)
+        barrier()
+        # flat query, device-resident
         launches1 = kernel_launches()
         ctx.prof_enable(True); ctx.prof_read(reset=True)
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record(stream)
-        for _ in range(K):
-            top2 = lq.query(d_q, LOOP_NQ)
-        l1.record(stream)
-        barrier()
-        loop_ms = max_over_ranks(l0.elapsed_time(l1))
-        loop_launches = kernel_launches() - launches1
-        loop_prof = ctx.prof_read(reset=True)
+        loop_ms = timed_loop(lambda: lq.query(d_q, LOOP_NQ), K)
+        loop_launches = (kernel_launches() - launches1) * K // (K + Wm)
+        loop_prof = {k: (v[0] * K / (K + Wm), v[1] * K // (K + Wm)) for k, v in ctx.prof_read(reset=True).items()}
         ctx.prof_enable(False)
+        top2 = lq.query(d_q, LOOP_NQ)
+        wait_us = None
+        if lq.exchange in ("ipc", "fused"):
+            st_, stamps = lq.db.exchange_status(nqb)
+            wait_us = float((stamps[:, 1].astype(np.int64) - stamps[:, 0].astype(np.int64)).max()) / 1e3 if st_ == 0 else -1.0
+        # flat query end to end: pinned host queries in (64 KB), merged top-2 out to pinned host memory (32 KB)
+        d_q2 = torch.empty_like(d_q)
+
+        def flat_e2e():
+            d_q2.copy_(h_q, non_blocking=True)
+            h_top2.copy_(lq.query(d_q2, LOOP_NQ), non_blocking=True)
+        loop_e2e_ms = timed_loop(flat_e2e, K)
+        # the reference-shaped query: ratio-0.7 survivors per keyframe (findCandidates, LoopClosure.cpp:86-95), sharded by
+        # keyframe; the exchange is one all-gather of int32 counts
+        seg_ms = timed_loop(lambda: lq.query_segmented(d_q, LOOP_NQ), K)
+        good = lq.query_segmented(d_q, LOOP_NQ)
+        h_good = torch.empty(lq.n_keyframes, dtype=torch.int32).pin_memory()
+
+        def seg_e2e():
+            d_q2.copy_(h_q, non_blocking=True)
+            h_good.copy_(lq.query_segmented(d_q2, LOOP_NQ), non_blocking=True)
+        seg_e2e_ms = timed_loop(seg_e2e, K)
+        torch.cuda.synchronize()
     clk = clocks.stop()
-    rows, dist_ = unpack_top2(top2.cpu().numpy().view(np.uint64))
+    keys = top2.cpu().numpy().view(np.uint64).copy()
+    good_np = good.cpu().numpy().copy()
+
+    # ---- parity of the sharded queries, checked inside the bench at every N (the full [nq, 2] keys: both neighbours and
+    # both distances, which is what a faulty merge or flag protocol would corrupt)
+    loop_checks = {}
+    if world > 1:
+        gathered = torch.empty((world, LOOP_NQ, 2), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(gathered.view(-1, 2), top2.contiguous())
+        loop_checks["ranks_identical"] = bool((gathered == gathered[0]).all().item())
+        gg = torch.empty((world, lq.n_keyframes), dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(gg.view(-1), good.contiguous())
+        loop_checks["segmented_ranks_identical"] = bool((gg == gg[0]).all().item())
+    else:
+        loop_checks["ranks_identical"] = True
+        loop_checks["segmented_ranks_identical"] = True
+    if rank == 0:
+        import cv2
+        # the whole database on ONE GPU (rank 0), before any sharding
+        whole = LoopDB(ctx, LOOP_DB_ROWS, LOOP_DB_ROWS // LOOP_KF_ROWS)
+        for k in range(LOOP_DB_ROWS // LOOP_KF_ROWS):
+            whole.add(db[k * LOOP_KF_ROWS:(k + 1) * LOOP_KF_ROWS], k)
+        one = np.zeros((LOOP_NQ, 2), np.uint64)
+        from aria_slam_b200._lib import check, lib, ptr
+        check(lib().aslam_loopdb_query_global(whole.h, ptr(q), LOOP_NQ, ptr(one)))
+        loop_checks["equals_single_shard"] = bool((keys == one).all())
+        loop_checks["segmented_equals_single_gpu"] = bool((good_np == whole.query_segmented(q, 0.7)).all())
+        whole.close()
+        # a sample of queries against the reference's own matcher over all 1 M rows
+        cv2.setNumThreads(os.cpu_count() or 1)
+        pick = np.arange(0, LOOP_NQ, LOOP_NQ // 80)[:80]
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        # cv2 refuses train sets of 2^18 rows or more (IMGIDX_ONE): match in blocks of 250 000 rows, keep the two smallest
+        # (distance, row) per query -- the order cv2 uses inside a block
+        best = [[] for _ in pick]
+        for lo in range(0, LOOP_DB_ROWS, 250_000):
+            for i, m in enumerate(bf.knnMatch(q[pick], db[lo:lo + 250_000], k=2)):
+                best[i] += [(int(e.distance), lo + e.trainIdx) for e in m]
+        ok = True
+        for cand, row in zip(best, keys[pick]):
+            r_, d_ = unpack_top2(row)
+            two = sorted(cand)[:2]
+            ok = ok and len(two) == 2 and [two[0][1], two[1][1]] == list(r_) and [two[0][0], two[1][0]] == list(d_)
+        loop_checks["sample_equals_cv2"] = bool(ok)
+        loop_checks["sample_queries"] = int(len(pick))
+        loop_checks["second_neighbour_checked"] = True
+        # per-keyframe counts against cv2 on a sample of keyframes (the query's source keyframes are among them)
+        kf_pick = sorted(set([0, 1, 250, 499] + [int(r) // LOOP_KF_ROWS for r in src[:4]]))
+        okc = True
+        for kf in kf_pick:
+            cnt = 0
+            for m in bf.knnMatch(q, db[kf * LOOP_KF_ROWS:(kf + 1) * LOOP_KF_ROWS], k=2):
+                if len(m) >= 2 and m[0].distance < 0.7 * m[1].distance:       # LoopClosure.cpp:92
+                    cnt += 1
+            okc = okc and cnt == int(good_np[kf])
+        loop_checks["segmented_sample_equals_cv2"] = bool(okc)
+        loop_checks["segmented_sample_keyframes"] = len(kf_pick)
+        loop_checks["keys_crc32"] = int(__import__("zlib").crc32(keys.tobytes()))
+        loop_checks["exchange_status_ok"] = wait_us is None or wait_us >= 0
+    rows, dist_ = unpack_top2(keys)
     loop_ok = bool((rows[:, 0] == src).all())
-    loop_val = LOOP_NQ * K / (loop_ms * 1e-3)
+    loop_val = LOOP_NQ * K / (loop_ms * K * 1e-3)
+    waits = None
+    if world > 1 and wait_us is not None:
+        wt = torch.tensor([wait_us], dtype=torch.float64, device="cuda")
+        allw = torch.empty(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allw, wt)
+        waits = [round(x, 1) for x in allw.cpu().tolist()]
 
     if rank != 0:
         if world > 1:
@@ -440,6 +615,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
+    POPC_EXECUTED, POPC_ALGORITHMIC = 4.0, 8.0         # per descriptor pair: the carry-save form executes 4 (match.cu), SURVEY 8d counts 8
     for name, (tot_ms, n) in prof.items():
         if n == 0:
             continue
@@ -448,10 +624,12 @@ def run_ours(args):
             ach = BYTES_PER_FRAME[name] * frames_total / (tot_ms * 1e-3) / 1e9
             ent.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak)
         elif name == "knn2_partial":
-            # algorithmic: 8 POPC32 per descriptor pair; the kernel's carry-save adders execute 4
-            ach = 8.0 * pairs_per_step * K / (tot_ms * 1e-3) / 1e9
-            ent.update(bound="int_pipe(popc)", achieved=ach, peak=popc_peak, unit="Gpopc32/s", frac=ach / popc_peak,
-                       executed_popc_per_pair=4, frac_executed=0.5 * ach / popc_peak)
+            # `frac` = POPC instructions the kernel EXECUTES (4 per pair) over the POPC rate measured on this GPU;
+            # the algorithmic count of SURVEY 8d (8 per pair) is reported beside it as frac_algorithmic
+            ach = POPC_EXECUTED * pairs_per_step * K / (tot_ms * 1e-3) / 1e9
+            ent.update(bound="int_pipe(popc)", achieved=ach, peak=popc_peak, unit="Gpopc32/s executed", frac=ach / popc_peak,
+                       executed_popc_per_pair=POPC_EXECUTED, algorithmic_popc_per_pair=POPC_ALGORITHMIC,
+                       frac_algorithmic=POPC_ALGORITHMIC / POPC_EXECUTED * ach / popc_peak)
             # the same launch seen as HBM traffic (each descriptor row read once: 32 B per query and per train row) --
             # far below the HBM roofline, which is why the bound above is the POPC pipe
             kb = 32.0 * float(np.sum(cnt_np[1:].astype(np.float64) + cnt_np[:-1])) * K / (tot_ms * 1e-3) / 1e9
@@ -464,37 +642,58 @@ def run_ours(args):
         ent["traffic"] = traffic.get(name)
         stages[name] = ent
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
-    roof = dict(stages[dom]); roof["kernel"] = dom; roof["peak_source"] = peak_src if roof.get("bound") == "hbm" else "aslam_microbench(POPC) on this GPU"
+    roof = dict(stages[dom]); roof["kernel"] = dom; roof["peak_source"] = peak_src if roof.get("bound") == "hbm" else "aslam_microbench(POPC) on this GPU (MEASURED_PEAKS.json has no integer-pipe entry)"
     for k in ("bound", "achieved", "peak", "unit", "frac"):
         roof.setdefault(k, None)
     grp_ms = sum(stages[k]["ms_per_step"] for k in ("resize", "fast_nms") if k in stages)
     grp = (BYTES_PER_FRAME["resize"] + BYTES_PER_FRAME["fast_nms"]) * BATCH / (grp_ms * 1e-3) / 1e9 if grp_ms else None
 
+    # loop query: its own roofline (shard scan = XOR/POPC over nq x rows/N pairs per GPU) and end-to-end figure
+    scan_ms = loop_prof.get("knn2_partial", (0.0, 0))[0] / K
+    pairs_per_gpu = LOOP_NQ * float(LOOP_DB_ROWS) / world
+    loop_roof = None
+    if scan_ms > 0:
+        ach = POPC_EXECUTED * pairs_per_gpu / (scan_ms * 1e-3) / 1e9
+        loop_roof = {"kernel": "knn2_partial (shard scan%s)" % (" + fused exchange tail" if lq.exchange in ("ipc", "fused") else ""),
+                     "bound": "int_pipe(popc)", "achieved": ach, "peak": popc_peak, "unit": "Gpopc32/s executed per GPU", "frac": ach / popc_peak,
+                     "frac_algorithmic": POPC_ALGORITHMIC / POPC_EXECUTED * ach / popc_peak, "ms": scan_ms,
+                     "peak_source": "aslam_microbench(POPC) on this GPU",
+                     "note": "at N > 1 the fused kernel's duration includes the wait for the slowest peer (wait_for_slowest_peer_us)"}
+
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": BATCH, "streams_per_gpu": n_streams, "l2_policy": "working set per step (pyramid+blur+candidates ~1.4 GB) exceeds the 126 MB L2",
-                   "multi_gpu": "replicas: independent frame streams per GPU, no collective"},
+        "config": bench_config(), "streams_per_gpu": n_streams, "host": host_info(),
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "streams_per_gpu": n_streams, "timing": "CUDA events around all frame streams, max over ranks",
-                "wall_clock_value": world * BATCH * K / e2e_wall_s},
+                "wall_clock_value": world * BATCH * K / e2e_wall_s,
+                "copy_only_probe": copy_probe},
         "single_stream": {"ms_per_step": serial_ms / K, "value": world * BATCH * K / (serial_ms * 1e-3),
                           "note": "the K steps replayed on one stream with an event pair around every launch; roofline durations come from here"},
         "roofline": roof, "roofline_stages": stages,
         "roofline_group_pyramid_fast": {"bound": "hbm", "achieved": grp, "peak": hbm_peak, "unit": "GB/s", "frac": grp / hbm_peak if grp else None},
         "checks": checks,
         "loop_query": {"metric": "loop_query_descriptors_per_s", "value": loop_val, "unit": "query-descriptors/s", "db_rows": LOOP_DB_ROWS,
-                       "queries": LOOP_NQ, "n_gpus": world, "scaling": "strong", "ms_per_query_batch": loop_ms / K,
+                       "queries": LOOP_NQ, "keyframes": lq.n_keyframes, "n_gpus": world, "scaling": "strong", "ms_per_query_batch": loop_ms,
                        "collective": {"none": "none (1 GPU)",
-                                      "fused": "one kernel: scan finish + P2P stores of 2000x2 packed (dist,row) keys into every peer's buffer over NVLink + release/acquire flags + merge (no NCCL call)",
+                                      "ipc": "none: ONE kernel per query -- the shard scan whose last CTA per 512-query block stores the block's packed (dist,row) keys into every peer's buffer over NVLink (cudaMalloc buffers opened through CUDA IPC by the library), raises release flags, acquires the peers' flags and merges",
+                                      "fused": "as ipc, over buffers from torch symmetric memory",
                                       "push": "P2P stores from the finish kernel + symmetric-memory barriers + merge kernel",
                                       "nccl": "NCCL all_gather of 2000x2 packed (dist,row) keys per rank + merge kernel"}[lq.exchange],
-                       "exchange": lq.exchange,
-                       "best_row_is_source_row": loop_ok, "gpu_launches": int(loop_launches),
+                       "exchange": lq.exchange, "wait_for_slowest_peer_us_per_rank": waits,
+                       "best_row_is_source_row": loop_ok, "checks": loop_checks, "gpu_launches_per_query": loop_launches / K,
                        "stages_ms": {k: v[0] / K for k, v in loop_prof.items() if v[1]},
-                       "pairs_per_s": LOOP_NQ * float(LOOP_DB_ROWS) * K / (loop_ms * 1e-3)},
+                       "pairs_per_s": LOOP_NQ * float(LOOP_DB_ROWS) / (loop_ms * 1e-3),
+                       "roofline": loop_roof,
+                       "e2e": {"value": LOOP_NQ / (loop_e2e_ms * 1e-3), "unit": "query-descriptors/s", "ms_per_query_batch": loop_e2e_ms,
+                               "h2d_bytes_per_step": LOOP_NQ * 32, "d2h_bytes_per_step": LOOP_NQ * 16,
+                               "note": "pinned host queries in, merged top-2 keys out to pinned host memory, every query"},
+                       "per_keyframe": {"what": "findCandidates' ratio-0.7 survivor count per stored keyframe (LoopClosure.cpp:86-95), database sharded by keyframe, counts all-gathered (4 B per keyframe)",
+                                        "value": LOOP_NQ / (seg_ms * 1e-3), "unit": "query-descriptors/s", "ms_per_query_batch": seg_ms,
+                                        "e2e": {"value": LOOP_NQ / (seg_e2e_ms * 1e-3), "unit": "query-descriptors/s", "ms_per_query_batch": seg_e2e_ms,
+                                                "h2d_bytes_per_step": LOOP_NQ * 32, "d2h_bytes_per_step": lq.n_keyframes * 4}}},
     }
     if world == 1:
         out["latency_single_frame"] = single_frame_latency(ctx, frames)

@@ -244,12 +244,21 @@ def cv2_orb(img, nfeatures=1000, mask=None):
 
 
 def cv2_knn2(q, t):
-    """cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) -- LoopClosure.cpp:21,87."""
+    """cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) -- LoopClosure.cpp:21,87.  cv2 refuses train sets of 2^18 rows or more
+    (IMGIDX_ONE, matchers.cpp:860); larger sets are matched in blocks of 250 000 rows and the blocks' answers merged in
+    (distance, row) order, which is the order cv2 itself uses inside a block."""
     import cv2
     q = _u8(q).reshape(-1, 32); t = _u8(t).reshape(-1, 32)
     idx = -np.ones((len(q), 2), np.int32); dist = -np.ones((len(q), 2), np.int32)
     if len(q) == 0 or len(t) == 0:
         return idx, dist
+    if len(t) >= (1 << 18):
+        parts = []
+        for lo in range(0, len(t), 250_000):
+            i, d = cv2_knn2(q, t[lo:lo + 250_000])
+            parts.append((np.where(i >= 0, i.astype(np.int64) + lo, -1), d.astype(np.int64)))
+        mi, md = merge_top2(parts)
+        return mi.astype(np.int32), md.astype(np.int32)
     for i, m in enumerate(cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)):
         for j, e in enumerate(m):
             idx[i, j] = e.trainIdx; dist[i, j] = int(e.distance)

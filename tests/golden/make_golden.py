@@ -58,7 +58,42 @@ def main():
         out[name + "_descriptors"] = d[o]
     np.savez_compressed(os.path.join(HERE, "orb_configs.npz"), cv2_version=np.array(cv2.__version__), **out)
     print("wrote orb_320x240.npz (%d kp, %d masked), knn_ties.npz and orb_configs.npz" % (len(kps), len(kpm)))
+    main_c3_c5()
+
+
+def main_c3_c5():
+    """Configuration C3 (Aria RGB 1408x1408 as grey, 4000 keypoints, dynamic-object mask) and C5 (2000 queries against the
+    1 M-row keyframe database: all 4000 neighbour keys and the per-keyframe ratio-0.7 counts), again from cv2 itself."""
+    import zlib
+    w = h = 1408
+    f = synth.frame(w, h, 3000)
+    mask, _ = synth.mask_and_boxes(w, h, 3001, n=6)
+    k, d = O.cv2_orb(f, 4000, mask=mask)
+    o = np.lexsort((k["x"], k["y"], k["octave"]))
+    np.savez_compressed(os.path.join(HERE, "orb_c3.npz"), cv2_version=np.array(cv2.__version__),
+                        spec=np.array([w, h, 4000, 3000, 3001, zlib.crc32(f.tobytes()), zlib.crc32(mask.tobytes())], np.int64),
+                        keypoints=k[o], descriptors=d[o])
+    from aria_slam_b200.sharded import pack_top2
+    db = synth.descriptor_db(1_000_000, 5)
+    q, src = synth.loop_queries(db, 2000, 6)
+    cv2.setNumThreads(os.cpu_count() or 1)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    idx, dist = O.cv2_knn2(q, db)                # in blocks of 250 000 rows: cv2 refuses 2^18 train rows or more
+    keys = pack_top2(idx, dist)
+    good = np.zeros(500, np.int32)               # findCandidates' counts (LoopClosure.cpp:86-95) for a sample of keyframes
+    sample = sorted(set([0, 1, 7, 250, 499] + [int(r) // 2000 for r in src[:11]]))
+    for kf in sample:
+        good[kf] = sum(1 for m in bf.knnMatch(q, db[kf * 2000:(kf + 1) * 2000], k=2)
+                       if len(m) >= 2 and m[0].distance < 0.7 * m[1].distance)
+    np.savez_compressed(os.path.join(HERE, "loop_c5.npz"), cv2_version=np.array(cv2.__version__),
+                        spec=np.array([1_000_000, 5, 2000, 6, zlib.crc32(db[:100_000].tobytes()), zlib.crc32(q.tobytes())], np.int64),
+                        keys=keys, keys_crc32=np.array(zlib.crc32(keys.tobytes()), np.int64),
+                        keyframe_sample=np.array(sample, np.int32), good_sample=good[sample])
+    print("wrote orb_c3.npz (%d kp) and loop_c5.npz (crc %08x, %d keyframes sampled)" % (len(k), zlib.crc32(keys.tobytes()), len(sample)))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "c3c5":
+        main_c3_c5()
+    else:
+        main()

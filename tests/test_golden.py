@@ -87,3 +87,76 @@ def test_gpu_reproduces_golden_configs(ctx):
         f = Frame(); ex.extract(img, w, h, f)
         assert _orb_check(f.keypoints, f.descriptors, gk, gd) >= 0.99, name
         ex.close()
+
+
+def _c3():
+    import zlib
+    from aria_slam_b200 import synth
+    g = np.load(os.path.join(G, "orb_c3.npz"))
+    w, h, n, seed, mseed, crc, mcrc = (int(v) for v in g["spec"])
+    img = synth.frame(w, h, seed)
+    mask, boxes = synth.mask_and_boxes(w, h, mseed, n=6)
+    assert zlib.crc32(img.tobytes()) == crc and zlib.crc32(mask.tobytes()) == mcrc, "the synthetic generators drifted"
+    return img, mask, w, h, n, g["keypoints"], g["descriptors"]
+
+
+def test_oracle_reproduces_golden_c3(oracle):
+    """cv2's answer for configuration C3: 1408x1408, 4000 keypoints, dynamic-object mask."""
+    img, mask, w, h, n, gk, gd = _c3()
+    k, d = oracle.orb(img, n, mask=mask)
+    assert _orb_check(k, d, gk, gd) == 1.0
+
+
+def _c5():
+    import zlib
+    from aria_slam_b200 import synth
+    g = np.load(os.path.join(G, "loop_c5.npz"))
+    rows, dseed, nq, qseed, dcrc, qcrc = (int(v) for v in g["spec"])
+    db = synth.descriptor_db(rows, dseed)
+    q, src = synth.loop_queries(db, nq, qseed)
+    assert zlib.crc32(db[:100_000].tobytes()) == dcrc and zlib.crc32(q.tobytes()) == qcrc, "the synthetic generators drifted"
+    return g, db, q, src
+
+
+def test_oracle_reproduces_golden_c5_on_a_sample(oracle):
+    """cv2's neighbours over the whole 1 M-row database (all 4000 keys are in the fixture; the scalar oracle checks 24 queries)
+    and its per-keyframe ratio-0.7 counts on the sampled keyframes."""
+    import zlib
+    from aria_slam_b200.sharded import pack_top2
+    g, db, q, src = _c5()
+    assert zlib.crc32(g["keys"].tobytes()) == int(g["keys_crc32"])
+    pick = np.arange(0, len(q), len(q) // 24)[:24]
+    idx, dist = oracle.knn2(q[pick], db)
+    assert (pack_top2(idx, dist) == g["keys"][pick]).all()
+    for kf, want in zip(g["keyframe_sample"], g["good_sample"]):
+        got = oracle.loop_segment_counts(q, db[kf * 2000:(kf + 1) * 2000], np.array([0, 2000], np.int32), 7, 10)
+        assert int(got[0]) == int(want), kf
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_c3(ctx):
+    from aria_slam_b200.frontend import OrbB200Extractor, Frame
+    img, mask, w, h, n, gk, gd = _c3()
+    ex = OrbB200Extractor(n, ctx)
+    f = Frame(); ex.extract(img, w, h, f, mask=mask)
+    assert _orb_check(f.keypoints, f.descriptors, gk, gd) >= 0.99
+    ex.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_c5_every_key(ctx):
+    """All 4000 neighbour keys (both neighbours and both distances of all 2000 queries) of the 1 M-row query equal cv2's,
+    and so do the per-keyframe counts on the sampled keyframes."""
+    import zlib
+    from aria_slam_b200.frontend import LoopDB
+    from aria_slam_b200._lib import check, lib, ptr
+    g, db, q, src = _c5()
+    whole = LoopDB(ctx, len(db), 500)
+    for k in range(500):
+        whole.add(db[k * 2000:(k + 1) * 2000], k)
+    keys = np.zeros((len(q), 2), np.uint64)
+    check(lib().aslam_loopdb_query_global(whole.h, ptr(q), len(q), ptr(keys)))
+    assert (keys == g["keys"]).all() and zlib.crc32(keys.tobytes()) == int(g["keys_crc32"])
+    good = whole.query_segmented(q, 0.7)
+    assert (good[g["keyframe_sample"]] == g["good_sample"]).all()
+    whole.close()
