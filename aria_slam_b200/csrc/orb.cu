@@ -3,6 +3,9 @@
 //
 // Stands in for OrbCudaExtractor (src/adapters/gpu/OrbCudaExtractor.cpp) and the legacy Frame
 // constructors (src/legacy/Frame.cpp:6-49) of the reference.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <vector>
 
 #include "match.cuh"
@@ -23,6 +26,7 @@ struct aslam_orb {
     uint32_t *d_tabs = nullptr;
     float4 *d_pattern = nullptr;
     uint2 *d_ori_tab = nullptr;
+    void *d_tmaps = nullptr;               // [ORB_MAX_LEVELS][2] CUtensorMap: (pyr, 48 x 31 box), (blur, 64 x 39 box)
     // tracking
     aslam_match *d_matches = nullptr;      // [B][kp_cap]
     int32_t *d_match_counts = nullptr;     // [B]
@@ -53,6 +57,7 @@ static void orb_free_buffers(aslam_orb *o)
     cudaFree(o->d_matches); cudaFree(o->d_match_counts); cudaFree(o->d_probs); cudaFree(o->d_partial);
     cudaFree(o->d_tmp_kps); cudaFree(o->d_tmp_desc);
     cudaFree(o->d_retained[0]); cudaFree(o->d_retained[1]);
+    cudaFree(o->d_tmaps); o->d_tmaps = nullptr;
     o->d_retained[0] = o->d_retained[1] = nullptr; o->last_count = -1;
     if (o->h_counts) cudaFreeHost(o->h_counts);
     o->b = OrbBuffers();
@@ -76,6 +81,44 @@ __global__ void fill_track_problems_kernel(KnnProblem *probs, const uint8_t *des
     P.t_lo = min(s * rows_per, kp_cap);
     P.t_hi = min((s + 1) * rows_per, kp_cap);
     probs[i] = P;
+}
+
+// TMA descriptors of the describe kernel: every built level of `pyr` and `blur` as a 3-D u8 tensor (x = byte in the padded
+// row, y = row, z = frame of the batch).  The driver entry point comes through the runtime (no link against libcuda).
+static int orb_build_tensor_maps(aslam_orb *o)
+{
+#if ASLAM_DESC_TMA
+    static PFN_cuTensorMapEncodeTiled encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        cudaGetLastError();
+        return (PFN_cuTensorMapEncodeTiled)fn;
+    }();
+    if (!encode) return fail(ASLAM_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver (TMA needs CUDA 12 on sm_90+)");
+    const OrbGeom &g = o->g;
+    alignas(64) CUtensorMap maps[ORB_MAX_LEVELS * 2];
+    memset(maps, 0, sizeof(maps));
+    for (int l = 0; l < g.nbuilt; ++l) {
+        const LevelGeom &L = g.lv[l];
+        for (int which = 0; which < 2; ++which) {
+            uint8_t *base = (which ? o->b.blur : o->b.pyr) + L.off;
+            const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)o->max_batch};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyr_stride};      // bytes, dimensions 1 and 2
+            const cuuint32_t box[3] = {which ? 64u : 48u, which ? 39u : 31u, 1u};      // OPB_W x OPB_H, BPB_W x BPB_H of describe_kernel
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            const CUresult r = encode(&maps[2 * l + which], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ASLAM_E_CUDA, "cuTensorMapEncodeTiled(level %d, %s) -> CUresult %d", l, which ? "blur" : "pyr", (int)r);
+        }
+    }
+    ASLAM_CUDA(cudaMalloc(&o->d_tmaps, sizeof(maps)));
+    ASLAM_CUDA(cudaMemcpyAsync(o->d_tmaps, maps, sizeof(maps), cudaMemcpyHostToDevice, o->ctx->stream));
+    ASLAM_CUDA(cudaStreamSynchronize(o->ctx->stream));      // maps is a local
+    o->b.tmaps = o->d_tmaps;
+#endif
+    return ASLAM_OK;
 }
 
 static int orb_plan(aslam_orb *o)
@@ -115,6 +158,10 @@ static int orb_plan(aslam_orb *o)
     b.tabs = o->d_tabs;
     b.pattern = o->d_pattern;
     b.ori_tab = o->d_ori_tab;
+    {
+        const int rc = orb_build_tensor_maps(o);
+        if (rc) return rc;
+    }
     // tracking scratch
     o->track_splits = choose_splits(ctx, o->prm.nfeatures, o->prm.nfeatures, o->max_batch);     // expected rows, not the capacity
     ASLAM_CUDA(cudaMalloc(&o->d_matches, sizeof(aslam_match) * B * g.kp_cap));

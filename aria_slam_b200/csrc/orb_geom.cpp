@@ -105,7 +105,7 @@ bool build_orb_geometry(int width, int height, int nfeatures, float scale_factor
         L.sel_cap = L.quota + SEL_TIE_ROOM;
         sel_off += L.sel_cap;
         L.desc_block_off = desc_off;
-        if (active) desc_off += (L.sel_cap + 8 * DESC_KPW - 1) / (8 * DESC_KPW);      // 8 warps x DESC_KPW keypoints per describe CTA
+        if (active) desc_off += (L.sel_cap + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW);
         L.inv_sf = 1.f / L.sf;
         L.kp_size = 31.f * L.sf;
         L.row_fused_end = blur_mode == 0 ? 0 : blur_mode == 1 ? L.w : (L.w & ~31);

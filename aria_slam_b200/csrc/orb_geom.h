@@ -35,11 +35,18 @@ static_assert(31 * ((FT_OUT_H + 1) / 2) <= FT_CAP, "candidate slots per tile");
 #endif
 constexpr int BL_W = ASLAM_BL_W, BL_H = ASLAM_BL_H, BL_ROWS = BL_H + 6;
 static_assert(BL_W % 8 == 0 && BL_ROWS % 2 == 0 && BL_W * BL_ROWS * 4 <= 48 * 1024, "blur tile");
-// describe CTA = 8 warps x DESC_KPW keypoints handled one after another (the per-lane tables live in registers)
+// describe CTA = DESC_WARPS warps x DESC_KPW keypoints per warp (the per-lane tables live in registers)
 #ifndef ASLAM_DESC_KPW
 #define ASLAM_DESC_KPW 8
 #endif
-constexpr int DESC_KPW = ASLAM_DESC_KPW;
+#ifndef ASLAM_DESC_TMA
+#define ASLAM_DESC_TMA 1       // 1: patches arrive by TMA box loads (the shipped kernel); 0: round 1's LDG staging, kept for A/B runs
+#endif
+#ifndef ASLAM_DESC_WARPS
+#define ASLAM_DESC_WARPS (ASLAM_DESC_TMA ? 4 : 8)
+#endif
+constexpr int DESC_KPW = ASLAM_DESC_KPW, DESC_WARPS = ASLAM_DESC_WARPS;
+static_assert(DESC_KPW >= 1 && DESC_KPW <= 32, "a lane owns one of the warp's keypoints");
 constexpr int SEL_TIE_ROOM = 64;   // extra output rows per level for tied Harris responses
 
 struct LevelGeom {
@@ -50,7 +57,7 @@ struct LevelGeom {
     int blur_tile_off;       // first 128x58 blur tile of this level within the frame
     int quota;               // N_l
     int sel_off, sel_cap;    // rows of this level in the per-frame selection buffer
-    int desc_block_off;      // first describe CTA (64 keypoints each) of this level within the frame
+    int desc_block_off;      // first describe CTA (DESC_WARPS * DESC_KPW keypoints each) of this level within the frame
     int xtab_off, ytab_off;  // resize tables (level l-1 -> l), in uint32 entries
     int row_fused_end;       // blur: row-pass columns below this use fused multiply-add
     int col_fused_end;

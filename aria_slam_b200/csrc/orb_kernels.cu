@@ -1033,6 +1033,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 
+#if !ASLAM_DESC_TMA
 constexpr int DP_ROWS = 39, DP_WORDS = 12;      // blurred patch: +-19 rows of 12 aligned words
 constexpr int OP_ROWS = 31;                     // unblurred patch for the moments: +-15 rows, same row format
 
@@ -1059,6 +1060,8 @@ __device__ __forceinline__ void stage_rows_store(uint32_t *ps, int lane, const u
     for (int it = 0; it < (ROWS + 1) / 2; ++it)
         if (lane < 24 && 24 * it + lane < ROWS * DP_WORDS) ps[24 * it + lane] = w[it];
 }
+
+#endif
 
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c)
 {
@@ -1095,15 +1098,16 @@ __device__ __forceinline__ void sincos_0_2pi(double t, double &s, double &c)
     c = ((q + 1) & 2) ? -c0 : c0;
 }
 
+#if !ASLAM_DESC_TMA
 // grid.x = describe CTAs of all levels (LevelGeom::desc_block_off): the level is CTA-uniform.  A warp
 // handles DESC_KPW keypoints one after another, so its per-lane constants are fetched once and stay
 // in registers: the 8 rBRIEF comparisons of lane k (bits of descriptor byte k) as (x,y) float pairs,
 // and the orientation weights of the lane's 8 patch words.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * DESC_WARPS)
 describe_kernel(OrbGeom g, OrbBuffers b)
 {
-    __shared__ uint32_t blur_s[8][DP_ROWS * DP_WORDS];
-    __shared__ uint32_t orig_s[8][(OP_ROWS + 1) * DP_WORDS];      // +1 row: the lanes of row 31 read (weight 0)
+    __shared__ uint32_t blur_s[DESC_WARPS][DP_ROWS * DP_WORDS];
+    __shared__ uint32_t orig_s[DESC_WARPS][(OP_ROWS + 1) * DP_WORDS];      // +1 row: the lanes of row 31 read (weight 0)
     const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l = 0;
 #pragma unroll
@@ -1118,7 +1122,7 @@ describe_kernel(OrbGeom g, OrbBuffers b)
         b.counts[fslot] = min(total, g.kp_cap);
     }
     const int cnt = sc[l];
-    const int k0 = (((int)blockIdx.x - L.desc_block_off) * 8 + warp) * DESC_KPW;
+    const int k0 = (((int)blockIdx.x - L.desc_block_off) * DESC_WARPS + warp) * DESC_KPW;
     if (k0 >= cnt) return;
     int level_base = 0;                         // position of the level's first keypoint in the frame
     for (int i = 0; i < l; ++i) level_base += sc[i];
@@ -1228,10 +1232,241 @@ int launch_describe(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int n
     }
     dim3 grid(g.desc_blocks_per_frame, nframes);
     ProfScope ps(ctx, PK_DESCRIBE);
-    describe_kernel<<<grid, 256, 0, ctx->stream>>>(g, b);
+    describe_kernel<<<grid, 32 * DESC_WARPS, 0, ctx->stream>>>(g, b);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
+
+#else
+// ---- TMA form (the shipped kernel).  grid.x = describe CTAs of all levels (LevelGeom::desc_block_off): the level is
+// CTA-uniform.  A warp owns DESC_KPW keypoints, lane kk holds keypoint kk's coordinates, angle and rotation.
+//  * Patches arrive by TMA box loads (cp.async.bulk.tensor.3d over an (x, y, frame) u8 tensor per level): no staging
+//    loads or stores and no per-load addressing arithmetic.  Measured on B200: the box's first byte must be 16-byte
+//    aligned in global memory (an unaligned innermost coordinate of a u8 tensor raises "illegal instruction",
+//    tools/probes/tma_probe.cu), so a box starts at the patch's first column rounded down to 16 and is 48 x 31 bytes
+//    for the orientation patch (31 columns + up to 15 of slack) and 64 x 39 for the rBRIEF patch (39 + 15).
+//    A lane issues the loads of its own keypoint; both kinds go through small rings of buffers (DESC_ORING / DESC_RING
+//    slots per warp) refilled as keypoints finish; completion is signalled on per-warp mbarriers.
+//  * Two passes: (1) integer moments of every keypoint (2 DP4A per patch word), then fastAtan2 and the double-precision
+//    sin/cos ONCE for the whole warp -- lane kk computes keypoint kk's -- instead of once per keypoint on all lanes;
+//    (2) the 256 rotated comparisons of each keypoint, lane k = descriptor byte k.
+constexpr int OPB_W = 48, OPB_H = 31, OPB_BYTES = OPB_W * OPB_H, OPB_STRIDE = 1536;     // orientation box; smem slots are 128-B multiples
+constexpr int BPB_W = 64, BPB_H = 39, BPB_BYTES = BPB_W * BPB_H, BPB_STRIDE = 2560;     // rBRIEF box
+// Measured on B200 (ms per 256 frames x 2000 keypoints; round 1's LDG staging: 0.510): rings of 2 + 2 slots 0.322,
+// 4 + 3 slots 0.350, 4 + 4 or 8-warp CTAs 0.40 (fewer resident warps), 1 + 1 (no prefetch) 0.404.
+#ifndef ASLAM_DESC_RING
+#define ASLAM_DESC_RING 2
+#endif
+#ifndef ASLAM_DESC_ORING
+#define ASLAM_DESC_ORING 2
+#endif
+constexpr int DESC_RING = ASLAM_DESC_RING < DESC_KPW ? ASLAM_DESC_RING : DESC_KPW;
+constexpr int DESC_ORING = ASLAM_DESC_ORING < DESC_KPW ? ASLAM_DESC_ORING : DESC_KPW;
+constexpr int DESC_WARP_SMEM = DESC_ORING * OPB_STRIDE + DESC_RING * BPB_STRIDE;
+constexpr size_t DESC_SMEM_BYTES = (size_t)DESC_WARPS * DESC_WARP_SMEM + 128;           // + slack to align the base to 128 B
+static_assert(OPB_STRIDE >= (OPB_H + 1) * OPB_W && OPB_STRIDE % 128 == 0 && BPB_STRIDE >= BPB_BYTES && BPB_STRIDE % 128 == 0, "patch slots");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// one box of a 3-D tensor (x, y, frame) -> shared memory; completion bytes are counted on `bar`.  x must be a multiple of 16.
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * DESC_WARPS)
+describe_kernel(OrbGeom g, OrbBuffers b)
+{
+    extern __shared__ uint8_t desc_smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[DESC_WARPS][DESC_ORING + DESC_RING];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ORB_MAX_LEVELS; ++i)
+        if (i < g.nbuilt && (int)blockIdx.x >= g.lv[i].desc_block_off) l = i;
+    const LevelGeom L = g.lv[l];
+    const int32_t *sc = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS;
+    const size_t fslot = (size_t)frame + 1;     // output slot 0 is the tracker's carry
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int total = 0;
+        for (int i = 0; i < g.nbuilt; ++i) total += sc[i];
+        b.counts[fslot] = min(total, g.kp_cap);
+    }
+    const int cnt = sc[l];
+    const int k0 = (((int)blockIdx.x - L.desc_block_off) * DESC_WARPS + warp) * DESC_KPW;
+    int level_base = 0;                         // position of the level's first keypoint in the frame
+    for (int i = 0; i < l; ++i) level_base += sc[i];
+    const int nk = min(DESC_KPW, min(cnt - k0, g.kp_cap - level_base - k0));      // this warp's keypoints
+    if (nk <= 0) return;                        // warps are independent from here on (no CTA-wide barrier below)
+
+    uint8_t *wsm = desc_smem_raw + ((128u - (smem_u32(desc_smem_raw) & 127u)) & 127u) + (size_t)warp * DESC_WARP_SMEM;
+    uint8_t *bp_ring = wsm + DESC_ORING * OPB_STRIDE;
+    const uint32_t obar = smem_u32(&bars[warp][0]), bbar = obar + 8u * DESC_ORING;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < DESC_ORING + DESC_RING; ++r) mbar_init(obar + 8u * r, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane kk < nk: keypoint kk of this warp
+    int x = 0, y = 0, xi = 0, yi = 0;
+    float resp = 0.f, kx = 0.f, ky = 0.f;
+    const uint8_t *tm = reinterpret_cast<const uint8_t *>(b.tmaps) + (size_t)l * 256;
+    if (lane < nk) {
+        const int si = L.sel_off + k0 + lane;
+        const uint32_t xy = b.sel_xy[(size_t)frame * g.kp_cap + si];
+        resp = b.sel_resp[(size_t)frame * g.kp_cap + si];
+        x = (int)(xy & 0xfffu); y = (int)(xy >> 12);
+        // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
+        kx = __fmul_rn((float)x, L.sf); ky = __fmul_rn((float)y, L.sf);
+        xi = __float2int_rn(__fmul_rn(kx, L.inv_sf)); yi = __float2int_rn(__fmul_rn(ky, L.inv_sf));
+        if (lane < DESC_ORING) {
+            mbar_arrive_expect_tx(obar + 8u * lane, OPB_BYTES);
+            tma_load_box(smem_u32(wsm + lane * OPB_STRIDE), tm, (x - 15) & ~15, y - 15, frame, obar + 8u * lane);
+        }
+        if (lane < DESC_RING) {
+            mbar_arrive_expect_tx(bbar + 8u * lane, BPB_BYTES);
+            tma_load_box(smem_u32(bp_ring + lane * BPB_STRIDE), tm + 128, (xi - 19) & ~15, yi - 19, frame, bbar + 8u * lane);
+        }
+    }
+
+    // ---- pass 1: ICAngles moments m10 = sum u*I, m01 = sum v*I over the radius-15 disc.  Lane = (row 4*it + lane/8,
+    // word lane%8) of the patch; its word is re-aligned to the patch's first column (funnel shift of two staged words),
+    // so byte bt is column u = 4*(lane%8) + bt - 15 whatever the keypoint: the weights are per-lane constants.
+    int my_m10 = 0, my_m01 = 0;
+    {
+        uint2 OW[8];                            // (u*mask as s8x4, mask as u8x4) of patch word (row 4*it + lane/8, lane%8)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) OW[it] = __ldg(b.ori_tab + it * 32 + lane);
+        const int vl = (lane >> 3) - 15;
+#pragma unroll 1
+        for (int kk = 0; kk < nk; ++kk) {
+            const int slot = kk % DESC_ORING;
+            const int off = __shfl_sync(0xffffffffu, (x - 15) & 15, kk);           // patch's first column inside the box
+            mbar_wait(obar + 8u * slot, (uint32_t)(kk / DESC_ORING) & 1u);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(wsm + slot * OPB_STRIDE) + (lane >> 3) * (OPB_W / 4) + (lane & 7) + (off >> 2);
+            const uint32_t sh = (uint32_t)(off & 3) * 8u;
+            int m10 = 0, m01 = 0;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const uint32_t px = __funnelshift_r(row[it * 4 * (OPB_W / 4)], row[it * 4 * (OPB_W / 4) + 1], sh);
+                m10 = dp4a_u8_s8(px, OW[it].x, m10);
+                m01 += (vl + 4 * it) * (int)__dp4a(px, OW[it].y, 0u);
+            }
+            __syncwarp();                       // every lane has read this slot
+            if (lane == kk + DESC_ORING && lane < nk) {     // the slot's next tenant is this lane's keypoint
+                mbar_arrive_expect_tx(obar + 8u * slot, OPB_BYTES);
+                tma_load_box(smem_u32(wsm + slot * OPB_STRIDE), tm, (x - 15) & ~15, y - 15, frame, obar + 8u * slot);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            }
+            if (lane == kk) { my_m10 = m10; my_m01 = m01; }
+        }
+    }
+    // orientation and rotation of all keypoints of the warp in one go (lane kk: keypoint kk)
+    const float angle = fast_atan2_deg((float)my_m01, (float)my_m10);
+    float my_ca, my_sa;
+    {
+        const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+        double sd, cd;
+        sincos_0_2pi((double)ang, sd, cd);
+        my_ca = (float)cd; my_sa = (float)sd;
+    }
+    if (lane < nk) {
+        aslam_keypoint kp;
+        kp.x = kx; kp.y = ky; kp.size = L.kp_size; kp.angle = angle; kp.response = resp; kp.octave = l;
+        b.kps[fslot * g.kp_cap + level_base + k0 + lane] = kp;
+    }
+
+    // ---- pass 2: rBRIEF, lane k = descriptor byte k (comparisons 8k .. 8k+7 as (x,y) float pairs in registers)
+    float2 P0[8], P1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 pt = __ldg(b.pattern + j * 32 + lane);        // (x0, y0, x1, y1) of comparison 8*lane + j
+        P0[j] = make_float2(pt.x, pt.y);
+        P1[j] = make_float2(pt.z, pt.w);
+    }
+    uint8_t *dout = b.desc + (fslot * g.kp_cap + level_base + k0) * 32 + lane;
+#pragma unroll 1
+    for (int kk = 0; kk < nk; ++kk) {
+        const int slot = kk % DESC_RING;
+        const float ca = __shfl_sync(0xffffffffu, my_ca, kk), sa = __shfl_sync(0xffffffffu, my_sa, kk);
+        const int off = __shfl_sync(0xffffffffu, (xi - 19) & 15, kk);              // patch's first column inside the box
+        mbar_wait(bbar + 8u * slot, (uint32_t)(kk / DESC_RING) & 1u);
+        // Rotation: (px*ca, py*ca) and (px*sa, py*sa) by FMUL2, then the two exactly rounded sums
+        //   X = px*ca - py*sa,  Y = px*sa + py*ca   as OpenCV's unfused expression evaluates them.
+        // cvRound by the 1.5*2^23 trick: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v); the constant
+        // is folded into the patch base: byte = (iy + 19) * 64 + off + 19 + ix (the box starts at row yi - 19).
+        // (32-bit shared-window address: the subtraction wraps and the additions below wrap back)
+        const float2 CC = make_float2(ca, ca), SS = make_float2(sa, sa), MG = make_float2(12582912.0f, 12582912.0f);
+        const uint32_t pb = smem_u32(bp_ring + slot * BPB_STRIDE) + (uint32_t)(19 * BPB_W + 19 + off) - 0x4B400000u * (uint32_t)(BPB_W + 1);
+        uint32_t byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 a1 = __fmul2_rn(P0[j], CC), a2 = __fmul2_rn(P0[j], SS);
+            const float2 c1 = __fmul2_rn(P1[j], CC), c2 = __fmul2_rn(P1[j], SS);
+            const float2 r0 = __fadd2_rn(make_float2(__fsub_rn(a1.x, a2.y), __fadd_rn(a2.x, a1.y)), MG);
+            const float2 r1 = __fadd2_rn(make_float2(__fsub_rn(c1.x, c2.y), __fadd_rn(c2.x, c1.y)), MG);
+            const uint32_t t0 = lds_u8(pb + __float_as_uint(r0.y) * (uint32_t)BPB_W + __float_as_uint(r0.x));
+            const uint32_t t1 = lds_u8(pb + __float_as_uint(r1.y) * (uint32_t)BPB_W + __float_as_uint(r1.x));
+            byte |= (uint32_t)(t0 < t1) << j;
+        }
+        dout[(size_t)kk * 32] = (uint8_t)byte;
+        __syncwarp();                           // every lane has read this slot
+        if (lane == kk + DESC_RING && lane < nk) {      // the slot's next tenant is this lane's keypoint
+            mbar_arrive_expect_tx(bbar + 8u * slot, BPB_BYTES);
+            tma_load_box(smem_u32(bp_ring + slot * BPB_STRIDE), tm + 128, (xi - 19) & ~15, yi - 19, frame, bbar + 8u * slot);
+        }
+    }
+}
+
+int launch_describe(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
+{
+    if (g.desc_blocks_per_frame == 0) {
+        ASLAM_CUDA(cudaMemsetAsync(b.counts + 1, 0, sizeof(int32_t) * nframes, ctx->stream));
+        return ASLAM_OK;
+    }
+    if (!b.tmaps) return fail(ASLAM_E_STATE, "describe_kernel: the handle has no TMA descriptors");
+    if (!ctx->desc_attr_set) {                  // per device, once
+        ASLAM_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DESC_SMEM_BYTES));
+        ctx->desc_attr_set = true;
+    }
+    dim3 grid(g.desc_blocks_per_frame, nframes);
+    ProfScope ps(ctx, PK_DESCRIBE);
+    describe_kernel<<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, ctx->stream>>>(g, b);
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+#endif      // ASLAM_DESC_TMA
 
 // ------------------------------------------------------------------ dynamic-object filter (a4)
 // src/main.cpp:29-50 DYNAMIC_CLASSES {0,1,2,3,5,6,7,14,15,16}; Detection::contains is closed on

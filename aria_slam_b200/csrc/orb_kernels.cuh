@@ -29,6 +29,9 @@ struct OrbBuffers {
     int32_t *overflow;     // [B+1]
     const uint2 *ori_tab;      // [8][32]: (u*mask as s8x4, mask as u8x4) of patch word (row 4*it + lane/8, lane%8)
     const float4 *pattern;     // 256 x (x0, y0, x1, y1): entry j*32 + k = comparison 8*k + j
+    // TMA descriptors (CUtensorMap, 128 B each) of every level as a 3-D u8 tensor (x, y, frame): entry 2*l = the level
+    // in `pyr` with a 48 x 31 box (orientation patch), entry 2*l + 1 = the level in `blur` with a 64 x 39 box (rBRIEF patch)
+    const void *tmaps;
 };
 
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask);
