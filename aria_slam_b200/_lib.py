@@ -50,7 +50,9 @@ SYMBOLS = {
     "aslam_prof_name": (C.c_char_p, [C.c_int]),
     "aslam_prof_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "aslam_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "aslam_host_alloc_wc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "aslam_host_free": (C.c_int, [_P]),
+    "aslam_memcpy_async": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "aslam_orb_default_params": (None, [C.POINTER(OrbParams)]),
     "aslam_orb_create": (C.c_int, [_P, C.POINTER(OrbParams), C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "aslam_orb_destroy": (None, [_P]),
@@ -90,7 +92,7 @@ SYMBOLS = {
     "aslam_loopdb_query_global_device": (C.c_int, [_P, _P, C.c_int, _P]),
     "aslam_loopdb_query_global_push_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int]),
     "aslam_loopdb_query_global_exchange_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_uint64, _P]),
-    "aslam_loopdb_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), _P, C.c_int]),
+    "aslam_loopdb_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), _P, C.c_int, C.c_int]),
     "aslam_loopdb_capacity_rows": (C.c_int64, [_P]),
     "aslam_loopdb_query_segmented_device": (C.c_int, [_P, _P, C.c_int, C.c_double, _P]),
     "aslam_loopdb_match_keyframe": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_double, _P, C.POINTER(C.c_int)]),

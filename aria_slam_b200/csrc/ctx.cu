@@ -160,6 +160,21 @@ int aslam_host_alloc(size_t bytes, void **out)
     return ASLAM_OK;
 }
 
+int aslam_host_alloc_wc(size_t bytes, void **out)
+{
+    ASLAM_REQUIRE(out, "out is NULL");
+    ASLAM_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocWriteCombined));
+    return ASLAM_OK;
+}
+
+int aslam_memcpy_async(aslam_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    ASLAM_REQUIRE(ctx && (bytes == 0 || (dst && src)), "NULL argument");
+    ASLAM_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) ASLAM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return ASLAM_OK;
+}
+
 int aslam_host_free(void *p)
 {
     if (p) ASLAM_CUDA(cudaFreeHost(p));

@@ -133,17 +133,20 @@ static RowMap db_row_map(const aslam_loopdb *db)
     return m;
 }
 
-// One problem per stored keyframe: the query set against that keyframe's rows.
+// `splits` problems per stored keyframe: the query set against row range j of that keyframe's rows (the scan merges the
+// ranges of a keyframe into one slot per query, so short keyframe lists still fill the GPU).
 __global__ void fill_segment_problems_kernel(KnnProblem *probs, const uint8_t *q, const uint8_t *rows_at_head,
-                                             const int *__restrict__ lstart, int nseg, int nq)
+                                             const int *__restrict__ lstart, int nseg, int nq, int splits)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg * splits) return;
+    const int s = i / splits, j = i - s * splits;
     KnnProblem P;
     P.q = q; P.t = rows_at_head + (size_t)lstart[s] * 32;
     P.nq_dev = nullptr; P.nt_dev = nullptr; P.nq = nq; P.nt = lstart[s + 1] - lstart[s];
-    P.t_lo = 0; P.t_hi = P.nt;
-    probs[s] = P;
+    const int per = (P.nt + splits - 1) / splits;
+    P.t_lo = min(j * per, P.nt); P.t_hi = min((j + 1) * per, P.nt);
+    probs[i] = P;
 }
 
 static void db_evict_oldest(aslam_loopdb *db)
@@ -225,20 +228,24 @@ static int db_query_segmented_device(aslam_loopdb *db, const uint8_t *d_q, int n
     aslam_ctx *ctx = db->ctx;
     const int nseg = (int)db->segs.size();
     const int q_stride = (int)align_up((size_t)nq, 64);
-    int rc = db_reserve(db, 0, nseg, (size_t)nseg * q_stride);
+    // keyframes are cut into row ranges until the grid fills the GPU (8 GPUs x 63 keyframes x 4 query blocks would
+    // otherwise leave almost half of the resident CTA slots empty)
+    const int64_t rows = db->tail - db->head;
+    const int splits = choose_splits(ctx, nq, rows / nseg > 0 ? rows / nseg : 1, nseg);
+    int rc = db_reserve(db, 0, nseg * splits, (size_t)nseg * q_stride);
     if (rc) return rc;
     if ((rc = db_sync_map(db))) return rc;
     db->tab_splits = 0; db->armed = false;      // the flat query's table and preset slots are overwritten here
     {
         ProfScope ps(ctx, PK_MISC);
-        fill_segment_problems_kernel<<<(nseg + 127) / 128, 128, 0, ctx->stream>>>(db->d_probs, d_q, db->d_rows + db->head * 32,
-                                                                                   db->d_lstart, nseg, nq);
+        fill_segment_problems_kernel<<<(nseg * splits + 127) / 128, 128, 0, ctx->stream>>>(db->d_probs, d_q, db->d_rows + db->head * 32,
+                                                                                            db->d_lstart, nseg, nq, splits);
         ASLAM_LAUNCH_CHECK();
     }
-    rc = launch_knn2_partial(ctx, db->d_probs, nseg, nq, db->d_partial, q_stride);
+    rc = launch_knn2_partial(ctx, db->d_probs, nseg * splits, nq, db->d_partial, q_stride, splits);
     if (rc) return rc;
     RatioTest rt; rt.ratio = ratio; rt.as_double = 1; rt.disabled = ratio < 0;
-    return launch_knn2_finish_counts(ctx, db->d_probs, db->d_partial, nseg, q_stride, rt, d_good);
+    return launch_knn2_finish_counts(ctx, db->d_probs, db->d_partial, nseg, splits, q_stride, rt, d_good);
 }
 
 // Shared body of the flat query: scan this shard, then write d_top2, push to the peers, or run the fused exchange.
@@ -269,10 +276,10 @@ static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_
             if (!db->d_arrive) {
                 ASLAM_CUDA(cudaMalloc(&db->d_arrive, sizeof(unsigned int) * KNN_FUSED_MAX_QBLOCKS));
                 ASLAM_CUDA(cudaMalloc(&db->d_status, sizeof(unsigned int)));
-                ASLAM_CUDA(cudaMalloc(&db->d_stamps, sizeof(unsigned long long) * 2 * KNN_FUSED_MAX_QBLOCKS));
+                ASLAM_CUDA(cudaMalloc(&db->d_stamps, sizeof(unsigned long long) * 4 * KNN_FUSED_MAX_QBLOCKS));
                 ASLAM_CUDA(cudaMemsetAsync(db->d_arrive, 0, sizeof(unsigned int) * KNN_FUSED_MAX_QBLOCKS, ctx->stream));
                 ASLAM_CUDA(cudaMemsetAsync(db->d_status, 0, sizeof(unsigned int), ctx->stream));
-                ASLAM_CUDA(cudaMemsetAsync(db->d_stamps, 0, sizeof(unsigned long long) * 2 * KNN_FUSED_MAX_QBLOCKS, ctx->stream));
+                ASLAM_CUDA(cudaMemsetAsync(db->d_stamps, 0, sizeof(unsigned long long) * 4 * KNN_FUSED_MAX_QBLOCKS, ctx->stream));
             }
             if (!armed) ASLAM_CUDA(cudaMemsetAsync(db->d_partial, 0xff, sizeof(uint2) * (size_t)q_stride, ctx->stream));
             ExchangeArgs X;
@@ -518,7 +525,7 @@ int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d
     return db_query_global(db, d_q, nq, d_out, d_peer_bufs, nparts, my_part, round);
 }
 
-int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *stamps, int nqblocks)
+int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *stamps, int nqblocks, int reset)
 {
     ASLAM_REQUIRE(db && status, "NULL argument");
     ASLAM_REQUIRE(nqblocks >= 0 && nqblocks <= KNN_FUSED_MAX_QBLOCKS, "at most 64 query blocks");
@@ -527,7 +534,8 @@ int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *s
     ASLAM_CUDA(cudaSetDevice(db->ctx->device));
     ASLAM_CUDA(cudaStreamSynchronize(db->ctx->stream));
     ASLAM_CUDA(cudaMemcpy(status, db->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (stamps && nqblocks) ASLAM_CUDA(cudaMemcpy(stamps, db->d_stamps, sizeof(uint64_t) * 2 * (size_t)nqblocks, cudaMemcpyDeviceToHost));
+    if (stamps && nqblocks) ASLAM_CUDA(cudaMemcpy(stamps, db->d_stamps, sizeof(uint64_t) * 4 * (size_t)nqblocks, cudaMemcpyDeviceToHost));
+    if (reset) ASLAM_CUDA(cudaMemset(db->d_stamps, 0, sizeof(uint64_t) * 4 * KNN_FUSED_MAX_QBLOCKS));
     return ASLAM_OK;
 }
 

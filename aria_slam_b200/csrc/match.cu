@@ -263,7 +263,11 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *partial, int
         }
     }
     __syncthreads();
-    if (tid == 0 && X.stamps) { X.stamps[2 * blockIdx.x] = t_push; X.stamps[2 * blockIdx.x + 1] = global_timer_ns(); }
+    if (tid == 0 && X.stamps) {               // per query block: last push, last all-seen, sum of waits, exchanges
+        const unsigned long long t_seen = global_timer_ns();
+        unsigned long long *st = X.stamps + 4 * blockIdx.x;
+        st[0] = t_push; st[1] = t_seen; st[2] += t_seen - t_push; st[3] += 1;
+    }
 #pragma unroll
     for (int j = 0; j < KNN_RQ; ++j) {
         const int qi = qbase + j * KNN_THREADS + tid;
@@ -370,11 +374,11 @@ knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__
 
 __global__ void __launch_bounds__(FIN_THREADS)
 knn2_finish_counts_kernel(const KnnProblem *__restrict__ probs, const uint2 *__restrict__ partial,
-                          int q_stride, RatioTest rt, int32_t *__restrict__ good)
+                          int splits, int q_stride, RatioTest rt, int32_t *__restrict__ good)
 {
     __shared__ int warp_sums[FIN_THREADS / 32];
     const int s = blockIdx.x;
-    const KnnProblem P = probs[s];
+    const KnnProblem P = probs[s * splits];
     const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
     int cnt = 0;
     for (int q = threadIdx.x; q < nq; q += FIN_THREADS) {
@@ -521,11 +525,11 @@ int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const 
 }
 
 int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
-                              int nslots, int q_stride, RatioTest rt, int32_t *d_good)
+                              int nslots, int splits, int q_stride, RatioTest rt, int32_t *d_good)
 {
     if (nslots <= 0) return ASLAM_OK;
     ProfScope ps(ctx, PK_KNN_FINISH);
-    knn2_finish_counts_kernel<<<nslots, FIN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, rt, d_good);
+    knn2_finish_counts_kernel<<<nslots, FIN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, splits, q_stride, rt, d_good);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

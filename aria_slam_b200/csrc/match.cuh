@@ -75,9 +75,10 @@ int launch_knn2_finish_matches(aslam_ctx *ctx, const KnnProblem *d_probs, const 
                                aslam_match *d_out, int out_stride, int32_t *d_nout,
                                int32_t *d_raw_idx, int32_t *d_raw_dist, const DynFilter &filter = DynFilter());
 
-// One count per slot: queries passing the ratio test within that slot alone.
+// One count per slot: queries passing the ratio test within that slot alone.  Slot s was merged from the `splits`
+// consecutive problems s*splits .. (launch_knn2_partial with merge_div = splits; 1 = one problem per slot).
 int launch_knn2_finish_counts(aslam_ctx *ctx, const KnnProblem *d_probs, const uint2 *d_partial,
-                              int nslots, int q_stride, RatioTest rt, int32_t *d_good);
+                              int nslots, int splits, int q_stride, RatioTest rt, int32_t *d_good);
 
 // All slots merged into one top-2 per query, as 64-bit keys (distance << 40 | row_base + row
 // + slot_row_offset), where slot rows are relative to the problem's t base and row_base is
@@ -100,7 +101,7 @@ struct ExchangeArgs {
     unsigned long long round = 0;
     unsigned int *arrive = nullptr;        // [qblocks] CTA arrival counters, zero between launches
     unsigned long long *out = nullptr;     // [nq][2] merged keys
-    unsigned long long *stamps = nullptr;  // [qblocks][2] %globaltimer when the block was pushed / when all peers' flags were seen
+    unsigned long long *stamps = nullptr;  // [qblocks][4]: %globaltimer of the last push / last all-peers-seen, sum of (seen - push), exchanges
     unsigned int *status = nullptr;        // bit 0: a wait for a peer's flag timed out (the result is then invalid)
     RowMap map;
 };

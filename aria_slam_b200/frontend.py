@@ -287,12 +287,21 @@ class LoopDB:
         check(lib().aslam_loopdb_query_global(self.h, ptr(q), len(q), ptr(top2)))
         return unpack_top2(top2)
 
-    def exchange_status(self, nqblocks=0):
-        """(status word, stamps[nqblocks,2] of %globaltimer ns: pushed / all peers seen) of the last fused exchange."""
+    def exchange_status(self, nqblocks=0, reset=False):
+        """(status word, stamps[nqblocks, 4]) of the fused exchange: per query block the %globaltimer ns of the last push and
+        of the last all-peers-seen, the sum of (seen - push) since the last reset, and the number of exchanges."""
         st = C.c_uint32(0)
-        stamps = np.zeros((max(nqblocks, 1), 2), np.uint64)
-        check(lib().aslam_loopdb_exchange_status(self.h, C.byref(st), ptr(stamps), int(nqblocks)))
+        stamps = np.zeros((max(nqblocks, 1), 4), np.uint64)
+        check(lib().aslam_loopdb_exchange_status(self.h, C.byref(st), ptr(stamps), int(nqblocks), 1 if reset else 0))
         return st.value, stamps[:nqblocks]
+
+    def mean_exchange_wait_us(self, nqblocks):
+        """Mean time per exchange this rank waited for its slowest peer (worst query block), since the last reset."""
+        st, stamps = self.exchange_status(nqblocks)
+        if st != 0:
+            return -1.0
+        n = stamps[:, 3].astype(np.float64)
+        return float((stamps[:, 2].astype(np.float64) / np.maximum(n, 1)).max()) / 1e3
 
     # one process per GPU: peers' exchange buffers through CUDA IPC (aslam_loopdb_shard_export / _init)
     def shard_export(self, nranks, max_nq):

@@ -55,41 +55,74 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml
+pynvml.nvmlInit()
+h = pynvml.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+period = float(sys.argv[2])
+reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+print("max", pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        print(repr(time.time()), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(reasons(h)), flush=True)
+    except Exception:
+        pass
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML from a thread every few milliseconds while the timed
-    regions run (the regions last tens of milliseconds: an nvidia-smi process would return a handful of
-    samples at best); falls back to the recipe's nvidia-smi line when NVML is not importable."""
+    """SM clock and throttle reasons sampled through NVML every 2 ms while the timed regions run.  The sampler is a
+    separate PROCESS (a thread in this interpreter competes with the launching thread for the GIL and, at N = 8, made
+    rank 0 the straggler every other rank's exchange waited for); its samples carry wall-clock stamps and are matched
+    to the timed regions afterwards.  Falls back to the recipe's nvidia-smi line when pynvml is not importable."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index, period_s=0.004):
+    def __init__(self, index, period_s=0.002):
         self.index, self.period, self.rows, self.max_mhz = index, period_s, [], None
-        self.timed = False                  # set by the bench around its timed regions
-        self._stop = threading.Event()
-        self._thread = self.proc = None
+        self.windows, self._t0 = [], None      # wall-clock windows of the timed regions
+        self.proc, self.source = None, None
+
+    @property
+    def timed(self):
+        return self._t0 is not None
+
+    @timed.setter
+    def timed(self, on):
+        if on and self._t0 is None:
+            self._t0 = time.time()
+        elif not on and self._t0 is not None:
+            self.windows.append((self._t0, time.time()))
+            self._t0 = None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-
-            def loop():
-                while not self._stop.is_set():
-                    try:
-                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                        why = reasons(h)
-                        self.rows.append((self.timed, float(mhz), int(why)))
-                    except Exception:
-                        pass
-                    self._stop.wait(self.period)
-
-            self._thread = threading.Thread(target=loop, daemon=True)
-            self._thread.start()
+            import pynvml  # noqa: F401  (only to know the subprocess can import it)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index), str(self.period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvml (separate process)"
         except Exception:
             self._start_smi()
+        if self.proc:
+            threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:        # blocks in read(): the GIL is released while waiting
+            c = line.split()
+            try:
+                if c[0] == "max":
+                    self.max_mhz = float(c[1])
+                elif self.source.startswith("nvml"):
+                    self.rows.append((float(c[0]), float(c[1]), int(c[2])))
+                else:
+                    c = [x.strip() for x in line.split(",")]
+                    self.max_mhz = float(c[1])
+                    why = sum(bit for (_, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
+                    self.rows.append((time.time(), float(c[0]), why))
+            except (ValueError, IndexError):
+                pass
 
     def _start_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -97,33 +130,23 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-
-            def read():
-                for line in self.proc.stdout:
-                    c = [x.strip() for x in line.split(",")]
-                    if len(c) >= 6 and c[0].replace(".", "").isdigit():
-                        self.max_mhz = float(c[1]) if c[1].replace(".", "").isdigit() else self.max_mhz
-                        why = sum(bit for (_, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
-                        self.rows.append((self.timed, float(c[0]), why))
-
-            threading.Thread(target=read, daemon=True).start()
+            self.source = "nvidia-smi"
         except OSError:
             self.proc = None
 
     def stop(self):
-        self._stop.set()
-        if self._thread:
-            self._thread.join(timeout=1.0)
+        self.timed = False
         if self.proc:
             self.proc.terminate()
-        timed = [r for r in self.rows if r[0]] or self.rows
+        rows = list(self.rows)
+        timed = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)] or rows
         sm = [r[1] for r in timed]
         bits = 0
         for r in timed:
             bits |= r[2]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(name for name, bit in self.REASONS if bits & bit),
-                "samples": len(sm), "samples_total": len(self.rows), "source": "nvml" if self._thread else "nvidia-smi"}
+                "samples": len(sm), "samples_total": len(rows), "timed_windows": len(self.windows), "source": self.source}
 
 
 def measured_peaks():
@@ -478,11 +501,13 @@ def run_ours(args):
     q, src = synth.loop_queries(db, LOOP_NQ, 6)
     nqb = (LOOP_NQ + 511) // 512
 
-    def timed_loop(fn, steps):
+    def timed_loop(fn, steps, reset=None):
         """K calls of fn() back to back on `stream`, CUDA events, max over ranks -> ms per call."""
         for _ in range(Wm):
             fn()
         barrier()
+        if reset:
+            reset()
         t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0_.record(stream)
         for _ in range(steps):
@@ -501,15 +526,14 @@ def run_ours(args):
         # flat query, device-resident
         launches1 = kernel_launches()
         ctx.prof_enable(True); ctx.prof_read(reset=True)
-        loop_ms = timed_loop(lambda: lq.query(d_q, LOOP_NQ), K)
+        clocks.timed = True
+        loop_ms = timed_loop(lambda: lq.query(d_q, LOOP_NQ), K, reset=lambda: lq.db.exchange_status(0, reset=True) if lq.exchange in ("ipc", "fused") else None)
+        clocks.timed = False
         loop_launches = (kernel_launches() - launches1) * K // (K + Wm)
         loop_prof = {k: (v[0] * K / (K + Wm), v[1] * K // (K + Wm)) for k, v in ctx.prof_read(reset=True).items()}
         ctx.prof_enable(False)
+        wait_us = lq.db.mean_exchange_wait_us(nqb) if lq.exchange in ("ipc", "fused") else None     # mean over the K timed queries
         top2 = lq.query(d_q, LOOP_NQ)
-        wait_us = None
-        if lq.exchange in ("ipc", "fused"):
-            st_, stamps = lq.db.exchange_status(nqb)
-            wait_us = float((stamps[:, 1].astype(np.int64) - stamps[:, 0].astype(np.int64)).max()) / 1e3 if st_ == 0 else -1.0
         # flat query end to end: pinned host queries in (64 KB), merged top-2 out to pinned host memory (32 KB)
         d_q2 = torch.empty_like(d_q)
 
@@ -658,7 +682,7 @@ def run_ours(args):
                      "bound": "int_pipe(popc)", "achieved": ach, "peak": popc_peak, "unit": "Gpopc32/s executed per GPU", "frac": ach / popc_peak,
                      "frac_algorithmic": POPC_ALGORITHMIC / POPC_EXECUTED * ach / popc_peak, "ms": scan_ms,
                      "peak_source": "aslam_microbench(POPC) on this GPU",
-                     "note": "at N > 1 the fused kernel's duration includes the wait for the slowest peer (wait_for_slowest_peer_us)"}
+                     "note": "at N > 1 the fused kernel's duration includes the wait for the slowest peer (mean_wait_for_slowest_peer_us_per_rank)"}
 
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -682,7 +706,7 @@ def run_ours(args):
                                       "fused": "as ipc, over buffers from torch symmetric memory",
                                       "push": "P2P stores from the finish kernel + symmetric-memory barriers + merge kernel",
                                       "nccl": "NCCL all_gather of 2000x2 packed (dist,row) keys per rank + merge kernel"}[lq.exchange],
-                       "exchange": lq.exchange, "wait_for_slowest_peer_us_per_rank": waits,
+                       "exchange": lq.exchange, "mean_wait_for_slowest_peer_us_per_rank": waits,
                        "best_row_is_source_row": loop_ok, "checks": loop_checks, "gpu_launches_per_query": loop_launches / K,
                        "stages_ms": {k: v[0] / K for k, v in loop_prof.items() if v[1]},
                        "pairs_per_s": LOOP_NQ * float(LOOP_DB_ROWS) / (loop_ms * 1e-3),

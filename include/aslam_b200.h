@@ -108,7 +108,12 @@ ASLAM_API const char *aslam_prof_name(int kind);
 ASLAM_API int aslam_prof_read(aslam_ctx *ctx, int kind, double *total_ms, int64_t *launches, int reset);
 /* pinned host memory for callers that want truly asynchronous H2D/D2H */
 ASLAM_API int aslam_host_alloc(size_t bytes, void **out);
+/* The same as write-combined memory (cudaHostAllocWriteCombined): for buffers the host only WRITES (frames on their
+ * way to the device); not snooped during the transfer, but very slow for the host to read back. */
+ASLAM_API int aslam_host_alloc_wc(size_t bytes, void **out);
 ASLAM_API int aslam_host_free(void *p);
+/* cudaMemcpyAsync(cudaMemcpyDefault) on the context's stream, for hosts that do not link the CUDA runtime themselves. */
+ASLAM_API int aslam_memcpy_async(aslam_ctx *ctx, void *dst, const void *src, size_t bytes);
 
 /* ------------------------------------------------------------------ ORB extraction
  * Replaces OrbCudaExtractor::extract / extractAsync / sync / setMaxFeatures / getMaxFeatures
@@ -296,10 +301,11 @@ ASLAM_API int aslam_loopdb_query_global_push_device(aslam_loopdb *db, const uint
 ASLAM_API int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
                                                         uint64_t *const *d_peer_bufs, int nparts, int my_part,
                                                         uint64_t round, uint64_t *d_out);
-/* Waits for the stream; *status = 0 when no exchange on this database ever timed out.  stamps (may be NULL):
- * per query block of the last exchange, %globaltimer (ns) when the block was pushed to the peers and when all peers'
- * flags had been seen -- the difference is how long this rank waited for the slowest peer. */
-ASLAM_API int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *stamps, int nqblocks);
+/* Waits for the stream; *status = 0 when no exchange on this database ever timed out.  stamps (may be NULL) receives
+ * 4 words per query block: %globaltimer (ns) of the last exchange's push to the peers and of the moment all peers'
+ * flags had been seen, the SUM of (seen - push) over all exchanges since the last reset -- the time this rank spent
+ * waiting for its slowest peer -- and the number of exchanges.  reset != 0 clears the sums. */
+ASLAM_API int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *stamps, int nqblocks, int reset);
 ASLAM_API size_t aslam_loop_exchange_buffer_bytes(int nparts, int nq);
 /* Host-buffer form of the flat query (copies in and out, synchronous). */
 ASLAM_API int aslam_loopdb_query_global(aslam_loopdb *db, const uint8_t *q, int nq, uint64_t *top2);

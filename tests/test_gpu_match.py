@@ -388,7 +388,7 @@ def test_fused_scan_exchange_with_one_shard_equals_the_plain_query(ctx, oracle):
             if rnd == 2:
                 db.query_segmented(q[:50], 0.7)            # overwrites the armed slots and the row-range table
         st, stamps = db.exchange_status((nq + 511) // 512)
-        assert st == 0 and (stamps[:, 1] >= stamps[:, 0]).all() and (stamps[:, 0] > 0).all()
+        assert st == 0 and (stamps[:, 1] >= stamps[:, 0]).all() and (stamps[:, 0] > 0).all() and (stamps[:, 3] == 3).all()
     db.close()
 
 

@@ -27,5 +27,23 @@ for rows in [int(a) for a in sys.argv[1:]] or [1_000_000, 125_000]:
     pr = {k: round(v[0] / K, 4) for k, v in ctx.prof_read(reset=True).items() if v[1]}
     ctx.prof_enable(False)
     out[rows] = {"ms": round(dt, 4), **pr}
+    # the fused scan + exchange kernel with this GPU as its only peer (what every rank of an N-GPU run launches)
+    from aria_slam_b200._lib import lib
+    words = lib().aslam_loop_exchange_buffer_bytes(1, 2000) // 8
+    buf = torch.zeros(words, dtype=torch.int64, device="cuda")
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    rnd = 0
+    for _ in range(3):
+        rnd += 1; ldb.query_global_exchange_device(dq, 2000, ptrs, 1, 0, rnd, top)
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.ExternalStream(ctx.stream)
+    e0.record(st)
+    for _ in range(K):
+        rnd += 1; ldb.query_global_exchange_device(dq, 2000, ptrs, 1, 0, rnd, top)
+    e1.record(st)
+    ctx.sync()
+    out[rows]["fused_ms"] = round(e0.elapsed_time(e1) / K, 4)
     ldb.close()
 print(json.dumps(out))

@@ -44,6 +44,8 @@ with torch.cuda.stream(stream):
         for _ in range(3):
             out = lq.query(dq, NQ)
         torch.cuda.synchronize(); dist.barrier()
+        if lq.exchange in ("ipc", "fused"):
+            lq.db.exchange_status(0, reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -61,13 +63,13 @@ with torch.cuda.stream(stream):
         if ref_keys is not None:
             ent["every_rank_equals_oracle_full_keys"] = all_ranks((keys == ref_keys).all())
         if lq.exchange in ("ipc", "fused"):
-            st, stamps = lq.db.exchange_status((NQ + 511) // 512)
-            wait_us = float((stamps[:, 1].astype(np.int64) - stamps[:, 0].astype(np.int64)).max()) / 1e3
+            st = lq.db.exchange_status(0)[0]
+            wait_us = lq.db.mean_exchange_wait_us((NQ + 511) // 512)
             w = torch.tensor([wait_us], dtype=torch.float64, device="cuda")
             allw = torch.empty(world, dtype=torch.float64, device="cuda")
             dist.all_gather_into_tensor(allw, w)
             ent["status"] = st
-            ent["wait_for_slowest_peer_us_per_rank"] = [round(x, 1) for x in allw.cpu().tolist()]
+            ent["mean_wait_for_slowest_peer_us_per_rank"] = [round(x, 1) for x in allw.cpu().tolist()]
         # the per-keyframe (reference-semantics) query, sharded: counts all-gathered
         for _ in range(2):
             good = lq.query_segmented(dq, NQ)
