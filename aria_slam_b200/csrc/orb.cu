@@ -24,6 +24,7 @@ struct aslam_orb {
     OrbGeom g{};
     OrbBuffers b{};
     uint32_t *d_tabs = nullptr;
+    uint32_t *d_tile_tab = nullptr;
     float4 *d_pattern = nullptr;
     uint2 *d_ori_tab = nullptr;
     void *d_tmaps = nullptr;               // [ORB_MAX_LEVELS][2] CUtensorMap: (pyr, 48 x 31 box), (blur, 64 x 39 box)
@@ -53,7 +54,7 @@ static void orb_free_buffers(aslam_orb *o)
     cudaFree(o->b.pyr); cudaFree(o->b.blur); cudaFree(o->b.mask); cudaFree(o->b.cand); cudaFree(o->b.cand_cnt);
     cudaFree(o->b.tile_base); cudaFree(o->b.surv); cudaFree(o->b.hresp); cudaFree(o->b.rank); cudaFree(o->b.sel_xy);
     cudaFree(o->b.sel_resp); cudaFree(o->b.sel_cnt); cudaFree(o->b.kps); cudaFree(o->b.desc);
-    cudaFree(o->b.counts); cudaFree(o->b.overflow); cudaFree(o->d_tabs);
+    cudaFree(o->b.counts); cudaFree(o->b.overflow); cudaFree(o->d_tabs); cudaFree(o->d_tile_tab);
     cudaFree(o->d_matches); cudaFree(o->d_match_counts); cudaFree(o->d_probs); cudaFree(o->d_partial);
     cudaFree(o->d_tmp_kps); cudaFree(o->d_tmp_desc);
     cudaFree(o->d_retained[0]); cudaFree(o->d_retained[1]);
@@ -61,7 +62,7 @@ static void orb_free_buffers(aslam_orb *o)
     o->d_retained[0] = o->d_retained[1] = nullptr; o->last_count = -1;
     if (o->h_counts) cudaFreeHost(o->h_counts);
     o->b = OrbBuffers();
-    o->d_tabs = nullptr; o->d_matches = nullptr; o->d_match_counts = nullptr; o->d_probs = nullptr;
+    o->d_tabs = nullptr; o->d_tile_tab = nullptr; o->d_matches = nullptr; o->d_match_counts = nullptr; o->d_probs = nullptr;
     o->d_partial = nullptr; o->d_tmp_kps = nullptr; o->d_tmp_desc = nullptr; o->h_counts = nullptr;
 }
 
@@ -156,6 +157,16 @@ static int orb_plan(aslam_orb *o)
     if (!tabs.empty())
         ASLAM_CUDA(cudaMemcpyAsync(o->d_tabs, tabs.data(), sizeof(uint32_t) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
     b.tabs = o->d_tabs;
+    {
+        std::vector<uint32_t> tt(tiles, 0u);
+        for (int l = 0; l < g.nbuilt; ++l)
+            for (int t = 0; t < g.lv[l].tiles_x * g.lv[l].tiles_y; ++t)
+                tt[(size_t)g.lv[l].tile_off + t] = (uint32_t)l | ((uint32_t)(t % g.lv[l].tiles_x) << 4) | ((uint32_t)(t / g.lv[l].tiles_x) << 16);
+        ASLAM_CUDA(cudaMalloc(&o->d_tile_tab, sizeof(uint32_t) * tiles));
+        ASLAM_CUDA(cudaMemcpyAsync(o->d_tile_tab, tt.data(), sizeof(uint32_t) * tiles, cudaMemcpyHostToDevice, ctx->stream));
+        ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));      // tt is a local
+        b.tile_tab = o->d_tile_tab;
+    }
     b.pattern = o->d_pattern;
     b.ori_tab = o->d_ori_tab;
     {

@@ -265,13 +265,11 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
 #endif
 
     const int tile = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < ORB_MAX_LEVELS; ++i)
-        if (i < g.nbuilt && tile >= g.lv[i].tile_off) l = i;
+    // tile -> (level, tx, ty) from a table built on the host (level | tx << 4 | ty << 16) instead of an 8-way level search
+    // and an integer division per CTA: 0.845 -> 0.832 ms in the A/B of round 2
+    const uint32_t tt = __ldg(b.tile_tab + tile);
+    const int l = (int)(tt & 15u), tx = (int)((tt >> 4) & 0xfffu), ty = (int)(tt >> 16);
     const LevelGeom L = g.lv[l];
-    const int tl = tile - L.tile_off;
-    const int ty = tl / L.tiles_x, tx = tl - ty * L.tiles_x;
     const int sx0 = ((g.edge - 1) & ~1) + tx * FT_OUT_W, sy0 = g.edge - 1 + ty * FT_OUT_H;
     const int gx0 = (sx0 - 3) & ~3;          // first staged column (aligned), staged row 0 is y = sy0-3
     const int g0 = sx0 - gx0;                // 4 or 6

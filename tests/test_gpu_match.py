@@ -380,6 +380,7 @@ def test_fused_scan_exchange_with_one_shard_equals_the_plain_query(ctx, oracle):
         dq = torch.from_numpy(q).cuda()
         out = torch.zeros((nq, 2), dtype=torch.int64, device="cuda")
         torch.cuda.synchronize()
+        db.exchange_status(0, reset=True)
         for rnd in (1, 2, 3):
             out.zero_(); torch.cuda.synchronize()
             db.query_global_exchange_device(dq, nq, ptrs, 1, 0, rnd, out)
