@@ -158,14 +158,23 @@ static int orb_plan(aslam_orb *o)
         ASLAM_CUDA(cudaMemcpyAsync(o->d_tabs, tabs.data(), sizeof(uint32_t) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
     b.tabs = o->d_tabs;
     {
-        std::vector<uint32_t> tt(tiles, 0u);
-        for (int l = 0; l < g.nbuilt; ++l)
-            for (int t = 0; t < g.lv[l].tiles_x * g.lv[l].tiles_y; ++t)
-                tt[(size_t)g.lv[l].tile_off + t] = (uint32_t)l | ((uint32_t)(t % g.lv[l].tiles_x) << 4) | ((uint32_t)(t / g.lv[l].tiles_x) << 16);
-        ASLAM_CUDA(cudaMalloc(&o->d_tile_tab, sizeof(uint32_t) * tiles));
-        ASLAM_CUDA(cudaMemcpyAsync(o->d_tile_tab, tt.data(), sizeof(uint32_t) * tiles, cudaMemcpyHostToDevice, ctx->stream));
+        // FAST and blur work tiles -> level | tx << 4 | ty << 16 (one table: FAST tiles first, blur tiles behind them)
+        const size_t btiles = (size_t)(g.blur_tiles_per_frame > 0 ? g.blur_tiles_per_frame : 1);
+        std::vector<uint32_t> tt(tiles + btiles, 0u);
+        for (int l = 0; l < g.nbuilt; ++l) {
+            const LevelGeom &L = g.lv[l];
+            for (int t = 0; t < L.tiles_x * L.tiles_y; ++t)
+                tt[(size_t)L.tile_off + t] = (uint32_t)l | ((uint32_t)(t % L.tiles_x) << 4) | ((uint32_t)(t / L.tiles_x) << 16);
+            if (L.tiles_x * L.tiles_y == 0) continue;               // levels without keypoints are not blurred
+            const int btx = (L.w + BL_W - 1) / BL_W, bty = (L.h + BL_H - 1) / BL_H;
+            for (int t = 0; t < btx * bty; ++t)
+                tt[tiles + (size_t)L.blur_tile_off + t] = (uint32_t)l | ((uint32_t)(t % btx) << 4) | ((uint32_t)(t / btx) << 16);
+        }
+        ASLAM_CUDA(cudaMalloc(&o->d_tile_tab, sizeof(uint32_t) * tt.size()));
+        ASLAM_CUDA(cudaMemcpyAsync(o->d_tile_tab, tt.data(), sizeof(uint32_t) * tt.size(), cudaMemcpyHostToDevice, ctx->stream));
         ASLAM_CUDA(cudaStreamSynchronize(ctx->stream));      // tt is a local
         b.tile_tab = o->d_tile_tab;
+        b.blur_tile_tab = o->d_tile_tab + tiles;
     }
     b.pattern = o->d_pattern;
     b.ori_tab = o->d_ori_tab;

@@ -11,6 +11,47 @@
 
 namespace aslam {
 
+// ------------------------------------------------------------------ mbarrier / bulk-copy (TMA) primitives
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// one box of a 3-D tensor (x, y, frame) -> shared memory; completion bytes are counted on `bar`.  x must be a multiple of 16.
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+// rows of bytes global -> shared without a tensor map (cp.async.bulk, UBLKCP): addresses and size multiples of 16 bytes
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // ------------------------------------------------------------------ exact bilinear resize (A2)
 // Per source row and group of 4 output columns:
 //   3 aligned 32-bit loads cover the <= 6-byte window of the 4 outputs, a funnel shift aligns it,
@@ -42,18 +83,31 @@ __device__ __forceinline__ HRow resize_hrow(uint32_t w0, uint32_t w1, uint32_t w
 #define ASLAM_RS_ROWS 16
 #endif
 constexpr int RS_ROWS = ASLAM_RS_ROWS;
+#ifndef ASLAM_RS_DEPTH
+#define ASLAM_RS_DEPTH 4        // source rows in flight per thread: 2 or 4
+#endif
+static_assert(ASLAM_RS_DEPTH == 2 || ASLAM_RS_DEPTH == 4, "resize prefetch depth");
 
+// THRESH: the mask pyramid's levels are thresholded (threshold(254, TOZERO)); image levels skip those 12 instructions per
+// group of 4 pixels (the kernel is bound by instruction issue: 73 % issue-active at 44 % ALU and 34 % DRAM on level 1).
+template <bool THRESH>
 __global__ void __launch_bounds__(256)
 resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
-              LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs, int thresh)
+              LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs)
 {
     // a CTA's warps sit side by side on the same strip of rows, so the CTA reads and writes whole row segments
     const int cg = blockIdx.x * blockDim.x + threadIdx.x;
     const int y0 = blockIdx.y * RS_ROWS;
     if (cg * 4 >= D.w || y0 >= D.h) return;
     // CTA-uniform bases + 32-bit per-thread offsets (a frame's pyramid is far below 4 GB)
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(srcb + (size_t)blockIdx.z * stride + S.off);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(dstb + (size_t)blockIdx.z * stride + D.off);
+    // The frame's base pointers are CTA-uniform.  Passed through an empty asm they stay in ordinary registers; left to the
+    // compiler they are re-derived from blockIdx.z and the parameters on the uniform datapath for every source row and
+    // every emitted row (8 + 10 of the loop's ~60 instructions per group of 4 pixels).
+    unsigned long long sbase = reinterpret_cast<unsigned long long>(srcb + (size_t)blockIdx.z * stride + S.off);
+    unsigned long long dbase = reinterpret_cast<unsigned long long>(dstb + (size_t)blockIdx.z * stride + D.off);
+    asm volatile("" : "+l"(sbase), "+l"(dbase));
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(sbase);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(dbase);
     const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
     const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
     const uint32_t *ytab = tabs + D.ytab_off;
@@ -65,12 +119,23 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
     // row s goes through the horizontal pass, then every output row whose lower tap is s is emitted.
     uint32_t e = __ldg(ytab + y0);
     int s_row = (int)(e & 0xffffu);                    // upper tap of the strip's first output row
-    // raw words of the next two source rows are always in flight (buffers a and b alternate)
+    // raw words of the next RS_DEPTH source rows are always in flight (the kernel waits on load latency -- 47 % of its
+    // stall cycles are long-scoreboard -- not on instruction issue)
     uint32_t so = t0.x + (uint32_t)s_row * pw;
     uint32_t a0 = __ldg(src + so), a1 = __ldg(src + so + 1), a2 = __ldg(src + so + 2);
     so = min(so + pw, so_last);
     uint32_t b0 = __ldg(src + so), b1 = __ldg(src + so + 1), b2 = __ldg(src + so + 2);
-    uint32_t dofs = (uint32_t)y0 * dpw + (uint32_t)cg;
+#if ASLAM_RS_DEPTH == 4
+    so = min(so + pw, so_last);
+    uint32_t c0 = __ldg(src + so), c1 = __ldg(src + so + 1), c2 = __ldg(src + so + 2);
+    so = min(so + pw, so_last);
+    uint32_t d0 = __ldg(src + so), d1 = __ldg(src + so + 1), d2 = __ldg(src + so + 2);
+#endif
+    // per-thread running pointers (the destination word and the row-table entry advance by constants): without them the
+    // compiler rebuilds both base addresses on the uniform datapath for every emitted row -- 17 of an emit's 42 instructions
+    uint32_t *dp = dst + ((size_t)y0 * dpw + (size_t)cg);
+    const uint32_t *yp = ytab + y0;
+    asm volatile("" : "+l"(yp));            // (same reason: a running pointer in ordinary registers)
     uint32_t y = (uint32_t)y0;
 #define ASLAM_RS_HROW(H, N0, N1, N2)                                        \
     do {                                                                    \
@@ -85,13 +150,13 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
         _Pragma("unroll")                                                   \
         for (int i = 0; i < 4; ++i) {                                       \
             v[i] = NEW.h[i] * wy1 + (OLD.h[i] * wy0 + 32768u);              /* 16.16, byte 2 = rounded pixel */ \
-            if (thresh && (v[i] >> 16) <= 254u) v[i] = 0;                   /* mask levels: threshold(254, TOZERO) */ \
+            if (THRESH && (v[i] >> 16) <= 254u) v[i] = 0;                   /* mask levels: threshold(254, TOZERO) */ \
         }                                                                   \
         const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062); \
-        dst[dofs] = __byte_perm(p01, p23, 0x5410);                          \
-        dofs += dpw;                                                        \
+        *dp = __byte_perm(p01, p23, 0x5410);                                \
+        dp += dpw;                                                          \
         if (++y == yend) return;                                            \
-        e = __ldg(ytab + y);                                                \
+        e = __ldg(++yp);                                                    \
     }
     HRow h0, h1;
     ASLAM_RS_HROW(h1, a0, a1, a2);
@@ -100,6 +165,14 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
         ++s_row;
         ASLAM_RS_HROW(h0, b0, b1, b2);
         ASLAM_RS_EMIT(h1, h0)
+#if ASLAM_RS_DEPTH == 4
+        ++s_row;
+        ASLAM_RS_HROW(h1, c0, c1, c2);
+        ASLAM_RS_EMIT(h0, h1)
+        ++s_row;
+        ASLAM_RS_HROW(h0, d0, d1, d2);
+        ASLAM_RS_EMIT(h1, h0)
+#endif
         ++s_row;
         ASLAM_RS_HROW(h1, a0, a1, a2);
         ASLAM_RS_EMIT(h0, h1)
@@ -108,15 +181,132 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
 #undef ASLAM_RS_EMIT
 }
 
+// ---- shared-memory form (the shipped kernel).  One CTA = a strip of RS_ROWS output rows over the level's full width.
+// The source rows the strip needs (about 1.2 * RS_ROWS + 2 of them) arrive by bulk asynchronous copies -- one
+// cp.async.bulk per row, issued by the first lanes of the CTA, completion on an mbarrier -- so every source byte crosses
+// L2 -> SM once per strip in full lines and no thread waits on its own global loads; the march then reads its 3-word
+// windows from shared memory.  Same arithmetic, same tables, same one-thread-per-4-columns march as resize_kernel.
+#ifndef ASLAM_RS_GROUP
+#define ASLAM_RS_GROUP 64       // rows per arrival barrier: 64 = the whole strip on one barrier (0.184 ms); 6: 0.192, 3: 0.191
+#endif
+constexpr int RS_GROUP = ASLAM_RS_GROUP;
+constexpr int RS_NGROUPS = (2 * RS_ROWS + 3 + RS_GROUP - 1) / RS_GROUP;      // a strip reads at most 2 * RS_ROWS + 3 source rows (scale <= 2)
+template <bool THRESH>
+__global__ void __launch_bounds__(1024)
+resize_smem_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
+                   LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs)
+{
+    extern __shared__ __align__(128) uint8_t rs_rows[];          // [rows of the strip][S.pitch]
+    // the strip's rows arrive in groups of RS_GROUP, one mbarrier each: the march starts when the first group is in and
+    // the later groups land while it computes
+    __shared__ __align__(8) unsigned long long bar[RS_NGROUPS];
+    const int tid = threadIdx.x, cg = tid;
+    const int y0 = blockIdx.x * RS_ROWS;
+    const uint32_t *ytab = tabs + D.ytab_off;
+    const int yend = min(y0 + RS_ROWS, D.h);
+    const int s_first = (int)(__ldg(ytab + y0) & 0xffffu);                                   // upper tap of the first output row
+    const int s_last = min((int)(__ldg(ytab + yend - 1) & 0xffffu) + 1, S.h - 1);          // lower tap of the last one
+    const int nrows = s_last - s_first + 1;
+    const uint32_t bar_a = smem_u32(&bar[0]);
+    if (tid < RS_NGROUPS) {
+        mbar_init(bar_a + 8u * tid, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int in_group = min(RS_GROUP, nrows - tid * RS_GROUP);
+        if (in_group > 0) mbar_arrive_expect_tx(bar_a + 8u * tid, (uint32_t)in_group * (uint32_t)S.pitch);
+    }
+    __syncthreads();
+    const uint8_t *sbase = srcb + (size_t)blockIdx.z * stride + S.off;
+    for (int r = tid; r < nrows; r += (int)blockDim.x)      // thread r fetches source row s_first + r
+        bulk_load(smem_u32(rs_rows + (size_t)r * S.pitch), sbase + (size_t)(s_first + r) * S.pitch, (uint32_t)S.pitch,
+                  bar_a + 8u * (uint32_t)(r / RS_GROUP));
+    if (cg * 4 >= D.w) return;
+    const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
+    const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
+    const uint32_t pw = (uint32_t)S.pitch >> 2, dpw = (uint32_t)D.pitch >> 2;
+    unsigned long long dbase = reinterpret_cast<unsigned long long>(dstb + (size_t)blockIdx.z * stride + D.off);
+    asm volatile("" : "+l"(dbase));
+    uint32_t *dp = reinterpret_cast<uint32_t *>(dbase) + ((size_t)y0 * dpw + (size_t)cg);
+    const uint32_t *yp = ytab + y0;
+    uint32_t e = __ldg(yp);
+    int s_row = s_first;
+    int y = y0;
+    // window of this thread in row r of the strip: words t0.x .. t0.x + 2 (the third may lie in the row's padding)
+    const uint32_t *win = reinterpret_cast<const uint32_t *>(rs_rows) + t0.x;
+    const uint32_t last = (uint32_t)(nrows - 1) * pw;                 // rows beyond the level's last are its last (clamped taps)
+    uint32_t ro = 0;
+    int ri = 0;                                                       // row of the strip the next horizontal pass reads
+#define ASLAM_RS_HROW_S(H)                                                  \
+    do {                                                                    \
+        if (ri % RS_GROUP == 0 && ri < nrows) mbar_wait(bar_a + 8u * (uint32_t)(ri / RS_GROUP), 0u); \
+        ++ri;                                                               \
+        H = resize_hrow(win[ro], win[ro + 1], win[ro + 2], t0, t1);         \
+        ro = min(ro + pw, last);                                            \
+    } while (0)
+#define ASLAM_RS_EMIT_S(OLD, NEW)                                           \
+    while ((int)(e & 0xffffu) + 1 == s_row) {                               \
+        const uint32_t wy1 = e >> 16, wy0 = 256u - wy1;                     \
+        uint32_t v[4];                                                      \
+        _Pragma("unroll")                                                   \
+        for (int i = 0; i < 4; ++i) {                                       \
+            v[i] = NEW.h[i] * wy1 + (OLD.h[i] * wy0 + 32768u);              /* 16.16, byte 2 = rounded pixel */ \
+            if (THRESH && (v[i] >> 16) <= 254u) v[i] = 0;                   /* mask levels: threshold(254, TOZERO) */ \
+        }                                                                   \
+        const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062); \
+        *dp = __byte_perm(p01, p23, 0x5410);                                \
+        dp += dpw;                                                          \
+        if (++y == yend) return;                                            \
+        e = __ldg(++yp);                                                    \
+    }
+    HRow h0, h1;
+    ASLAM_RS_HROW_S(h1);
+#pragma unroll 1
+    for (;;) {
+        ++s_row;
+        ASLAM_RS_HROW_S(h0);
+        ASLAM_RS_EMIT_S(h1, h0)
+        ++s_row;
+        ASLAM_RS_HROW_S(h1);
+        ASLAM_RS_EMIT_S(h0, h1)
+    }
+#undef ASLAM_RS_HROW_S
+#undef ASLAM_RS_EMIT_S
+}
+
+// Measured on B200 (ms per 256 frames, all 7 levels): direct loads with 4 source rows in flight 0.176 (2 rows: 0.189); source
+// rows staged in shared memory by bulk asynchronous copies (resize_smem_kernel) 0.184 with 16-row strips, 0.185 with 8,
+// 0.197 with 32, 0.191 when the rows arrive in groups on several barriers.
+#ifndef ASLAM_RS_SMEM
+#define ASLAM_RS_SMEM 0         // 1: the staged form (kept for A/B runs and for GPUs where it wins); 0: direct loads
+#endif
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask)
 {
     const LevelGeom &D = g.lv[level], &S = g.lv[level - 1];
     const int cgs = (D.w + 3) / 4;
+    uint8_t *base = is_mask ? b.mask : b.pyr;
+#if ASLAM_RS_SMEM
+    // a strip of RS_ROWS output rows reads at most ceil(RS_ROWS * S.h / D.h) + 2 source rows
+    const int max_rows = (int)(((long long)RS_ROWS * S.h + D.h - 1) / D.h) + 2;
+    const size_t smem = (size_t)max_rows * S.pitch + 16;        // + the last window's third word
+    const int threads = (cgs + 31) / 32 * 32;
+    if (threads <= 1024 && smem <= 200 * 1024) {
+        if (smem > 48 * 1024 && (size_t)ctx->resize_smem_set < smem) {       // opt in once per device (and size)
+            ASLAM_CUDA(cudaFuncSetAttribute(resize_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ASLAM_CUDA(cudaFuncSetAttribute(resize_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->resize_smem_set = 200 * 1024;
+        }
+        dim3 grid((D.h + RS_ROWS - 1) / RS_ROWS, 1, nframes);
+        ProfScope ps(ctx, PK_RESIZE);
+        if (is_mask) resize_smem_kernel<true><<<grid, threads, smem, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs);
+        else resize_smem_kernel<false><<<grid, threads, smem, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs);
+        ASLAM_LAUNCH_CHECK();
+        return ASLAM_OK;
+    }
+#endif
     const int warps = min(8, (cgs + 31) / 32);
     dim3 grid((cgs + 32 * warps - 1) / (32 * warps), (D.h + RS_ROWS - 1) / RS_ROWS, nframes), block(32 * warps);
-    uint8_t *base = is_mask ? b.mask : b.pyr;
     ProfScope ps(ctx, PK_RESIZE);
-    resize_kernel<<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, is_mask ? 1 : 0);
+    if (is_mask) resize_kernel<true><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs);
+    else resize_kernel<false><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs);
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }
@@ -1263,39 +1453,6 @@ constexpr int DESC_ORING = ASLAM_DESC_ORING < DESC_KPW ? ASLAM_DESC_ORING : DESC
 constexpr int DESC_WARP_SMEM = DESC_ORING * OPB_STRIDE + DESC_RING * BPB_STRIDE;
 constexpr size_t DESC_SMEM_BYTES = (size_t)DESC_WARPS * DESC_WARP_SMEM + 128;           // + slack to align the base to 128 B
 static_assert(OPB_STRIDE >= (OPB_H + 1) * OPB_W && OPB_STRIDE % 128 == 0 && BPB_STRIDE >= BPB_BYTES && BPB_STRIDE % 128 == 0, "patch slots");
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile("{\n"
-                 ".reg .pred P1;\n"
-                 "LAB_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-                 "@P1 bra DONE;\n"
-                 "bra LAB_WAIT;\n"
-                 "DONE:\n"
-                 "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-// one box of a 3-D tensor (x, y, frame) -> shared memory; completion bytes are counted on `bar`.  x must be a multiple of 16.
-__device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int x, int y, int z, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
 
 __global__ void __launch_bounds__(32 * DESC_WARPS)
 describe_kernel(OrbGeom g, OrbBuffers b)

@@ -15,6 +15,7 @@ struct OrbBuffers {
     uint8_t *mask;         // [B][pyr_stride] or NULL
     const uint32_t *tabs;  // resize tables
     const uint32_t *tile_tab;  // [tiles_per_frame] FAST tile -> level | tx << 4 | ty << 16
+    const uint32_t *blur_tile_tab;  // [blur_tiles_per_frame] blur tile -> level | tx << 4 | ty << 16
     uint32_t *cand;        // [B][tiles_per_frame][FT_CAP]  score<<24 | y<<12 | x
     uint32_t *cand_cnt;    // [B][tiles_per_frame]
     uint32_t *tile_base;   // [B][tiles_per_frame]  scratch of the selection kernel

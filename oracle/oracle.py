@@ -153,6 +153,15 @@ def blur7(img, mode=None):
     return out
 
 
+def blur7_split(img, row_fused_end, col_fused_end):
+    """blur7 with explicit split points: fused multiply-adds for columns below row_fused_end (row pass) / col_fused_end
+    (column pass), separately rounded products beyond."""
+    img = _u8(img)
+    out = np.zeros_like(img)
+    lib().orc_blur7_split(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(out), img.shape[1], int(row_fused_end), int(col_fused_end))
+    return out
+
+
 def brief(blurred, xi, yi, angle):
     blurred = _u8(blurred)
     d = np.zeros(32, np.uint8)

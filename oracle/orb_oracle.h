@@ -59,6 +59,7 @@ float orc_fast_atan2(float y, float x);
 float orc_ic_angle(const uint8_t *img, int stride, int x, int y);
 /* A8: blur_mode 0 = plain mul/add, 1 = fused multiply-add, 2 = cv2's measured hybrid (see .c) */
 void orc_blur7(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride, int blur_mode);
+void orc_blur7_split(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride, int row_fused_end, int col_fused_end);
 /* A9 */
 void orc_brief(const uint8_t *blurred, int stride, int xi, int yi, float angle_deg, uint8_t *desc32);
 

@@ -51,6 +51,30 @@ def test_blur_matches_cv2_sepfilter(oracle):
     assert bad == 0
 
 
+def test_blur_fma_split_of_this_hosts_cv2_is_measured_not_assumed(oracle):
+    """blur_mode 2 rests on one empirical property of the cv2 BUILD: its float sepFilter2D fuses multiply-adds in the vector
+    body of each pass and rounds products separately in the scalar tail.  This test measures where the tails start on the
+    running host -- it searches the (row, column) split points that reproduce cv2.sepFilter2D bit for bit on narrow, tall
+    images (where tail columns are a large share of the pixels) -- and fails with the measured values if they are not
+    (w & ~31, w & ~3), the split blur_mode 2 (oracle and CUDA path) implements."""
+    g = cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel()
+    never_differs = always_differs = 0
+    for w in (7, 31, 35, 77):
+        imgs = [np.random.RandomState(900 + i).randint(0, 256, (6000, w)).astype(np.uint8) for i in range(8)]
+        refs = [cv2.sepFilter2D(im, cv2.CV_8U, g, g, borderType=cv2.BORDER_REFLECT_101) for im in imgs]
+        cand = sorted({0, w} | {w & ~(m - 1) for m in (4, 8, 16, 32, 64)})
+        exact = [(r, c) for r in cand for c in cand
+                 if all((oracle.blur7_split(im, r, c) == ref).all() for im, ref in zip(imgs, refs))]
+        want = (w & ~31, w & ~3)
+        assert want in exact, ("width %d: this host's cv2 (%s) blurs like the split(s) %s, not like %s -- blur_mode 2 does not "
+                               "describe this OpenCV build; descriptors would still pass the 99 %% gate but not bit for bit"
+                               % (w, cv2.__version__, exact or "none of the candidates", want))
+        never_differs += sum(int((oracle.blur7_split(im, 0, 0) != ref).sum()) for im, ref in zip(imgs, refs))
+        always_differs += sum(int((oracle.blur7_split(im, w, w) != ref).sum()) for im, ref in zip(imgs, refs))
+    # the split is observable on these inputs: neither "never fused" nor "always fused" is what this cv2 computes
+    assert never_differs > 0 and always_differs > 0, (never_differs, always_differs)
+
+
 def test_fast_atan2_equals_cv2(oracle):
     rs = np.random.RandomState(0)
     ys, xs = rs.randint(-200000, 200000, 3000), rs.randint(-200000, 200000, 3000)
