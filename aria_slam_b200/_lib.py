@@ -37,6 +37,7 @@ class AslamError(RuntimeError):
 _P = C.c_void_p
 SYMBOLS = {
     "aslam_device_count": (C.c_int, []),
+    "aslam_debug_bounds": (C.c_int, [C.POINTER(C.c_uint64)]),
     "aslam_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "aslam_ctx_destroy": (None, [_P]),
     "aslam_ctx_sync": (C.c_int, [_P]),
@@ -93,6 +94,7 @@ SYMBOLS = {
     "aslam_loopdb_query_global_push_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int]),
     "aslam_loopdb_query_global_exchange_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_uint64, _P]),
     "aslam_loopdb_exchange_status": (C.c_int, [_P, C.POINTER(C.c_uint32), _P, C.c_int, C.c_int]),
+    "aslam_loopdb_set_pipelining": (C.c_int, [_P, C.c_int]),
     "aslam_loopdb_capacity_rows": (C.c_int64, [_P]),
     "aslam_loopdb_query_segmented_device": (C.c_int, [_P, _P, C.c_int, C.c_double, _P]),
     "aslam_loopdb_match_keyframe": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_double, _P, C.POINTER(C.c_int)]),

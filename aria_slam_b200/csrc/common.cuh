@@ -55,6 +55,23 @@ struct ProfScope {
 };
 
 #ifdef __CUDACC__
+// Debug build (-DASLAM_DEBUG_BOUNDS=1, libaslam_b200_dbg.so): every staged index -- shared-memory tiles, queues, candidate
+// slots, patch bytes, source and destination rows -- is checked and violations are counted (compute-sanitizer is closed
+// on the GPU pool this was developed on, so the parity tests over ragged sizes run once against this build as well).
+// Release builds compile the checks away.
+#if ASLAM_DEBUG_BOUNDS
+// (no relocatable device code in this build: every translation unit counts into its own copy and registers a reader)
+static __device__ unsigned long long g_bounds_violations;
+void register_bounds_reader(int (*reader)(unsigned long long *));
+static int tu_bounds_read(unsigned long long *v)
+{
+    return cudaMemcpyFromSymbol(v, g_bounds_violations, sizeof(*v)) == cudaSuccess ? 0 : 1;
+}
+[[maybe_unused]] static const int tu_bounds_registered = (register_bounds_reader(tu_bounds_read), 0);
+#define ASLAM_BOUNDS(cond) do { if (!(cond)) atomicAdd(&aslam::g_bounds_violations, 1ull); } while (0)
+#else
+#define ASLAM_BOUNDS(cond) do { } while (0)
+#endif
 // DYNAMIC_CLASSES of the reference (src/main.cpp:29-41): person, bicycle, car, motorcycle, bus, train, truck, bird, cat, dog
 __device__ __forceinline__ bool is_dynamic_class(int c)
 {

@@ -7,6 +7,14 @@ namespace aslam {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+#if ASLAM_DEBUG_BOUNDS
+static std::vector<int (*)(unsigned long long *)> &bounds_readers()
+{
+    static std::vector<int (*)(unsigned long long *)> r;
+    return r;
+}
+void register_bounds_reader(int (*reader)(unsigned long long *)) { bounds_readers().push_back(reader); }
+#endif
 
 int fail(int code, const char *fmt, ...)
 {
@@ -93,6 +101,26 @@ int aslam_prof_read(aslam_ctx *ctx, int kind, double *total_ms, int64_t *launche
 
 const char *aslam_last_error(void) { return aslam::g_err; }
 const char *aslam_version(void) { return "aslam_b200 0.2 (sm_100a)"; }
+
+int aslam_debug_bounds(uint64_t *violations)
+{
+#if ASLAM_DEBUG_BOUNDS
+    if (violations) {
+        unsigned long long sum = 0;
+        ASLAM_CUDA(cudaDeviceSynchronize());
+        for (auto reader : aslam::bounds_readers()) {
+            unsigned long long v = 0;
+            if (reader(&v)) return aslam::fail(ASLAM_E_CUDA, "cannot read a bounds counter");
+            sum += v;
+        }
+        *violations = sum;
+    }
+    return 1;
+#else
+    if (violations) *violations = 0;
+    return 0;
+#endif
+}
 
 int aslam_device_count(void)
 {

@@ -50,12 +50,16 @@ struct aslam_loopdb {
     std::vector<void *> x_opened;        // peers' buffers opened through IPC (closed on destroy)
     unsigned long long **d_x_peers = nullptr;      // device table of the nparts buffer addresses
     uint64_t x_round = 0;
+    // aslam_loopdb_set_pipelining: consecutive fused queries may overlap (programmatic dependent launch)
+    bool pipelining = false;
+    bool last_was_fused = false;         // the last operation this database put on the stream was a fused query kernel
 };
 
 static void db_invalidate_tables(aslam_loopdb *db)
 {
     db->tab_splits = 0;
     db->map_dirty = true;
+    db->last_was_fused = false;
 }
 
 static int db_reserve(aslam_loopdb *db, int nq, int nprobs, size_t partial_elems)
@@ -236,6 +240,7 @@ static int db_query_segmented_device(aslam_loopdb *db, const uint8_t *d_q, int n
     if (rc) return rc;
     if ((rc = db_sync_map(db))) return rc;
     db->tab_splits = 0; db->armed = false;      // the flat query's table and preset slots are overwritten here
+    db->last_was_fused = false;
     {
         ProfScope ps(ctx, PK_MISC);
         fill_segment_problems_kernel<<<(nseg * splits + 127) / 128, 128, 0, ctx->stream>>>(db->d_probs, d_q, db->d_rows + db->head * 32,
@@ -265,9 +270,11 @@ static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_
     if (rows > 0 || fused) {
         splits = rows > 0 ? choose_splits(ctx, nq, rows, 1) : 1;      // an empty shard still takes part in the exchange
         if ((rc = db_reserve(db, 0, splits, (size_t)splits * q_stride))) return rc;
+        bool table_rebuilt = false;
         if (db->tab_q != d_q || db->tab_nq != nq || db->tab_splits != splits || db->tab_head != db->head || db->tab_rows != rows) {
             rc = launch_fill_split_problems(ctx, db->d_probs, d_q, db->d_rows + db->head * 32, nullptr, nullptr, nq, (int)rows, splits);
             if (rc) return rc;
+            table_rebuilt = true;
             db->tab_q = d_q; db->tab_nq = nq; db->tab_splits = splits; db->tab_head = db->head; db->tab_rows = rows;
         }
         const bool armed = db->armed && db->armed_stride == q_stride;
@@ -286,10 +293,14 @@ static int db_query_global(aslam_loopdb *db, const uint8_t *d_q, int nq, uint64_
             X.peer_bufs = (unsigned long long *const *)d_peer_bufs; X.nparts = nparts; X.my_part = my_part; X.nq = nq;
             X.round = round; X.arrive = db->d_arrive; X.out = (unsigned long long *)d_top2; X.stamps = db->d_stamps;
             X.status = db->d_status; X.map = db_row_map(db);
-            rc = launch_knn2_scan_exchange(ctx, db->d_probs, splits, nq, db->d_partial, q_stride, X);
-            if (rc == ASLAM_OK) { db->armed = true; db->armed_stride = q_stride; }
+            // pipelined with the previous query only if that was the last thing this database enqueued and the row-range
+            // table, the slots and the counters are exactly as its kernel leaves them
+            const bool overlap = db->pipelining && db->last_was_fused && armed && !table_rebuilt;
+            rc = launch_knn2_scan_exchange(ctx, db->d_probs, splits, nq, db->d_partial, q_stride, X, overlap);
+            if (rc == ASLAM_OK) { db->armed = true; db->armed_stride = q_stride; db->last_was_fused = true; }
             return rc;
         }
+        db->last_was_fused = false;
         rc = launch_knn2_partial(ctx, db->d_probs, splits, nq, db->d_partial, q_stride, splits, armed);
         if (rc) return rc;
         rearm = splits > 1;                     // a single range writes its slot directly; nothing to preset
@@ -494,6 +505,7 @@ int aslam_loopdb_match_keyframe(aslam_loopdb *db, int kf_index, const uint8_t *q
     ASLAM_CUDA(cudaSetDevice(ctx->device));
     int rc = db_reserve(db, nq, 1, 1);
     if (rc) return rc;
+    db->last_was_fused = false;
     ASLAM_CUDA(cudaMemcpyAsync(db->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
     return knn2_resident_to_host(ctx, db->d_q, nq, db->d_rows + sg.start * 32, sg.n, ratio, 1, out, nout);
 }
@@ -523,6 +535,14 @@ int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d
     ASLAM_REQUIRE(nq >= 0 && nparts >= 1 && my_part >= 0 && my_part < nparts && round >= 1, "bad sizes or round");
     if (nq == 0) return ASLAM_OK;
     return db_query_global(db, d_q, nq, d_out, d_peer_bufs, nparts, my_part, round);
+}
+
+int aslam_loopdb_set_pipelining(aslam_loopdb *db, int on)
+{
+    ASLAM_REQUIRE(db, "db is NULL");
+    db->pipelining = on != 0;
+    db->last_was_fused = false;
+    return ASLAM_OK;
 }
 
 int aslam_loopdb_exchange_status(aslam_loopdb *db, uint32_t *status, uint64_t *stamps, int nqblocks, int reset)

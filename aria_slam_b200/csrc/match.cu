@@ -126,6 +126,10 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *partial, int
     static_assert(KNN_TILE == KNN_THREADS && KNN_TILE == 128 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
     __shared__ uint4 tile[2][KNN_TILE * 3];
 
+    // Pipelined queries (programmatic dependent launch): the next query's kernel may be scheduled while this one's
+    // last CTAs are still in their exchange tail; it scans at once and holds its merge (griddepcontrol.wait below)
+    // until this kernel has completed.  Both instructions do nothing in a launch without the attribute.
+    if (FUSED) asm volatile("griddepcontrol.launch_dependents;");
     const KnnProblem P = probs[blockIdx.y];
     const int nq = P.nq_dev ? min(*P.nq_dev, P.nq) : P.nq;
     const int nt = P.nt_dev ? min(*P.nt_dev, P.nt) : P.nt;
@@ -161,6 +165,7 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *partial, int
         {
             uint4 par;
             par.x = pre0.x ^ pre0.y ^ pre0.z; par.y = pre0.w ^ pre1.x ^ pre1.y; par.z = par.x ^ par.y ^ pre1.z; par.w = 0;
+            ASLAM_BOUNDS(3 * tid + 2 < KNN_TILE * 3 && t0 >= t_lo && t0 < t_hi && t_hi <= nt);
             tile[buf][3 * tid] = pre0; tile[buf][3 * tid + 1] = pre1; tile[buf][3 * tid + 2] = par;
         }
         __syncthreads();
@@ -196,6 +201,8 @@ knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *partial, int
             b2[j] = n2;
         }
     }
+    // (pipelined launch: the previous query's kernel re-arms the merged slots and the arrival counters in its tail)
+    if (FUSED) asm volatile("griddepcontrol.wait;" ::: "memory");
     // Row ranges of one (query set, train set) pair are consecutive problems: with merge_div > 1 they are merged
     // here, into one (best, second) per query and group, by three order-independent atomic minima (the slot
     // was preset to KEY_EMPTY): B1 <- min(B1, b1) returns the previous best; whichever of the two lost goes to
@@ -364,6 +371,7 @@ knn2_finish_matches_kernel(const KnnProblem *__restrict__ probs, const uint2 *__
         if (pass && out) {
             aslam_match m;
             m.query_idx = q; m.train_idx = i0; m.distance = (float)d0;
+            ASLAM_BOUNDS(i0 >= 0 && i0 < P.nt && q < nq);
             if (written + pos < out_stride) out[(size_t)g * out_stride + written + pos] = m;
         }
         written += total;
@@ -490,7 +498,7 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
 }
 
 int launch_knn2_scan_exchange(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int nq, uint2 *d_partial,
-                              int q_stride, const ExchangeArgs &X)
+                              int q_stride, const ExchangeArgs &X, bool overlap_previous)
 {
     if (nprobs <= 0 || nq <= 0) return fail(ASLAM_E_INVALID, "fused exchange needs at least one row range and one query");
     const int nqb = (nq + KNN_QBLOCK - 1) / KNN_QBLOCK;
@@ -505,8 +513,14 @@ int launch_knn2_scan_exchange(aslam_ctx *ctx, const KnnProblem *d_probs, int npr
     static const int csa = [] { const char *e = getenv("ASLAM_KNN_CSA"); return e ? atoi(e) : ASLAM_KNN_CSA; }();
     const KnnMul M{2u, 4u, 65536u, 128u};
     ProfScope ps(ctx, PK_KNN_PARTIAL);
-    if (csa == 7) knn2_partial_v2_kernel<false, true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, nprobs, X);
-    else knn2_partial_v2_kernel<true, true><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, nprobs, X);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(KNN_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = overlap_previous ? 1 : 0;
+    if (csa == 7) ASLAM_CUDA(cudaLaunchKernelEx(&cfg, knn2_partial_v2_kernel<false, true>, d_probs, d_partial, q_stride, M, nprobs, X));
+    else ASLAM_CUDA(cudaLaunchKernelEx(&cfg, knn2_partial_v2_kernel<true, true>, d_probs, d_partial, q_stride, M, nprobs, X));
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

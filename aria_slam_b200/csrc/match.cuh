@@ -111,7 +111,10 @@ constexpr int KNN_FUSED_MAX_QBLOCKS = 64;  // waiting CTAs (one per query block)
 // last CTA to arrive for a block of KNN_QBLOCK queries turns the merged slots into global keys, stores them into every
 // peer's buffer over NVLink, raises this shard's flag for that block on every peer, waits for the peers' flags of the
 // same block and round, merges and writes X.out.  The slots must hold KEY_EMPTY on entry and are left so.
+// overlap_previous: launched with programmatic stream serialization -- legal only when the kernel before it on the stream
+// is the previous query's launch of this same kernel and nothing it reads before its merge (problem table, queries,
+// database rows) was written by that kernel.
 int launch_knn2_scan_exchange(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, int nq, uint2 *d_partial,
-                              int q_stride, const ExchangeArgs &X);
+                              int q_stride, const ExchangeArgs &X, bool overlap_previous = false);
 
 }  // namespace aslam

@@ -141,6 +141,7 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
     do {                                                                    \
         H = resize_hrow(N0, N1, N2, t0, t1);                                \
         so = min(so + pw, so_last);                                         \
+        ASLAM_BOUNDS((size_t)(so + 3) * 4 <= (size_t)S.pitch * S.h + 256);  /* the third word may touch the 256-B level padding */ \
         N0 = __ldg(src + so); N1 = __ldg(src + so + 1); N2 = __ldg(src + so + 2); \
     } while (0)
 #define ASLAM_RS_EMIT(OLD, NEW)                                             \
@@ -153,6 +154,7 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
             if (THRESH && (v[i] >> 16) <= 254u) v[i] = 0;                   /* mask levels: threshold(254, TOZERO) */ \
         }                                                                   \
         const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062); \
+        ASLAM_BOUNDS(dp >= dst && dp + 1 <= dst + (size_t)dpw * D.h && y < (uint32_t)D.h); \
         *dp = __byte_perm(p01, p23, 0x5410);                                \
         dp += dpw;                                                          \
         if (++y == yend) return;                                            \
@@ -480,6 +482,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             for (int k = 0; k < PASSES; ++k) {
                 const int r = rr + 13 * k;
                 if (13 * (k + 1) <= FT_PIX_H || r < FT_PIX_H) {
+                    ASLAM_BOUNDS(r < FT_PIX_H && 4 * jj + 3 < FA_PITCH && x >= 0 && x + 4 <= L.pitch && xn < L.pitch && sy0 - 3 + r >= 0);
                     const uint8_t *row = img + (size_t)min(sy0 - 3 + r, L.h - 1) * L.pitch;
                     const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + x));
                     const uint32_t nx = __ldg(row + xn);
@@ -536,6 +539,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             const uint32_t ub = imad32(c, M.minus1, imad32(mb, M.one, kq));
             const uint32_t ud = imad32(md, M.minus1, imad32(c, M.one, kq));
             const bool pass = ((ub | ud) & colbits) != 0;
+            ASLAM_BOUNDS(r >= 0 && r + 6 < FT_PIX_H && gp - 2 >= 0 && 2 * (gp + 2) < FA_PITCH && nq <= FT_SCORE_H / 8 * 32);
             S[r][p] = 0u;
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             queue[pass ? nq + __popc(bal & ((1u << p) - 1u)) : FT_SCORE_H / 8 * 32] = (uint16_t)((r << 5) | p);      // branch-free: slot 256 is a sink
@@ -552,6 +556,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             const int rr = id >> 5, pp = id & 31;
             const uint32_t thr = __shfl_sync(0xffffffffu, neg_thr, pp);
             const uint32_t sc = fast_score_pair(A, Bc, rr, g0 / 2 + pp, thr, M);
+            ASLAM_BOUNDS(rr >= 0 && rr < FT_SCORE_H && pp >= 0 && pp < 32 && n2 <= i0);
             if (i < nq) S[rr][pp] = sc;
 #if ASLAM_FAST_NMS_QUEUE
             // keep the pairs with a positive score, in place: n2 <= i0, so a slot written here was read already
@@ -609,6 +614,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
                 }
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, e != 0);
+            ASLAM_BOUNDS(local + 32 <= FT_SCORE_H / 8 * 32 + 32 && (e == 0 || (((e >> 12) & 0xfffu) < (uint32_t)L.h && (e & 0xfffu) < (uint32_t)L.w)));
             if (e) stage[local + __popc(bal & ((1u << p) - 1u))] = e;
             local += __popc(bal);
         }
@@ -623,6 +629,7 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
         total += t;
     }
     uint32_t *out = b.cand + ((size_t)frame * g.tiles_per_frame + tile) * FT_CAP;
+    ASLAM_BOUNDS(total <= FT_CAP && base + local <= FT_CAP);
     for (int i = p; i < local; i += 32) out[base + i] = stage[i];
     if (tid == 0) b.cand_cnt[(size_t)frame * g.tiles_per_frame + tile] = (uint32_t)total;
 #else
@@ -782,6 +789,7 @@ __device__ __forceinline__ void blur_col_task(const float (*R)[BL_W], int c4, in
 {
     float4 w[10];
 #pragma unroll
+    ASLAM_BOUNDS(r0 >= 0 && r0 < BL_ROWS && c4 >= 0 && c4 + 4 <= BL_W);
     for (int k = 0; k < 10; ++k) w[k] = *reinterpret_cast<const float4 *>(&R[min(r0 + k, BL_ROWS - 1)][c4]);
     const float2 K0 = f2(T.k[0], T.k[0]), K1 = f2(T.k[1], T.k[1]), K2 = f2(T.k[2], T.k[2]), K3 = f2(T.k[3], T.k[3]);
     const float2 MG = f2(12582912.0f, 12582912.0f);
@@ -856,6 +864,7 @@ blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
         if (gi < left || gi >= gs) continue;
         const uint8_t *rowa = img + (size_t)reflect101(y0 - 3 + 2 * rp, L.h) * L.pitch;
         const uint8_t *rowb = img + (size_t)reflect101(y0 - 2 + 2 * rp, L.h) * L.pitch;
+        ASLAM_BOUNDS(2 * rp + 1 < BL_ROWS && gi * 8 + 8 <= BL_W && x0 + gi * 8 >= 4 && x0 + gi * 8 + 12 <= L.pitch);
         blur_row_task<false, true>(rowa, rowb, x0 + gi * 8, L.w, T, &R[2 * rp][gi * 8], &R[2 * rp + 1][gi * 8]);
     }
     // ---- row pass, special groups
@@ -1095,6 +1104,7 @@ select_kernel(OrbGeom g, OrbBuffers b)
             const uint32_t e = i < n ? cand[(size_t)t * FT_CAP + i] : 0u;
             const bool pass = i < n && (e >> 24) >= thr;
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+            ASLAM_BOUNDS(!pass || base + 32 <= ntiles * FT_CAP + 32);
             if (pass) surv[base + __popc(bal & ((1u << lane) - 1u))] = e;
             base += __popc(bal);
         }
@@ -1104,6 +1114,7 @@ select_kernel(OrbGeom g, OrbBuffers b)
     // --- Harris response of every survivor
     for (int i = tid; i < M1; i += SEL_THREADS) {
         const uint32_t e = surv[i];
+        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h);
         hresp[i] = harris_response(img, L.pitch, (int)(e & 0xfffu), (int)((e >> 12) & 0xfffu));
     }
     __syncthreads();
@@ -1501,6 +1512,8 @@ describe_kernel(OrbGeom g, OrbBuffers b)
         // computeKeyPoints scales the point to level-0 coordinates; computeOrbDescriptors scales it back.
         kx = __fmul_rn((float)x, L.sf); ky = __fmul_rn((float)y, L.sf);
         xi = __float2int_rn(__fmul_rn(kx, L.inv_sf)); yi = __float2int_rn(__fmul_rn(ky, L.inv_sf));
+        ASLAM_BOUNDS(x >= 15 && y >= 15 && y + 15 < L.h && x + 15 < L.w && xi >= 19 && yi >= 19 && yi + 19 < L.h && xi + 19 < L.w &&
+                     level_base + k0 + lane < g.kp_cap);
         if (lane < DESC_ORING) {
             mbar_arrive_expect_tx(obar + 8u * lane, OPB_BYTES);
             tma_load_box(smem_u32(wsm + lane * OPB_STRIDE), tm, (x - 15) & ~15, y - 15, frame, obar + 8u * lane);
@@ -1591,6 +1604,8 @@ describe_kernel(OrbGeom g, OrbBuffers b)
             const float2 c1 = __fmul2_rn(P1[j], CC), c2 = __fmul2_rn(P1[j], SS);
             const float2 r0 = __fadd2_rn(make_float2(__fsub_rn(a1.x, a2.y), __fadd_rn(a2.x, a1.y)), MG);
             const float2 r1 = __fadd2_rn(make_float2(__fsub_rn(c1.x, c2.y), __fadd_rn(c2.x, c1.y)), MG);
+            ASLAM_BOUNDS(pb + __float_as_uint(r0.y) * (uint32_t)BPB_W + __float_as_uint(r0.x) - smem_u32(bp_ring + slot * BPB_STRIDE) < (uint32_t)BPB_BYTES &&
+                         pb + __float_as_uint(r1.y) * (uint32_t)BPB_W + __float_as_uint(r1.x) - smem_u32(bp_ring + slot * BPB_STRIDE) < (uint32_t)BPB_BYTES);
             const uint32_t t0 = lds_u8(pb + __float_as_uint(r0.y) * (uint32_t)BPB_W + __float_as_uint(r0.x));
             const uint32_t t1 = lds_u8(pb + __float_as_uint(r1.y) * (uint32_t)BPB_W + __float_as_uint(r1.x));
             byte |= (uint32_t)(t0 < t1) << j;

@@ -287,6 +287,10 @@ class LoopDB:
         check(lib().aslam_loopdb_query_global(self.h, ptr(q), len(q), ptr(top2)))
         return unpack_top2(top2)
 
+    def set_pipelining(self, on=True):
+        """Consecutive fused queries may overlap (aslam_loopdb_set_pipelining; see the header for the caller's contract)."""
+        check(lib().aslam_loopdb_set_pipelining(self.h, 1 if on else 0))
+
     def exchange_status(self, nqblocks=0, reset=False):
         """(status word, stamps[nqblocks, 4]) of the fused exchange: per query block the %globaltimer ns of the last push and
         of the last all-peers-seen, the sum of (seen - push) since the last reset, and the number of exchanges."""

@@ -96,7 +96,7 @@ class ShardedLoopQuery:
     survivors for its own keyframes; the exchange is one all_gather of int32 counts.
     """
 
-    def __init__(self, ctx, db_rows, rank, world, keyframe_rows=2000, exchange="auto"):
+    def __init__(self, ctx, db_rows, rank, world, keyframe_rows=2000, exchange="auto", pipelined=False):
         import torch
         from .frontend import LoopDB
         self.ctx, self.rank, self.world = ctx, rank, world
@@ -109,6 +109,11 @@ class ShardedLoopQuery:
         for k in range(lo_kf, hi_kf):
             self.db.add(db_rows[starts[k]:starts[k + 1]], k)
         self.db.set_row_base(self.row_lo)
+        # consecutive fused queries may overlap (the next scan starts during the previous exchange tail): the caller
+        # promises that no kernel writes the query buffer between two calls (aslam_loopdb_set_pipelining)
+        self.pipelined = bool(pipelined)
+        if self.pipelined:
+            self.db.set_pipelining(True)
         self._torch = torch
         self._local = self._out = None
         self._symm = None

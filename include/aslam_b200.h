@@ -89,6 +89,10 @@ typedef struct {
  * (OrbCudaExtractor.cpp:21-33, CudaMatcher.cpp:7-19; FactoryConfig::cuda_device,
  * include/factory/PipelineFactory.hpp:21).  stream = a cudaStream_t to borrow, or NULL to
  * create (and later destroy) a private one. */
+/* 1 when this library is the bounds-checking debug build (-DASLAM_DEBUG_BOUNDS=1: every staged index of every kernel is
+ * checked on the device); *violations = checks that failed on the current device so far (after a device sync).  0 and
+ * *violations = 0 in the release build, whose kernels carry no checks. */
+ASLAM_API int aslam_debug_bounds(uint64_t *violations);
 ASLAM_API int aslam_device_count(void);      /* CUDA devices visible to this process (0 without a driver) */
 ASLAM_API int aslam_ctx_create(int device, void *stream, aslam_ctx **out);
 ASLAM_API void aslam_ctx_destroy(aslam_ctx *ctx);
@@ -301,6 +305,13 @@ ASLAM_API int aslam_loopdb_query_global_push_device(aslam_loopdb *db, const uint
 ASLAM_API int aslam_loopdb_query_global_exchange_device(aslam_loopdb *db, const uint8_t *d_q, int nq,
                                                         uint64_t *const *d_peer_bufs, int nparts, int my_part,
                                                         uint64_t round, uint64_t *d_out);
+/* Pipelining of consecutive fused queries (off by default).  When on, a fused query launched directly behind another
+ * fused query of the same database (same query buffer, same database content) starts its scan while the previous
+ * query's last CTAs are still exchanging with the peers (programmatic dependent launch; it holds its own merge until
+ * the previous kernel has completed).  The caller's part of the contract: between two such calls no KERNEL on this
+ * context's stream writes the query buffer (copies are fine -- they end the overlap by themselves).  A throughput
+ * feature for streams of queries; a single query's latency is unchanged. */
+ASLAM_API int aslam_loopdb_set_pipelining(aslam_loopdb *db, int on);
 /* Waits for the stream; *status = 0 when no exchange on this database ever timed out.  stamps (may be NULL) receives
  * 4 words per query block: %globaltimer (ns) of the last exchange's push to the peers and of the moment all peers'
  * flags had been seen, the SUM of (seen - push) over all exchanges since the last reset -- the time this rank spent

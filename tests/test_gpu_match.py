@@ -393,6 +393,53 @@ def test_fused_scan_exchange_with_one_shard_equals_the_plain_query(ctx, oracle):
     db.close()
 
 
+def test_pipelined_fused_queries_give_the_same_keys(ctx, oracle):
+    """aslam_loopdb_set_pipelining: fused queries launched back to back (programmatic dependent launch: a query's scan may start
+    while its predecessor's exchange tail runs) must leave exactly the keys of unpipelined queries -- also when the query
+    buffer alternates (which ends the overlap by itself) and when a keyframe is added in between."""
+    import torch
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import LoopDB
+    from aria_slam_b200._lib import lib
+    from aria_slam_b200.sharded import pack_top2
+    rows = synth.descriptor_db(64_000, 41)
+    db = LoopDB(ctx, 70_000, 64)
+    for k in range(31):
+        db.add(rows[k * 2000:(k + 1) * 2000], k)
+    db.set_pipelining(True)
+    nq = 2000
+    qa, _ = synth.loop_queries(rows[:62_000], nq, 42)
+    qb, _ = synth.loop_queries(rows[:62_000], nq, 43)
+    refs = {}
+    for name, q in (("a", qa), ("b", qb)):
+        ridx, rdist = oracle.knn2(q, rows[:62_000])
+        refs[name] = pack_top2(ridx, rdist)
+    words = lib().aslam_loop_exchange_buffer_bytes(1, nq) // 8
+    buf = torch.zeros(words, dtype=torch.int64, device="cuda")
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+    da, dbq = torch.from_numpy(qa).cuda(), torch.from_numpy(qb).cuda()
+    outs = [torch.zeros((nq, 2), dtype=torch.int64, device="cuda") for _ in range(12)]
+    torch.cuda.synchronize()
+    rnd = 0
+    order = ["a"] * 6 + ["b", "a", "b", "b", "a", "a"]            # six pipelined repeats, then alternating buffers
+    for i, name in enumerate(order):
+        rnd += 1
+        db.query_global_exchange_device(da if name == "a" else dbq, nq, ptrs, 1, 0, rnd, outs[i])
+    ctx.sync()
+    for i, name in enumerate(order):
+        assert (outs[i].cpu().numpy().view(np.uint64) == refs[name]).all(), (i, name)
+    db.add(rows[62_000:64_000], 31)                                # the database changes: the next query must see it
+    ridx, rdist = oracle.knn2(qa, rows)
+    for i in range(3):
+        rnd += 1
+        db.query_global_exchange_device(da, nq, ptrs, 1, 0, rnd, outs[i])
+    ctx.sync()
+    for i in range(3):
+        assert (outs[i].cpu().numpy().view(np.uint64) == pack_top2(ridx, rdist)).all()
+    assert db.exchange_status(0)[0] == 0
+    db.close()
+
+
 def test_shard_group_on_one_device_follows_the_single_database(ctx, oracle):
     """aslam_loopdb_shard_group with a single device: FIFO eviction, per-keyframe counts, flat top-2 with global rows
     that keep counting from creation, candidate re-match -- all equal to the plain aslam_loopdb and the oracle."""
