@@ -28,9 +28,9 @@ def test_sharded_loop_query_one_process_per_gpu():
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
     assert d["modes_agree"] and d["second_neighbour_checked"]
-    for mode in ("nccl", "push", "fused", "ipc"):
+    for mode in ("nccl", "push", "fused", "ipc", "ipc+pipelined"):
         e = d[mode]
-        assert e["exchange"] == mode and e["ranks_identical"] and e["every_rank_equals_oracle_full_keys"], (mode, e)
+        assert e["exchange"] == mode.split("+")[0] and e["ranks_identical"] and e["every_rank_equals_oracle_full_keys"], (mode, e)
         assert e["segmented_equals_oracle"] and e["flat_after_segmented_ok"], (mode, e)
     assert d["ipc"]["status"] == 0 and d["fused"]["status"] == 0
 

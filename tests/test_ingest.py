@@ -165,8 +165,8 @@ def test_replay_matches_oracle(tmp_path, oracle):
         assert key(kps) == key(ko)
         if prev_desc is None:
             assert nm == 0
-        else:                                                 # frame i (query) against its predecessor, across batch borders too
-            ki, kd = oracle.knn2(desc, prev_desc)
+        else:                                                 # its predecessor (query) against frame i (train) as main.cpp:158-161
+            ki, kd = oracle.knn2(prev_desc, desc)             # does; across batch borders too
             ref = oracle.ratio_matches(ki, kd, 3, 4)
             got = np.stack([m["q"], m["t"], m["d"].astype(np.int32)], 1)
             assert got.shape == ref.shape and (got == ref).all()

@@ -16,7 +16,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 stream = torch.cuda.Stream()
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
-modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["nccl", "push", "fused", "ipc"]
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["nccl", "push", "fused", "ipc", "ipc+pipelined"]
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 NQ, KF = 2000, 2000
 db = synth.descriptor_db(rows, 5)
@@ -40,7 +40,7 @@ with torch.cuda.stream(stream):
     ctx = Context(local, stream.cuda_stream)
     dq = torch.from_numpy(q).cuda()
     for mode in modes:
-        lq = ShardedLoopQuery(ctx, db, rank, world, keyframe_rows=KF, exchange=mode)
+        lq = ShardedLoopQuery(ctx, db, rank, world, keyframe_rows=KF, exchange=mode.split("+")[0], pipelined=mode.endswith("+pipelined"))
         for _ in range(3):
             out = lq.query(dq, NQ)
         torch.cuda.synchronize(); dist.barrier()
