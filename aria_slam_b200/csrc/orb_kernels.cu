@@ -1026,8 +1026,11 @@ __device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of
 
 // BUCKET = the grid-bucketed second cull (g.grid_cell > 0), an extension cv::ORB does not have; its definition is
 // in include/aslam_b200.h (aslam_orb_params::grid_cell) and DESIGN.md section 4a.
+#ifndef ASLAM_SEL_MINB
+#define ASLAM_SEL_MINB 1
+#endif
 template <bool BUCKET>
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, ASLAM_SEL_MINB)
 select_kernel(OrbGeom g, OrbBuffers b)
 {
     __shared__ int hist[256];
