@@ -81,6 +81,7 @@ SYMBOLS = {
     "aslam_loopdb_create": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(_P)]),
     "aslam_loopdb_destroy": (None, [_P]),
     "aslam_loopdb_add": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
+    "aslam_loopdb_add_at": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_int64]),
     "aslam_loopdb_add_device": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
     "aslam_loopdb_clear": (C.c_int, [_P]),
     "aslam_loopdb_save": (C.c_int, [_P, C.c_char_p]),

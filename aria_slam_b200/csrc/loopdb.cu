@@ -359,10 +359,23 @@ int aslam_loopdb_add_device(aslam_loopdb *db, const uint8_t *d_desc, int n, uint
     return db_append(db, d_desc, n, keyframe_id, cudaMemcpyDeviceToDevice);
 }
 
+int aslam_loopdb_add_at(aslam_loopdb *db, const uint8_t *desc, int n, uint64_t keyframe_id, int64_t global_row_base)
+{
+    ASLAM_REQUIRE(db, "db is NULL");
+    ASLAM_REQUIRE(global_row_base >= 0 && global_row_base < (1LL << 39), "global_row_base out of range");
+    if (!db->scattered && !db->segs.empty())
+        return fail(ASLAM_E_STATE, "aslam_loopdb_add_at on a database that already holds contiguous keyframes");
+    if (!db->segs.empty() && global_row_base < db->segs.back().gbase + db->segs.back().n)
+        return fail(ASLAM_E_INVALID, "keyframes of a shard must be added in increasing global row order");
+    db->scattered = true;
+    return db_append(db, desc, n, keyframe_id, cudaMemcpyHostToDevice, global_row_base);
+}
+
 int aslam_loopdb_clear(aslam_loopdb *db)
 {
     ASLAM_REQUIRE(db, "db is NULL");
     db->segs.clear(); db->head = db->tail = 0; db->row_base = 0;
+    db->scattered = false;
     db_invalidate_tables(db);
     return ASLAM_OK;
 }
@@ -842,7 +855,7 @@ int aslam_loopdb_shard_group_add(aslam_loopdb_group *g, const uint8_t *desc, int
 int aslam_loopdb_shard_group_clear(aslam_loopdb_group *g)
 {
     ASLAM_REQUIRE(g, "group is NULL");
-    for (auto *db : g->shard) { aslam_loopdb_clear(db); }
+    for (auto *db : g->shard) { aslam_loopdb_clear(db); db->scattered = true; }
     g->live.clear(); g->next_seq = 0; g->next_row = 0;
     return ASLAM_OK;
 }

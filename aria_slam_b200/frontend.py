@@ -230,6 +230,11 @@ class LoopDB:
         d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
         check(lib().aslam_loopdb_add(self.h, ptr(d), len(d), int(keyframe_id)))
 
+    def add_at(self, desc, keyframe_id, global_row_base):
+        """A keyframe whose rows sit at global rows global_row_base.. (shards with scattered keyframes)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        check(lib().aslam_loopdb_add_at(self.h, ptr(d), len(d), int(keyframe_id), int(global_row_base)))
+
     def add_device(self, d_desc, n, keyframe_id):
         check(lib().aslam_loopdb_add_device(self.h, ptr(d_desc), int(n), int(keyframe_id)))
 

@@ -255,6 +255,12 @@ ASLAM_API void aslam_loopdb_destroy(aslam_loopdb *db);
  * aslam_ctx_sync. */
 ASLAM_API int aslam_loopdb_add(aslam_loopdb *db, const uint8_t *desc, int n, uint64_t keyframe_id);
 ASLAM_API int aslam_loopdb_add_device(aslam_loopdb *db, const uint8_t *d_desc, int n, uint64_t keyframe_id);
+/* A shard whose keyframes are NOT contiguous in the global row space (keyframes dealt round-robin to the shards as they
+ * arrive, which is how aslam_loopdb_shard_group places them): this keyframe's rows are global rows global_row_base,
+ * global_row_base + 1, ...  Keyframes must arrive in increasing global order; a database is either built with this call
+ * or with aslam_loopdb_add (contiguous rows from row_base), not both.  Flat queries translate shard rows to global rows
+ * through the keyframe table, so the merged answer of any placement equals the unsharded one. */
+ASLAM_API int aslam_loopdb_add_at(aslam_loopdb *db, const uint8_t *desc, int n, uint64_t keyframe_id, int64_t global_row_base);
 ASLAM_API int aslam_loopdb_clear(aslam_loopdb *db);
 /* Persistence of the keyframe store (the reference keeps it in memory only, LoopClosure.hpp; its H14 notes plan
  * chunked stores): save writes ids, per-keyframe row counts, row_base and the live rows to one file; load

@@ -21,11 +21,19 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def ctx():
-    """One context for the whole GPU session.  Fails loudly if the CUDA library is absent."""
-    from aria_slam_b200._lib import Context
+    """One context for the whole GPU session.  Fails loudly if the CUDA library is absent.
+    Run the suite with ASLAM_B200_LIB=<repo>/aria_slam_b200/libaslam_b200_dbg.so and every staged index of every kernel is
+    checked on the device during ALL GPU tests; the session then fails here if any check tripped."""
+    import ctypes as C
+    from aria_slam_b200._lib import Context, lib
     c = Context(0)
     yield c
+    v = C.c_uint64(0)
+    debug_build = lib().aslam_debug_bounds(C.byref(v))
     c.close()
+    if debug_build:
+        print("\n[aslam] bounds-checking build: %d violations over the session" % v.value)
+        assert v.value == 0, "the debug build counted %d out-of-bounds staged indices" % v.value
 
 
 def kp_keys(k):

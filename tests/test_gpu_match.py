@@ -469,3 +469,54 @@ def test_shard_group_on_one_device_follows_the_single_database(ctx, oracle):
     grp.clear()
     assert grp.num_keyframes == 0 and len(grp.query_segmented(q, 0.7)) == 0
     grp.close(); one.close()
+
+
+def test_round_robin_shards_with_scattered_keyframes_merge_to_the_unsharded_answer(ctx, oracle):
+    """Keyframes dealt round-robin to 3 shards (aslam_loopdb_add_at: a shard's keyframes are scattered over the global row
+    space, as the single-process shard group places them), with evictions: every shard translates its rows through its
+    keyframe table, the merged flat top-2 equals the unsharded database's and the oracle's, including ties between
+    duplicate rows that live on different shards."""
+    import torch
+    from aria_slam_b200.frontend import LoopDB, unpack_top2
+    from aria_slam_b200._lib import lib, check, ptr
+    rs = np.random.RandomState(111)
+    kfs = [rs.randint(0, 256, (rs.randint(40, 700), 32), dtype=np.uint8) for _ in range(23)]
+    kfs[11][:30] = kfs[4][:30]                      # duplicate rows on different shards: (distance, global row) ties
+    kfs[17][5:25] = kfs[4][5:25]
+    nshard = 3
+    shards = [LoopDB(ctx, 2000, 64) for _ in range(nshard)]
+    whole = LoopDB(ctx, 2000, 64)
+    base = 0
+    for i, k in enumerate(kfs):
+        shards[i % nshard].add_at(k, i, base)
+        whole.add(k, i)
+        base += len(k)
+    flat = np.concatenate(kfs)
+    q = np.concatenate([kfs[4][:60], kfs[20][:50], rs.randint(0, 256, (90, 32), dtype=np.uint8)])
+    q[::7, 2] ^= 0x41
+    ridx, rdist = oracle.knn2(q, flat)
+    parts = torch.empty((nshard, len(q), 2), dtype=torch.int64, device="cuda")
+    dq = torch.from_numpy(q).cuda()
+    torch.cuda.synchronize()
+    for s_, sh in enumerate(shards):
+        sh.query_global_device(dq, len(q), parts[s_])
+    out = torch.empty((len(q), 2), dtype=torch.int64, device="cuda")
+    check(lib().aslam_loop_merge_top2_device(ctx.h, ptr(parts), nshard, len(q), ptr(out)))
+    ctx.sync()
+    mrows, mdist = unpack_top2(out.cpu().numpy().view(np.uint64))
+    wrows, wdist = whole.query_global(q)
+    assert (mrows == ridx).all() and (mdist == rdist).all() and (wrows == ridx).all() and (wdist == rdist).all()
+    # per-keyframe counts of the shards, put back in global keyframe order
+    start = np.concatenate([[0], np.cumsum([len(k) for k in kfs])]).astype(np.int32)
+    ref = oracle.loop_segment_counts(q, flat, start, 7, 10)
+    got = np.zeros(len(kfs), np.int32)
+    for s_, sh in enumerate(shards):
+        got[s_::nshard] = sh.query_segmented(q, 0.7)
+    assert (got == ref).all()
+    from aria_slam_b200 import _lib
+    with pytest.raises(_lib.AslamError):
+        whole.add_at(kfs[0], 99, 10**6)             # a contiguous database does not take scattered keyframes
+    with pytest.raises(_lib.AslamError):
+        shards[0].add_at(kfs[0], 99, 5)             # global rows must increase within a shard
+    for d in shards + [whole]:
+        d.close()
