@@ -26,6 +26,7 @@ struct aslam_ctx {
     std::vector<ProfRec> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
     int resize_smem_set = 0;       // resize_smem_kernel's dynamic shared memory opt-in made on this device (bytes)
+    bool knn_pad_set = false;
     bool desc_attr_set = false;    // describe_kernel's dynamic shared memory opt-in was made on this device
     double prof_ms[16] = {0};
     long long prof_n[16] = {0};

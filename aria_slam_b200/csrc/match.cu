@@ -490,9 +490,17 @@ int launch_knn2_partial(aslam_ctx *ctx, const KnnProblem *d_probs, int nprobs, i
     if (merge_div > 1 && !armed)
         ASLAM_CUDA(cudaMemsetAsync(d_partial, 0xff, sizeof(uint2) * (size_t)(nprobs / merge_div) * q_stride, ctx->stream));
     const KnnMul M{2u, 4u, 65536u, 128u};
+    // ASLAM_KNN_SMEM_PAD (A/B runs): unused dynamic shared memory per CTA, to cap the scan's resident CTAs per SM and leave
+    // room for the kernels of other frame streams (3 CTAs per SM fit by registers; 64 KB of padding leaves 2)
+    static const int pad = [] { const char *e = getenv("ASLAM_KNN_SMEM_PAD"); return e ? atoi(e) : 0; }();
+    if (pad > 0 && !ctx->knn_pad_set) {
+        ASLAM_CUDA(cudaFuncSetAttribute(knn2_partial_v2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        ASLAM_CUDA(cudaFuncSetAttribute(knn2_partial_v2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+        ctx->knn_pad_set = true;
+    }
     ProfScope ps(ctx, PK_KNN_PARTIAL);
-    if (csa == 7) knn2_partial_v2_kernel<false, false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div, ExchangeArgs());
-    else knn2_partial_v2_kernel<true, false><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div, ExchangeArgs());
+    if (csa == 7) knn2_partial_v2_kernel<false, false><<<grid, KNN_THREADS, pad, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div, ExchangeArgs());
+    else knn2_partial_v2_kernel<true, false><<<grid, KNN_THREADS, pad, ctx->stream>>>(d_probs, d_partial, q_stride, M, merge_div, ExchangeArgs());
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

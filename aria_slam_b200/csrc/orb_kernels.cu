@@ -1026,11 +1026,10 @@ __device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of
 
 // BUCKET = the grid-bucketed second cull (g.grid_cell > 0), an extension cv::ORB does not have; its definition is
 // in include/aslam_b200.h (aslam_orb_params::grid_cell) and DESIGN.md section 4a.
-#ifndef ASLAM_SEL_MINB
-#define ASLAM_SEL_MINB 1
-#endif
+// (58 registers, 2 CTAs per SM.  Measured: forcing 3 CTAs per SM spills Harris' rows and gains nothing, 0.214 ms either way;
+// 4 CTAs: 0.236; "at least 1" lets the compiler take 119 registers: 0.292.)
 template <bool BUCKET>
-__global__ void __launch_bounds__(SEL_THREADS, ASLAM_SEL_MINB)
+__global__ void __launch_bounds__(SEL_THREADS, 2)
 select_kernel(OrbGeom g, OrbBuffers b)
 {
     __shared__ int hist[256];
