@@ -68,3 +68,12 @@ def test_shard_group_two_devices_in_one_process(ctx, oracle):
     ids, rows, shards = grp.keyframes(with_shards=True)
     assert list(ids) == list(range(25, 40)) and list(shards) == [i % 2 for i in range(25, 40)]
     grp.close(); one.close()
+
+
+def test_sharded_loop_query_between_processes_without_torch():
+    """adapters/shard_ipc_selftest: two processes forked by a CUDA-free parent, CUDA-IPC handles exchanged through pipes, the C
+    ABI only (no torch, no NCCL, no CUDA runtime in the program); every rank's keys equal the unsharded database's."""
+    _two_gpus()
+    exe = os.path.join(ROOT, "aria_slam_b200", "adapters", "shard_ipc_selftest")
+    r = subprocess.run([exe, "2", "120000", "2000", "6"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:]
