@@ -245,7 +245,18 @@ __global__ void __launch_bounds__(256) pipe_bench_kernel(uint32_t *out, int iter
                     a[i] = __vimax3_u16x2(a[i], b, a[(i + 3) & 7]);
                     h[i] = hmax2_bits(h[i], h[(i + 3) & 7]);
                 } else if (WHICH == 6) a[i] = a[i] * b + a[(i + 3) & 7]; // IMAD
-                else a[i] = __byte_perm(a[i], a[(i + 3) & 7], b);        // PRMT
+                else if (WHICH == 7) a[i] = __byte_perm(a[i], a[(i + 3) & 7], b);        // PRMT
+                else if (WHICH == 8) a[i] = __float_as_uint(__fmaf_rn(__uint_as_float(a[i]), __uint_as_float(b), __uint_as_float(a[(i + 3) & 7])));   // FFMA
+                else if (WHICH >= 9 && (i & 1) == 0) {                   // packed f32x2 on register pairs (a[i], a[i+1]): 4 chains
+                    unsigned long long x, y, z;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a[i]), "r"(a[i + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "r"(a[(i + 2) & 7]), "r"(a[(i + 3) & 7]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(z) : "r"(b), "r"(b));
+                    if (WHICH == 9) asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(x), "l"(z), "l"(y));          // FFMA2
+                    else if (WHICH == 10) asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(y));               // FADD2
+                    else asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(z));                              // FMUL2
+                    asm("mov.b64 {%0, %1}, %2;" : "=r"(a[i]), "=r"(a[i + 1]) : "l"(x));
+                }
             }
         }
     }
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(256) pipe_bench_kernel(uint32_t *out, int iter
 extern "C" int aslam_microbench(aslam_ctx *ctx, int which, double *gops)
 {
     ASLAM_REQUIRE(ctx && gops, "NULL argument");
-    ASLAM_REQUIRE(which >= 0 && which <= 7, "which must be 0..7");
+    ASLAM_REQUIRE(which >= 0 && which <= 11, "which must be 0..11");
     ASLAM_CUDA(cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
     uint32_t *d = nullptr;
@@ -277,7 +288,11 @@ extern "C" int aslam_microbench(aslam_ctx *ctx, int which, double *gops)
         case 4: pipe_bench_kernel<4><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
         case 5: pipe_bench_kernel<5><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
         case 6: pipe_bench_kernel<6><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
-        default: pipe_bench_kernel<7><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 7: pipe_bench_kernel<7><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 8: pipe_bench_kernel<8><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 9: pipe_bench_kernel<9><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        case 10: pipe_bench_kernel<10><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
+        default: pipe_bench_kernel<11><<<blocks, threads, 0, ctx->stream>>>(d, iters, 12345u + rep); break;
         }
         ASLAM_LAUNCH_CHECK();
         ASLAM_CUDA(cudaEventRecord(e1, ctx->stream));
@@ -286,6 +301,7 @@ extern "C" int aslam_microbench(aslam_ctx *ctx, int which, double *gops)
         ASLAM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best) best = ms;
     }
+    // kinds 9..11 issue 4 packed instructions (8 lane operations) where the others issue 8 instructions
     double ops = (double)blocks * threads * (double)iters * 32.0 * (which == 5 ? 2.0 : 1.0);
     *gops = ops / (best * 1e-3) * 1e-9;
     cudaEventDestroy(e0);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace aslam {
 
@@ -125,6 +126,28 @@ bool build_orb_geometry(int width, int height, int nfeatures, float scale_factor
             L.ytab_off = (int)tables.size();
             tables.resize(tables.size() + (size_t)(L.h + 3) / 4 * 4, 0);
             resize_row_table(P.h, L.h, tables.data() + L.ytab_off);
+            // strip table of resize_march_kernel: the march walks the source rows s_first, s_first + 1, ... of a strip and
+            // bit i of the mask says "source row s_first + 1 + i is the lower tap of the strip's next output row"
+            static const int env_small = [] { const char *e = getenv("ASLAM_RS_ROWS_SMALL"); return e ? atoi(e) : 0; }();
+            static const int env_big = [] { const char *e = getenv("ASLAM_RS_ROWS_BIG"); return e ? atoi(e) : 0; }();
+            L.rs_rows = (long long)L.w * L.h >= 96 * 1024 ? (env_big > 0 ? env_big : 16) : (env_small > 0 ? env_small : 16);
+            const int nstrips = (L.h + L.rs_rows - 1) / L.rs_rows;
+            L.stab_off = (int)tables.size();
+            tables.resize(tables.size() + (size_t)(2 * nstrips + 3) / 4 * 4, 0);
+            L.rs_fast = 1;
+            for (int st = 0; st < nstrips; ++st) {
+                const uint32_t *yt = tables.data() + L.ytab_off;
+                const int ya = st * L.rs_rows, yb = std::min(ya + L.rs_rows, L.h);
+                const int s_first = (int)(yt[ya] & 0xffffu);
+                uint32_t mask = 0;
+                for (int y = ya; y < yb; ++y) {
+                    const int d = (int)(yt[y] & 0xffffu) - s_first;
+                    if (d < 0 || d >= 32 || (mask >> d & 1u)) { L.rs_fast = 0; break; }
+                    mask |= 1u << d;
+                }
+                tables[(size_t)L.stab_off + 2 * st] = mask;
+                tables[(size_t)L.stab_off + 2 * st + 1] = (uint32_t)s_first;
+            }
         }
     }
     g.pyr_stride = off ? off : 256;

@@ -59,6 +59,9 @@ struct LevelGeom {
     int sel_off, sel_cap;    // rows of this level in the per-frame selection buffer
     int desc_block_off;      // first describe CTA (DESC_WARPS * DESC_KPW keypoints each) of this level within the frame
     int xtab_off, ytab_off;  // resize tables (level l-1 -> l), in uint32 entries
+    int stab_off;            // strip table of the marching resize: 2 words per strip of rs_rows output rows (emit mask, first source row)
+    int rs_rows;             // output rows per strip of the marching resize
+    int rs_fast;             // 1: every strip fits the emit mask (<= 32 source rows, no two output rows with the same upper tap)
     int row_fused_end;       // blur: row-pass columns below this use fused multiply-add
     int col_fused_end;
     float sf;                // scale of the level

@@ -6,6 +6,7 @@
 // is spelled with __fmul_rn/__fadd_rn/__fsub_rn here (nvcc contracts a*b+c by default);
 // cvRound is __float2int_rn (half to even).
 #include <cfloat>
+#include <cstdlib>
 
 #include "orb_kernels.cuh"
 
@@ -183,6 +184,118 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
 #undef ASLAM_RS_EMIT
 }
 
+// ---- round 2, second form: the same march with its control flow taken off the memory system.  resize_kernel decides
+// after every source row whether to emit by comparing against a row-table entry it has just loaded (a global load, two
+// logic instructions and a branch in the loop-carried path, and ~13 instructions of pointer upkeep per emitted row).  Here
+// the emit decisions of a strip are one 32-bit mask built on the host (LevelGeom::stab_off: bit i = "source row
+// s_first + 1 + i is the lower tap of the next output row"), the weight of the next output row is fetched right after the
+// previous emit, and the loop ends with the mask.  Levels whose strips do not fit the mask (rs_fast == 0: more than 32
+// source rows per strip, or two output rows with the same upper tap) keep resize_kernel.
+// MEASURED SLOWER and therefore off by default (ASLAM_RS_MARCH=0): 26 % fewer executed instructions (32.2 M -> 23.7 M warp
+// instructions on level 1) but 0.189 ms per 256 frames against 0.176 (0.198 with two frames per thread, 0.187 / 0.225 /
+// 0.240 with 6 / 8 / 12 source rows in flight, 0.213 with the mask in ordinary registers).  ncu, level 1, two frames per
+// thread: issue-active 43 % instead of 77 %, long-scoreboard stall 8.6 instead of 4.4 warps per issue, achieved occupancy
+// 34 % instead of 57 % -- the pass is bound by the latency of its DRAM reads (L2 hit rate 18 %), and the instructions that
+// were removed had been issuing in that shadow (profiles/r02_resize_march_ncu.csv).
+// NF frames per thread (same column group, same strip): the tables, the emit decisions, the weights and the address
+// arithmetic are shared, and the frames' independent loads and multiplies fill each other's latencies.
+#ifndef ASLAM_RM_NF
+#define ASLAM_RM_NF 1
+#endif
+#ifndef ASLAM_RM_DEPTH
+#define ASLAM_RM_DEPTH 8        // source rows in flight per thread and frame (even)
+#endif
+#ifndef ASLAM_RM_VMASK
+#define ASLAM_RM_VMASK 0
+#endif
+template <bool THRESH, int NF, int DEPTH>
+__global__ void __launch_bounds__(256)
+resize_march_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
+                    LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs, int nframes)
+{
+    static_assert(DEPTH >= 2 && DEPTH % 2 == 0, "the two horizontal results alternate");
+    const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * D.rs_rows;
+    if (cg * 4 >= D.w) return;
+    // frame f of this thread; a batch that is not a multiple of NF repeats its last frame (same bytes written twice)
+    const uint32_t *src[NF];
+    uint32_t *dp[NF];
+    const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
+    const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
+    // (ASLAM_RM_VMASK: fetch the CTA-uniform mask through an address ptxas cannot prove uniform, so that it is tested in
+    // ordinary registers instead of on the uniform datapath -- measured slower, 0.213 vs 0.189 ms)
+    const uint2 st = __ldg(reinterpret_cast<const uint2 *>(tabs + D.stab_off) + blockIdx.y + (ASLAM_RM_VMASK ? (cg >> 28) : 0));
+    uint32_t mask = st.x;
+    const uint32_t pw = (uint32_t)S.pitch >> 2, dpw = (uint32_t)D.pitch >> 2;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const int z = min((int)blockIdx.z * NF + f, nframes - 1);
+        unsigned long long sb = reinterpret_cast<unsigned long long>(srcb + (size_t)z * stride + S.off);
+        unsigned long long db = reinterpret_cast<unsigned long long>(dstb + (size_t)z * stride + D.off);
+        asm volatile("" : "+l"(sb), "+l"(db));
+        src[f] = reinterpret_cast<const uint32_t *>(sb);
+        dp[f] = reinterpret_cast<uint32_t *>(db) + ((size_t)y0 * dpw + (size_t)cg);
+    }
+    const uint32_t so_last = t0.x + (uint32_t)(S.h - 1) * pw;     // window offset in the last source row
+    uint32_t so = t0.x + st.y * pw;
+    uint32_t raw[DEPTH][NF][3];                                   // raw words of the next DEPTH source rows, per frame
+    int rows_left = 33 - __clz((int)st.x);                        // the strip reads source rows s_first .. s_first + 1 + highest mask bit
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            raw[j][f][0] = raw[j][f][1] = raw[j][f][2] = 0u;
+            if (rows_left > 0) { raw[j][f][0] = __ldg(src[f] + so); raw[j][f][1] = __ldg(src[f] + so + 1); raw[j][f][2] = __ldg(src[f] + so + 2); }
+        }
+        --rows_left;
+        if (j + 1 < DEPTH) so = min(so + pw, so_last);
+    }
+    uint32_t yi = (uint32_t)(D.ytab_off + y0);
+    uint32_t e = __ldg(tabs + yi);                                // weight word of the next output row
+    uint32_t doff = 0;                                            // words from dp[f] to the next output row
+    HRow h[2][NF];
+    // source row j of the ring through the horizontal pass into h[j & 1]; its registers take the row DEPTH further on
+    auto hrow = [&](int j) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) h[j & 1][f] = resize_hrow(raw[j][f][0], raw[j][f][1], raw[j][f][2], t0, t1);
+        so = min(so + pw, so_last);
+        ASLAM_BOUNDS((size_t)(so + 3) * 4 <= (size_t)S.pitch * S.h + 256);
+        if (rows_left > 0) {                                       // (CTA-uniform) no loads past the strip's last source row
+#pragma unroll
+            for (int f = 0; f < NF; ++f) { raw[j][f][0] = __ldg(src[f] + so); raw[j][f][1] = __ldg(src[f] + so + 1); raw[j][f][2] = __ldg(src[f] + so + 2); }
+        }
+        --rows_left;
+    };
+    hrow(0);
+#pragma unroll 1
+    for (;;) {
+#pragma unroll
+        for (int jj = 1; jj <= DEPTH; ++jj) {
+            const int j = jj % DEPTH;                              // rows 1 .. DEPTH-1, then 0 again
+            hrow(j);
+            if (mask & 1u) {                                       // row j is the lower tap of the next output row
+                const uint32_t wy1 = e >> 16, wy0 = 256u - wy1;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i] = h[j & 1][f].h[i] * wy1 + (h[(j & 1) ^ 1][f].h[i] * wy0 + 32768u);     // 16.16, byte 2 = rounded pixel
+                        if (THRESH && (v[i] >> 16) <= 254u) v[i] = 0;                              // mask levels: threshold(254, TOZERO)
+                    }
+                    const uint32_t p01 = __byte_perm(v[0], v[1], 0x0062), p23 = __byte_perm(v[2], v[3], 0x0062);
+                    ASLAM_BOUNDS((size_t)y0 * dpw + cg + doff < (size_t)dpw * D.h);
+                    dp[f][doff] = __byte_perm(p01, p23, 0x5410);
+                }
+                if (mask == 1u) return;
+                doff += dpw;
+                e = __ldg(tabs + ++yi);
+            }
+            mask >>= 1;
+        }
+    }
+}
+
 // ---- shared-memory form (the shipped kernel).  One CTA = a strip of RS_ROWS output rows over the level's full width.
 // The source rows the strip needs (about 1.2 * RS_ROWS + 2 of them) arrive by bulk asynchronous copies -- one
 // cp.async.bulk per row, issued by the first lanes of the CTA, completion on an mbarrier -- so every source byte crosses
@@ -277,6 +390,9 @@ resize_smem_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
 // Measured on B200 (ms per 256 frames, all 7 levels): direct loads with 4 source rows in flight 0.176 (2 rows: 0.189); source
 // rows staged in shared memory by bulk asynchronous copies (resize_smem_kernel) 0.184 with 16-row strips, 0.185 with 8,
 // 0.197 with 32, 0.191 when the rows arrive in groups on several barriers.
+#ifndef ASLAM_RS_MARCH
+#define ASLAM_RS_MARCH 0        // 1: resize_march_kernel (host-built emit masks) wherever a level's strips fit it -- measured slower, see there
+#endif
 #ifndef ASLAM_RS_SMEM
 #define ASLAM_RS_SMEM 0         // 1: the staged form (kept for A/B runs and for GPUs where it wins); 0: direct loads
 #endif
@@ -305,6 +421,23 @@ int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, i
     }
 #endif
     const int warps = min(8, (cgs + 31) / 32);
+#if ASLAM_RS_MARCH
+    if (D.rs_fast) {
+        // several frames per thread only once there are enough of them to fill the GPU anyway
+        const int nf = nframes >= 16 ? ASLAM_RM_NF : 1;
+        dim3 grid((cgs + 32 * warps - 1) / (32 * warps), (D.h + D.rs_rows - 1) / D.rs_rows, (nframes + nf - 1) / nf), block(32 * warps);
+        ProfScope ps(ctx, PK_RESIZE);
+        if (nf == 1) {
+            if (is_mask) resize_march_kernel<true, 1, ASLAM_RM_DEPTH><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, nframes);
+            else resize_march_kernel<false, 1, ASLAM_RM_DEPTH><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, nframes);
+        } else {
+            if (is_mask) resize_march_kernel<true, ASLAM_RM_NF, ASLAM_RM_DEPTH><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, nframes);
+            else resize_march_kernel<false, ASLAM_RM_NF, ASLAM_RM_DEPTH><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs, nframes);
+        }
+        ASLAM_LAUNCH_CHECK();
+        return ASLAM_OK;
+    }
+#endif
     dim3 grid((cgs + 32 * warps - 1) / (32 * warps), (D.h + RS_ROWS - 1) / RS_ROWS, nframes), block(32 * warps);
     ProfScope ps(ctx, PK_RESIZE);
     if (is_mask) resize_kernel<true><<<grid, block, 0, ctx->stream>>>(base, base, g.pyr_stride, S, D, b.tabs);
@@ -900,16 +1033,293 @@ blur_kernel(OrbGeom g, OrbBuffers b, BlurTaps T)
     }
 }
 
+// ---- round 2: the blur as a register march (the shipped kernel; blur_kernel above stays for A/B runs, ASLAM_BLUR_MARCH=0).
+// One thread = 4 adjacent columns of a strip of rows, marched top to bottom two rows per step; nothing goes through
+// shared memory.  Per step a thread
+//   * reads the three aligned words around its columns in two source rows (the loads of the NEXT step are issued first),
+//     patches them at the image's left/right border with per-thread PRMT selectors (BORDER_REFLECT_101; identity selectors
+//     in the interior, so the instruction stream is the same for every thread),
+//   * converts 10 bytes per row with the exponent trick and runs the 7 row taps on packed f32x2 lanes, lane .x = the
+//     upper row, .y = the lower one: P = (R[2m], R[2m+1]) for each of its 4 columns,
+//   * keeps the last four P and the three "odd" pairs Q = (R[2m-1], R[2m]) (two register moves per column and step), which
+//     are exactly the operands of the column pass for the output rows centred on R[2m-3] and R[2m-2]:
+//       K3*Q[m-1] + K2*(P[m-2] + P[m-1]) + K1*(Q[m-2] + Q[m]) + K0*(P[m-3] + P[m]),
+//     again on packed lanes (.x = upper output row, .y = lower) -- 8 packed instructions per column for two pixels,
+//   * rounds by the 1.5*2^23 trick, packs 4 pixels per row with 3 PRMTs and stores one word per row.
+// The rings of P and Q are register names rotated by unrolling the march four steps.  Threads of the unfused column tail
+// (x >= row_fused_end / col_fused_end, the split of the cv2 build) take product-then-sum forms that are still packed:
+// s = fma(fmul(k, v), ONE, s) with ONE = 1.0f arriving as a kernel parameter rounds the product first and ptxas cannot
+// contract it.  ~130 instructions per 8 pixels against ~270 in blur_kernel; the FMA pipe (70 packed instructions per step
+// at one per two cycles) is the floor.
+struct BlurPlan {
+    int cta_off[ORB_MAX_LEVELS + 1];   // first CTA of each level within a frame
+    int strip_h[ORB_MAX_LEVELS];       // rows per strip (even)
+    int nstrips[ORB_MAX_LEVELS];
+};
+struct BlurTapsM { float k[4]; float one; };
+constexpr int BM_THREADS = 128;
+
+// Packed f32x2 values live in 64-bit registers from birth to death (inline PTX with "l" operands): held as float2 the
+// halves are two 32-bit values to the register allocator, which then assembles an aligned pair with MOVs for every packed
+// operand that crosses a step of the march (measured: 39 MOVs per step, 18 % of the executed instructions).
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk_make(uint32_t lo, uint32_t hi) { pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ pk2 pk_dup(float v) { return pk_make(__float_as_uint(v), __float_as_uint(v)); }
+__device__ __forceinline__ uint32_t pk_lo(pk2 v) { [[maybe_unused]] uint32_t lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ uint32_t pk_hi(pk2 v) { [[maybe_unused]] uint32_t lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) { pk2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// round(k*v) first, then round(. + s): ONE = 1.0f arrives as a kernel parameter, so ptxas cannot contract the pair
+__device__ __forceinline__ pk2 pk_fma_unfused(pk2 k, pk2 v, pk2 s, pk2 one) { return pk_fma(pk_mul(k, v), one, s); }
+
+#ifndef ASLAM_BM_DEPTH
+#define ASLAM_BM_DEPTH 2        // source-row pairs in flight per thread (1, 2 or 4: the ring must divide the 4-step unrolling)
+#endif
+#ifndef ASLAM_BM_PF
+#define ASLAM_BM_PF 0           // > 0: also prefetch the rows of step m + PF into L2
+#endif
+constexpr int BM_DEPTH = ASLAM_BM_DEPTH;
+static_assert(BM_DEPTH == 1 || BM_DEPTH == 2 || BM_DEPTH == 4, "blur march prefetch depth");
+struct BlurMarch {
+    pk2 P[4][4], Q[4][4];              // [ring slot][column]
+    uint32_t wa[BM_DEPTH][3], wb[BM_DEPTH][3];     // words of the two source rows of steps m .. m + BM_DEPTH - 1 (slot = step % BM_DEPTH)
+    const uint8_t *col;                // level base + x0 (frame's pyramid)
+    uint8_t *dp;                       // destination of the next output row pair
+    int h, pitch, two_h_m2;
+    uint32_t selL, selM, selR1, selR2;
+    bool not_left, row_unf, col_unf;
+    pk2 K0, K1, K2, K3, ONE;
+
+    __device__ __forceinline__ const uint8_t *row_ptr(int v) const
+    {
+        int a = abs(v);
+        a = max(min(a, two_h_m2 - a), 0);               // BORDER_REFLECT_101 (rows past 2h-2 belong to no output)
+        ASLAM_BOUNDS(a >= 0 && a < h);
+        return col + (unsigned long long)(unsigned)a * (unsigned)pitch;
+    }
+    __device__ __forceinline__ void load(int v, uint32_t (&w)[3]) const
+    {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row_ptr(v));
+        if (not_left) w[0] = __ldg(p - 1);
+        w[1] = __ldg(p);
+        w[2] = __ldg(p + 1);
+    }
+    __device__ __forceinline__ void prefetch_l2(int v) const
+    {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr(v)));
+    }
+};
+
+template <int SLOT, bool OUT>
+__device__ __forceinline__ void blur_march_step(BlurMarch &S, int v_next, int y_out)
+{
+    // borders: l' = columns x0-4..x0-1, m' = x0..x0+3, r' = x0+4..x0+7 after reflection (identity in the interior)
+    constexpr int WS = SLOT % BM_DEPTH;
+    pk2 v[10];
+    {
+        uint32_t (&wa)[3] = S.wa[WS], (&wb)[3] = S.wb[WS];
+        const uint32_t la = __byte_perm(wa[0], wa[1], S.selL), lb = __byte_perm(wb[0], wb[1], S.selL);
+        const uint32_t ma = __byte_perm(wa[1], wa[0], S.selM), mb = __byte_perm(wb[1], wb[0], S.selM);
+        const uint32_t ra = __byte_perm(__byte_perm(wa[2], wa[1], S.selR1), wa[0], S.selR2);
+        const uint32_t rb = __byte_perm(__byte_perm(wb[2], wb[1], S.selR1), wb[0], S.selR2);
+        // the words are consumed: their registers take the rows of step m + BM_DEPTH, whose latency hides behind the
+        // arithmetic of BM_DEPTH steps
+        S.load(v_next, wa);
+        S.load(v_next + 1, wb);
+#if ASLAM_BM_PF > 0
+        S.prefetch_l2(v_next + 2 * (ASLAM_BM_PF - BM_DEPTH));
+        S.prefetch_l2(v_next + 2 * (ASLAM_BM_PF - BM_DEPTH) + 1);
+#endif
+        const uint32_t A[3] = {la, ma, ra}, B[3] = {lb, mb, rb};
+        const pk2 M = pk_dup(-8388608.0f);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const int byte = k + 1;                     // v[k] = column x0 - 3 + k = byte k + 1 of the 12-byte window
+            v[k] = pk_add(pk_make(u8_magic(A[byte >> 2], byte & 3), u8_magic(B[byte >> 2], byte & 3)), M);
+        }
+    }
+    // row pass -> P[SLOT]
+    if (!S.row_unf) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            pk2 s = pk_mul(S.K0, v[o]);
+            s = pk_fma(S.K1, v[o + 1], s);
+            s = pk_fma(S.K2, v[o + 2], s);
+            s = pk_fma(S.K3, v[o + 3], s);
+            s = pk_fma(S.K2, v[o + 4], s);
+            s = pk_fma(S.K1, v[o + 5], s);
+            s = pk_fma(S.K0, v[o + 6], s);
+            S.P[SLOT][o] = s;
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            pk2 s = pk_mul(S.K0, v[o]);
+            s = pk_fma_unfused(S.K1, v[o + 1], s, S.ONE);
+            s = pk_fma_unfused(S.K2, v[o + 2], s, S.ONE);
+            s = pk_fma_unfused(S.K3, v[o + 3], s, S.ONE);
+            s = pk_fma_unfused(S.K2, v[o + 4], s, S.ONE);
+            s = pk_fma_unfused(S.K1, v[o + 5], s, S.ONE);
+            s = pk_fma_unfused(S.K0, v[o + 6], s, S.ONE);
+            S.P[SLOT][o] = s;
+        }
+    }
+    constexpr int S1 = (SLOT + 1) & 3, S2 = (SLOT + 2) & 3, S3 = (SLOT + 3) & 3;     // steps m-3, m-2, m-1
+#pragma unroll
+    for (int o = 0; o < 4; ++o) S.Q[SLOT][o] = pk_make(pk_hi(S.P[S3][o]), pk_lo(S.P[SLOT][o]));       // (R[2m-1], R[2m])
+
+    if (OUT) {
+        uint32_t bx[4], by[4];
+        const pk2 MG = pk_dup(12582912.0f);
+        if (!S.col_unf) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                pk2 s = pk_mul(S.K3, S.Q[S3][o]);
+                s = pk_fma(S.K2, pk_add(S.P[S3][o], S.P[S2][o]), s);
+                s = pk_fma(S.K1, pk_add(S.Q[SLOT][o], S.Q[S2][o]), s);
+                s = pk_fma(S.K0, pk_add(S.P[SLOT][o], S.P[S1][o]), s);
+                s = pk_add(s, MG);
+                bx[o] = pk_lo(s); by[o] = pk_hi(s);
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                pk2 s = pk_mul(S.K3, S.Q[S3][o]);
+                s = pk_fma_unfused(S.K2, pk_add(S.P[S3][o], S.P[S2][o]), s, S.ONE);
+                s = pk_fma_unfused(S.K1, pk_add(S.Q[SLOT][o], S.Q[S2][o]), s, S.ONE);
+                s = pk_fma_unfused(S.K0, pk_add(S.P[SLOT][o], S.P[S1][o]), s, S.ONE);
+                s = pk_add(s, MG);
+                bx[o] = pk_lo(s); by[o] = pk_hi(s);
+            }
+        }
+        if (y_out < S.h) {
+            ASLAM_BOUNDS(y_out >= 0);
+            *reinterpret_cast<uint32_t *>(S.dp) = __byte_perm(__byte_perm(bx[0], bx[1], 0x0040), __byte_perm(bx[2], bx[3], 0x0040), 0x5410);
+            if (y_out + 1 < S.h)
+                *reinterpret_cast<uint32_t *>(S.dp + S.pitch) = __byte_perm(__byte_perm(by[0], by[1], 0x0040), __byte_perm(by[2], by[3], 0x0040), 0x5410);
+        }
+        S.dp += 2 * (size_t)S.pitch;
+    }
+}
+
+#ifndef ASLAM_BM_MINB
+#define ASLAM_BM_MINB 5         // 96 registers (8 bytes of spill) and 20 warps per SM: 0.369 ms; 4 (120 registers, 16 warps): 0.380; 3: 0.380
+#endif
+__global__ void __launch_bounds__(BM_THREADS, ASLAM_BM_MINB)
+blur_march_kernel(OrbGeom g, OrbBuffers b, BlurTapsM T, BlurPlan plan)
+{
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ORB_MAX_LEVELS; ++i)
+        if (i < g.nbuilt && (int)blockIdx.x >= plan.cta_off[i]) l = i;
+    const LevelGeom L = g.lv[l];
+    const int ncg = (L.w + 3) >> 2;                                   // column groups per row
+    const int t = ((int)blockIdx.x - plan.cta_off[l]) * BM_THREADS + (int)threadIdx.x;
+    const int strip = t / ncg, x0 = (t - strip * ncg) * 4;
+    if (strip >= plan.nstrips[l]) return;
+    const int hs = plan.strip_h[l], ys = strip * hs;
+    const int nsteps = hs / 2 + 3;                                    // steps m = 0 .. hs/2 + 2; outputs from m = 3
+
+    BlurMarch S;
+    S.h = L.h; S.pitch = L.pitch; S.two_h_m2 = 2 * L.h - 2;
+    S.col = b.pyr + (size_t)blockIdx.y * g.pyr_stride + L.off + x0;
+    S.dp = b.blur + (size_t)blockIdx.y * g.pyr_stride + L.off + (size_t)ys * L.pitch + x0;
+    S.not_left = x0 != 0;
+    S.row_unf = x0 >= L.row_fused_end;
+    S.col_unf = x0 >= L.col_fused_end;
+    S.K0 = pk_dup(T.k[0]); S.K1 = pk_dup(T.k[1]); S.K2 = pk_dup(T.k[2]); S.K3 = pk_dup(T.k[3]);
+    S.ONE = pk_dup(T.one);
+    // border selectors.  Window byte j (j = 0..11) is column x0 - 4 + j; the pixel wanted there is reflect101 of it.
+    {
+        S.selL = x0 == 0 ? 0x5670u : 0x3210u;                         // columns -3, -2, -1 -> 3, 2, 1 (all in m)
+        const int d = L.w - x0;                                       // columns x0 + j, j >= d, lie right of the image
+        uint32_t sm = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int jj = j < d ? j : 2 * d - 2 - j;                       // source column relative to x0
+            jj = max(jj, -4);
+            if (j < 4) {                                              // m' = PRMT(m, l): m = bytes 0..3, l = bytes 4..7
+                sm |= (uint32_t)(jj >= 0 ? jj : 8 + jj) << (4 * j);
+            } else {                                                  // t = PRMT(r, m): r = 0..3, m = 4..7; r' = PRMT(t, l)
+                const int q = j - 4;
+                s1 |= (uint32_t)(jj >= 4 ? jj - 4 : jj >= 0 ? 4 + jj : 0) << (4 * q);
+                s2 |= (uint32_t)(jj >= 0 ? q : 8 + jj) << (4 * q);
+            }
+        }
+        S.selM = sm; S.selR1 = s1; S.selR2 = s2;
+    }
+#pragma unroll
+    for (int d = 0; d < BM_DEPTH; ++d) {
+        S.wa[d][0] = S.wb[d][0] = 0u;
+        S.load(ys - 3 + 2 * d, S.wa[d]);
+        S.load(ys - 2 + 2 * d, S.wb[d]);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { S.P[s][o] = 0ull; S.Q[s][o] = 0ull; }
+
+    // step m reads virtual rows ys - 3 + 2m, + 1 (fetched by step m - BM_DEPTH), fetches those of step m + BM_DEPTH and
+    // writes rows ys + 2m - 6, + 1
+    constexpr int VN = 2 * BM_DEPTH - 3;
+    blur_march_step<0, false>(S, ys + VN, 0);
+    blur_march_step<1, false>(S, ys + VN + 2, 0);
+    blur_march_step<2, false>(S, ys + VN + 4, 0);
+    int m = 3;
+#pragma unroll 1
+    for (;;) {
+        blur_march_step<3, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+        blur_march_step<0, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+        blur_march_step<1, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+        blur_march_step<2, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+    }
+}
+
+#ifndef ASLAM_BLUR_MARCH
+#define ASLAM_BLUR_MARCH 1      // 1: blur_march_kernel (registers only); 0: round 1's shared-memory tiles
+#endif
 int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
 {
     if (g.blur_tiles_per_frame == 0) return ASLAM_OK;
-    BlurTaps T;
     double t[7], sum = 0;
     for (int i = 0; i < 7; ++i) { const double x = i - 3; t[i] = exp(-0.125 * x * x); sum += t[i]; }
+#if ASLAM_BLUR_MARCH
+    BlurTapsM T;
+    for (int i = 0; i < 4; ++i) T.k[i] = (float)(t[i] / sum);
+    T.one = 1.0f;
+    // strips: tall for big batches (6 halo rows per strip), short when a few frames must still fill 148 SMs
+    static const int env_h = [] { const char *e = getenv("ASLAM_BLUR_STRIP"); return e ? atoi(e) : 0; }();
+    const int hmax = env_h > 0 ? env_h : nframes >= 32 ? 64 : nframes >= 8 ? 32 : 16;
+    BlurPlan plan;
+    int cta = 0;
+    for (int l = 0; l < ORB_MAX_LEVELS; ++l) {
+        plan.cta_off[l] = cta;
+        plan.strip_h[l] = 2; plan.nstrips[l] = 0;
+        if (l >= g.nbuilt) continue;
+        const LevelGeom &L = g.lv[l];
+        const int ns = (L.h + hmax - 1) / hmax;
+        const int hs = ((L.h + ns - 1) / ns + 1) & ~1;
+        plan.nstrips[l] = (L.h + hs - 1) / hs;
+        plan.strip_h[l] = hs;
+        const long long threads = (long long)((L.w + 3) / 4) * plan.nstrips[l];
+        cta += (int)((threads + BM_THREADS - 1) / BM_THREADS);
+    }
+    plan.cta_off[ORB_MAX_LEVELS] = cta;
+    dim3 grid(cta, nframes);
+    ProfScope ps(ctx, PK_BLUR);
+    blur_march_kernel<<<grid, BM_THREADS, 0, ctx->stream>>>(g, b, T, plan);
+#else
+    BlurTaps T;
     for (int i = 0; i < 4; ++i) T.k[i] = (float)(t[i] / sum);
     dim3 grid(g.blur_tiles_per_frame, nframes);
     ProfScope ps(ctx, PK_BLUR);
     blur_kernel<<<grid, 256, 0, ctx->stream>>>(g, b, T);
+#endif
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

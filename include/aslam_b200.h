@@ -378,7 +378,8 @@ ASLAM_API int aslam_loopdb_shard_group_match_keyframe(aslam_loopdb_group *g, int
  * Measured integer-pipe ceilings used as roofline denominators for the matching kernel
  * (SURVEY.md 8d asks for the POPC rate to be measured, not assumed).  which: 0 = POPC,
  * 1 = LOP3, 2 = IADD3, 3 = VIMNMX3.U16x2, 4 = HMNMX2, 5 = VIMNMX3.U16x2 + HMNMX2 interleaved,
- * 6 = IMAD, 7 = PRMT.  Returns giga warp-lane operations per second. */
+ * 6 = IMAD, 7 = PRMT, 8 = FFMA, 9 = FFMA2, 10 = FADD2, 11 = FMUL2 (packed f32x2: two lane operations per
+ * instruction and lane; the blur's floor).  Returns giga warp-lane operations per second. */
 ASLAM_API int aslam_microbench(aslam_ctx *ctx, int which, double *gops);
 
 #ifdef __cplusplus

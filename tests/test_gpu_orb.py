@@ -54,7 +54,34 @@ def test_pyramid_levels_bit_exact(ctx, oracle, w, h, seed):
     tr.close()
 
 
-@pytest.mark.parametrize("w,h,seed", [(752, 480, 1), (401, 300, 5)])
+@pytest.mark.parametrize("w,h,batch", [(752, 480, 17), (333, 257, 16), (161, 203, 33)])
+def test_pyramid_levels_bit_exact_in_batches(ctx, oracle, w, h, batch):
+    """Batches of 16 frames or more go through the resize two frames per thread (an odd batch repeats its last frame):
+    every level of the first, a middle and the last frame against the oracle, with a mask pyramid alongside."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import OrbBatchTracker
+    imgs = np.stack([synth.frame(w, h, 70 + i) for i in range(3)])
+    frames = np.ascontiguousarray(imgs[np.arange(batch) % 3])
+    m, _ = synth.mask_and_boxes(w, h, seed=5)
+    masks = np.ascontiguousarray(np.broadcast_to(m, frames.shape))
+    tr = OrbBatchTracker(w, h, 500, batch, ctx)
+    tr.extract_async(frames, masks=masks)
+    kps, desc, cnt, _, _ = tr.results()
+    for f in sorted({0, batch // 2, batch - 1}):
+        ref = oracle.pyramid(frames[f])
+        for l in range(8):
+            if min(ref[l].shape) <= 62:
+                continue
+            got = tr.read_level(f, l)
+            assert got.shape == ref[l].shape and (got == ref[l]).all(), "frame %d level %d differs" % (f, l)
+    # the masked extraction equals the oracle's on the last frame (the mask levels are thresholded resizes)
+    ko, do = oracle.orb(frames[batch - 1], 500, mask=m)
+    n = int(cnt[batch - 1])
+    assert set(kp_keys(kps[batch - 1][:n])) == set(kp_keys(ko))
+    tr.close()
+
+
+@pytest.mark.parametrize("w,h,seed", [(752, 480, 1), (401, 300, 5), (333, 257, 9), (130, 97, 2), (70, 200, 3), (1408, 1408, 8)])
 def test_blurred_levels_match_oracle(ctx, oracle, w, h, seed):
     from aria_slam_b200 import synth
     img = synth.frame(w, h, seed)
@@ -69,7 +96,32 @@ def test_blurred_levels_match_oracle(ctx, oracle, w, h, seed):
         got = tr.read_level(0, l, blurred=True)
         ref = oracle.blur7(pyr[l])
         bad += int((got != ref).sum()); tot += ref.size
-    assert bad == 0, "%d of %d blurred pixels differ" % (bad, tot)
+    assert tot > 0 and bad == 0, "%d of %d blurred pixels differ" % (bad, tot)
+    tr.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("batch", [1, 8, 32])
+def test_blurred_levels_every_fma_split_and_strip_height(ctx, oracle, mode, batch):
+    """The marching blur picks its strip height from the batch size (16 / 32 / 64 rows) and has packed product-then-sum
+    forms for the unfused column tail: all three blur modes (never / always / the cv2 build's split) against the oracle,
+    first and last frame of the batch."""
+    from aria_slam_b200 import synth
+    from aria_slam_b200.frontend import OrbBatchTracker
+    w, h = 333, 257
+    imgs = np.stack([synth.frame(w, h, 40 + i) for i in range(2)])
+    frames = np.ascontiguousarray(imgs[np.arange(batch) % 2])
+    tr = OrbBatchTracker(w, h, 500, batch, ctx, blur_mode=mode)
+    tr.extract_async(frames)
+    tr.sync()
+    for f in sorted({0, batch - 1}):
+        pyr = oracle.pyramid(frames[f])
+        for l in range(8):
+            if min(pyr[l].shape) <= 62:
+                continue
+            got = tr.read_level(f, l, blurred=True)
+            ref = oracle.blur7(pyr[l], mode)
+            assert (got == ref).all(), "mode %d batch %d frame %d level %d: %d pixels differ" % (mode, batch, f, l, int((got != ref).sum()))
     tr.close()
 
 
