@@ -504,6 +504,9 @@ __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { r
 #ifndef ASLAM_FAST_COMPACT
 #define ASLAM_FAST_COMPACT 1
 #endif
+#ifndef ASLAM_FAST_NET
+#define ASLAM_FAST_NET 1     // 1: the 72-instruction score network (shared eight-pixel windows); 0: round 1's 80
+#endif
 struct FastMul { uint32_t one, minus1, bias; };      // 1, 0xffffffff, 0x01000100
 
 __device__ __forceinline__ uint32_t imad32(uint32_t a, uint32_t b, uint32_t c)
@@ -528,6 +531,30 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*A)[FA_PITCH
     v[14] = ring_pair<-2, 2>(A, Bc, r, gp);  v[15] = ring_pair<-1, 3>(A, Bc, r, gp);
     const uint32_t c = ring_pair<0, 0>(A, Bc, r, gp);
 
+#if ASLAM_FAST_NET == 1
+    // 72 min/max instead of 80.  The arcs starting at 2j and 2j+1 share the eight pixels 2j+1 .. 2j+8 (W) and differ in
+    // one end pixel: max(min(W, v[2j]), min(W, v[2j+9])) = min(W, max(v[2j], v[2j+9])) -- the form of cv::cornerScore's
+    // loop -- and W is two of the eight 4-windows that start at odd pixels, each two of the eight odd-aligned pairs.
+    uint32_t plo[8], phi[8], qlo[8], qhi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        plo[j] = __vminu2(v[(2 * j + 1) & 15], v[(2 * j + 2) & 15]);
+        phi[j] = __vmaxu2(v[(2 * j + 1) & 15], v[(2 * j + 2) & 15]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        qlo[j] = __vminu2(plo[j], plo[(j + 1) & 7]);
+        qhi[j] = __vmaxu2(phi[j], phi[(j + 1) & 7]);
+    }
+    uint32_t rmin[8], rmax[8];      // rmin[j] = max over the arcs starting at 2j, 2j+1 of the arc's minimum; rmax alike
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        rmin[j] = min3(qlo[j], qlo[(j + 2) & 7], __vmaxu2(v[2 * j], v[(2 * j + 9) & 15]));
+        rmax[j] = max3(qhi[j], qhi[(j + 2) & 7], __vminu2(v[2 * j], v[(2 * j + 9) & 15]));
+    }
+    const uint32_t mx = __vmaxu2(max3(max3(rmin[0], rmin[1], rmin[2]), max3(rmin[3], rmin[4], rmin[5]), rmin[6]), rmin[7]);
+    const uint32_t mn = __vminu2(min3(min3(rmax[0], rmax[1], rmax[2]), min3(rmax[3], rmax[4], rmax[5]), rmax[6]), rmax[7]);
+#else
     uint32_t hi3[16], lo3[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -548,6 +575,8 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*A)[FA_PITCH
                        max3(arc_min[6], arc_min[7], arc_min[8]));
     mx = max3(mx, max3(arc_min[9], arc_min[10], arc_min[11]), max3(arc_min[12], arc_min[13], arc_min[14]));
     mx = __vmaxu2(mx, arc_min[15]);
+
+#endif
 
     // per u16 lane: s = max(c - mn, mx - c); result = max(s - t, 0).  The two differences are taken with a
     // +256 bias per lane (no borrow between lanes: every lane stays in [1, 511]) as 32-bit IMADs whose
@@ -1332,9 +1361,50 @@ int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfram
 constexpr int SEL_THREADS = 512;
 
 // HarrisResponses(blockSize 7, k 0.04f): integer sums, then a fixed unfused float expression.
+#ifndef ASLAM_HARRIS_DP4A
+#define ASLAM_HARRIS_DP4A 1     // 1: rows by three aligned word loads, Sobel sums by DP4A; 0: round 1's 81 byte loads
+#endif
+__device__ __forceinline__ int dp4a_px(uint32_t px, uint32_t w, int c)       // unsigned pixels x signed weights
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(w), "r"(c));
+    return d;
+}
 __device__ __forceinline__ float harris_response(const uint8_t *__restrict__ img, int pitch, int x, int y)
 {
     int a = 0, b = 0, c = 0;
+#if ASLAM_HARRIS_DP4A
+    // The 9 x 9 window (columns x-4 .. x+4) as, per row, the seven words win[k] = columns x-4+k .. x-1+k (k = 0..6):
+    // three aligned loads (rows are 16-byte padded, so the third word lies inside the row whenever x+4 does), three
+    // funnel shifts by the window's byte offset, five more by constants.  Sobel x / y at window column i = k+1 are dot
+    // products of win[k] of the three rows with (-1,0,1,0) / (-2,0,2,0) and (-1,-2,-1,0) / (1,2,1,0): exact integers.
+    const int xs = x - 4, sh = (xs & 3) * 8;
+    const uint8_t *p = img + (size_t)(y - 4) * pitch + (xs & ~3);
+    constexpr uint32_t WX1 = 0x000100ffu, WX2 = 0x000200feu, WY0 = 0x00fffeffu, WY2 = 0x00010201u;
+    uint32_t r0[7], r1[7], r2[7];
+    auto load_row = [&](int j, uint32_t (&win)[7]) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p + (size_t)j * pitch);
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = w2 >> sh;
+        win[0] = s0; win[4] = s1;
+        win[1] = __funnelshift_r(s0, s1, 8); win[2] = __funnelshift_r(s0, s1, 16); win[3] = __funnelshift_r(s0, s1, 24);
+        win[5] = __funnelshift_r(s1, s2, 8); win[6] = __funnelshift_r(s1, s2, 16);
+    };
+    load_row(0, r0);
+    load_row(1, r1);
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+        load_row(dy + 2, r2);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int Ix = dp4a_px(r2[k], WX1, dp4a_px(r1[k], WX2, dp4a_px(r0[k], WX1, 0)));
+            const int Iy = dp4a_px(r2[k], WY2, dp4a_px(r0[k], WY0, 0));
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
+    }
+#else
     int r0[9], r1[9], r2[9];
     const uint8_t *p = img + (size_t)(y - 4) * pitch + (x - 4);
 #pragma unroll
@@ -1353,6 +1423,7 @@ __device__ __forceinline__ float harris_response(const uint8_t *__restrict__ img
 #pragma unroll
         for (int i = 0; i < 9; ++i) { r0[i] = r1[i]; r1[i] = r2[i]; }
     }
+#endif
     const float scale = 1.f / (4 * 7 * 255.f);
     const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
     const float fa = (float)a, fb = (float)b, fc = (float)c;

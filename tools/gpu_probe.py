@@ -8,7 +8,7 @@ from aria_slam_b200 import synth
 
 ctx = Context(0)
 out = {"sm_count": ctx.sm_count}
-for which, name in enumerate(["popc", "lop3", "iadd3", "vimnmx3_u16x2", "hmnmx2", "vimnmx3+hmnmx2", "imad", "prmt"]):
+for which, name in enumerate(["popc", "lop3", "iadd3", "vimnmx3_u16x2", "hmnmx2", "vimnmx3+hmnmx2", "imad", "prmt", "ffma", "ffma2_lanes", "fadd2_lanes", "fmul2_lanes"]):
     out["gops_" + name] = ctx.microbench(which)
 if os.environ.get("ASLAM_PROBE_FRAMES", "") == "natural":       # 1/f noise: the FAST quick-reject discards most pixel pairs
     frames = np.stack([synth.natural_frame(752, 480, 1000 + i) if i % 2 == 0 else synth.shifted(synth.natural_frame(752, 480, 999 + i), seed=i)
