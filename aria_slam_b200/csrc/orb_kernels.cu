@@ -5,6 +5,7 @@
 // Bit-exactness notes: every float expression that OpenCV evaluates without fused multiply-add
 // is spelled with __fmul_rn/__fadd_rn/__fsub_rn here (nvcc contracts a*b+c by default);
 // cvRound is __float2int_rn (half to even).
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -1084,6 +1085,10 @@ struct BlurPlan {
     int cta_off[ORB_MAX_LEVELS + 1];   // first CTA of each level within a frame
     int strip_h[ORB_MAX_LEVELS];       // rows per strip (even)
     int nstrips[ORB_MAX_LEVELS];
+    // ASLAM_BM_SPLIT: a level's column groups g in [1, gs) are "bulk" -- no image border inside their 12-byte window, both
+    // passes fused -- and come first, in CTAs of their own (bulk_ctas); group 0 and the groups from gs on follow.
+    int bulk_ctas[ORB_MAX_LEVELS];
+    int gs[ORB_MAX_LEVELS];
 };
 struct BlurTapsM { float k[4]; float one; };
 constexpr int BM_THREADS = 128;
@@ -1232,6 +1237,128 @@ __device__ __forceinline__ void blur_march_step(BlurMarch &S, int v_next, int y_
     }
 }
 
+#ifndef ASLAM_BM_SPLIT
+#define ASLAM_BM_SPLIT 1        // 1: bulk column groups take blur_bulk_march (below); 0: every thread takes the general march
+#endif
+// The march of the bulk threads (interior columns, fused taps: > 95 % of a level).  Same arithmetic as the general march,
+// different bookkeeping: the row pass still works on (upper row, lower row) lane pairs, but its LAST tap is two scalar
+// FFMAs per column whose results are born in column-packed pairs C[row][h] = (R[row][2h], R[row][2h+1]).  The column pass
+// then reads only aligned pairs of a ring of 8 rows (16 pairs; the general march keeps 16 P and 16 Q pairs and builds Q
+// with register moves), has no border selectors and no fused / unfused branches, so nothing is copied at a join.
+struct BlurBulk {
+    pk2 C[8][2];
+    uint32_t wa[BM_DEPTH][3], wb[BM_DEPTH][3];
+    const uint8_t *col;
+    uint8_t *dp;
+    int h, pitch, two_h_m2;
+    pk2 K0, K1, K2, K3;
+    float k0;
+
+    __device__ __forceinline__ const uint32_t *row_ptr(int v) const
+    {
+        int a = abs(v);
+        a = max(min(a, two_h_m2 - a), 0);
+        ASLAM_BOUNDS(a >= 0 && a < h);
+        return reinterpret_cast<const uint32_t *>(col + (unsigned long long)(unsigned)a * (unsigned)pitch);
+    }
+    __device__ __forceinline__ void load(int v, uint32_t (&w)[3]) const
+    {
+        const uint32_t *p = row_ptr(v);
+        w[0] = __ldg(p - 1); w[1] = __ldg(p); w[2] = __ldg(p + 1);
+    }
+};
+
+template <int STEP, bool OUT>
+__device__ __forceinline__ void blur_bulk_step(BlurBulk &S, int v_next, int y_out)
+{
+    constexpr int WS = STEP % BM_DEPTH;
+    pk2 v[10];
+    {
+        const uint32_t A[3] = {S.wa[WS][0], S.wa[WS][1], S.wa[WS][2]}, B[3] = {S.wb[WS][0], S.wb[WS][1], S.wb[WS][2]};
+        S.load(v_next, S.wa[WS]);
+        S.load(v_next + 1, S.wb[WS]);
+        const pk2 M = pk_dup(-8388608.0f);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const int byte = k + 1;
+            v[k] = pk_add(pk_make(u8_magic(A[byte >> 2], byte & 3), u8_magic(B[byte >> 2], byte & 3)), M);
+        }
+    }
+    uint32_t ra[4], rb[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        pk2 s = pk_mul(S.K0, v[o]);
+        s = pk_fma(S.K1, v[o + 1], s);
+        s = pk_fma(S.K2, v[o + 2], s);
+        s = pk_fma(S.K3, v[o + 3], s);
+        s = pk_fma(S.K2, v[o + 4], s);
+        s = pk_fma(S.K1, v[o + 5], s);
+        ra[o] = __float_as_uint(__fmaf_rn(S.k0, __uint_as_float(pk_lo(v[o + 6])), __uint_as_float(pk_lo(s))));
+        rb[o] = __float_as_uint(__fmaf_rn(S.k0, __uint_as_float(pk_hi(v[o + 6])), __uint_as_float(pk_hi(s))));
+    }
+    constexpr int RA = (2 * STEP) & 7, RB = (2 * STEP + 1) & 7;        // ring slots of this step's two rows
+    S.C[RA][0] = pk_make(ra[0], ra[1]); S.C[RA][1] = pk_make(ra[2], ra[3]);
+    S.C[RB][0] = pk_make(rb[0], rb[1]); S.C[RB][1] = pk_make(rb[2], rb[3]);
+
+    if (OUT) {
+        const pk2 MG = pk_dup(12582912.0f);
+        uint32_t px[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            constexpr int dummy = 0; (void)dummy;
+            const int c = (2 * STEP - 3 + r) & 7;                      // centre row of output row r (compile-time after unrolling)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                pk2 s = pk_mul(S.K3, S.C[c][hh]);
+                s = pk_fma(S.K2, pk_add(S.C[(c + 7) & 7][hh], S.C[(c + 1) & 7][hh]), s);
+                s = pk_fma(S.K1, pk_add(S.C[(c + 6) & 7][hh], S.C[(c + 2) & 7][hh]), s);
+                s = pk_fma(S.K0, pk_add(S.C[(c + 5) & 7][hh], S.C[(c + 3) & 7][hh]), s);
+                s = pk_add(s, MG);
+                px[r][2 * hh] = pk_lo(s); px[r][2 * hh + 1] = pk_hi(s);
+            }
+        }
+        if (y_out < S.h) {
+            ASLAM_BOUNDS(y_out >= 0);
+            *reinterpret_cast<uint32_t *>(S.dp) = __byte_perm(__byte_perm(px[0][0], px[0][1], 0x0040), __byte_perm(px[0][2], px[0][3], 0x0040), 0x5410);
+            if (y_out + 1 < S.h)
+                *reinterpret_cast<uint32_t *>(S.dp + S.pitch) = __byte_perm(__byte_perm(px[1][0], px[1][1], 0x0040), __byte_perm(px[1][2], px[1][3], 0x0040), 0x5410);
+        }
+        S.dp += 2 * (size_t)S.pitch;
+    }
+}
+
+__device__ __forceinline__ void blur_bulk_march(const uint8_t *col, uint8_t *dp, int h, int pitch, int ys, int nsteps, const BlurTapsM &T)
+{
+    BlurBulk S;
+    S.h = h; S.pitch = pitch; S.two_h_m2 = 2 * h - 2;
+    S.col = col; S.dp = dp;
+    S.K0 = pk_dup(T.k[0]); S.K1 = pk_dup(T.k[1]); S.K2 = pk_dup(T.k[2]); S.K3 = pk_dup(T.k[3]);
+    S.k0 = T.k[0];
+#pragma unroll
+    for (int d = 0; d < BM_DEPTH; ++d) {
+        S.load(ys - 3 + 2 * d, S.wa[d]);
+        S.load(ys - 2 + 2 * d, S.wb[d]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { S.C[r][0] = 0ull; S.C[r][1] = 0ull; }
+    constexpr int VN = 2 * BM_DEPTH - 3;
+    blur_bulk_step<0, false>(S, ys + VN, 0);
+    blur_bulk_step<1, false>(S, ys + VN + 2, 0);
+    blur_bulk_step<2, false>(S, ys + VN + 4, 0);
+    int m = 3;
+#pragma unroll 1
+    for (;;) {
+        blur_bulk_step<3, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+        blur_bulk_step<0, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+        blur_bulk_step<1, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+        blur_bulk_step<2, true>(S, ys + VN + 2 * m, ys + 2 * m - 6);
+        if (++m >= nsteps) break;
+    }
+}
+
 #ifndef ASLAM_BM_MINB
 #define ASLAM_BM_MINB 5         // 96 registers (8 bytes of spill) and 20 warps per SM: 0.369 ms; 4 (120 registers, 16 warps): 0.380; 3: 0.380
 #endif
@@ -1244,11 +1371,37 @@ blur_march_kernel(OrbGeom g, OrbBuffers b, BlurTapsM T, BlurPlan plan)
         if (i < g.nbuilt && (int)blockIdx.x >= plan.cta_off[i]) l = i;
     const LevelGeom L = g.lv[l];
     const int ncg = (L.w + 3) >> 2;                                   // column groups per row
+    const int hs = plan.strip_h[l];
+    const int nsteps = hs / 2 + 3;                                    // steps m = 0 .. hs/2 + 2; outputs from m = 3
+#if ASLAM_BM_SPLIT
+    const int cta = (int)blockIdx.x - plan.cta_off[l], gs = plan.gs[l];
+    int strip, x0;
+    if (cta < plan.bulk_ctas[l]) {                                    // CTA-uniform
+        const int nb = gs - 1;
+        const int t = cta * BM_THREADS + (int)threadIdx.x;
+        strip = t / nb;
+        x0 = (1 + t - strip * nb) * 4;
+        if (strip >= plan.nstrips[l]) return;
+        ASLAM_BOUNDS(x0 >= 4 && x0 + 7 < L.w && x0 + 3 < L.row_fused_end && x0 + 3 < L.col_fused_end);
+        const int ys = strip * hs;
+        blur_bulk_march(b.pyr + (size_t)blockIdx.y * g.pyr_stride + L.off + x0,
+                        b.blur + (size_t)blockIdx.y * g.pyr_stride + L.off + (size_t)ys * L.pitch + x0, L.h, L.pitch, ys, nsteps, T);
+        return;
+    }
+    {
+        const int nsp = ncg - (gs - 1);                               // group 0 and groups gs .. ncg-1
+        const int t = (cta - plan.bulk_ctas[l]) * BM_THREADS + (int)threadIdx.x;
+        strip = t / nsp;
+        const int k = t - strip * nsp;
+        x0 = (k == 0 ? 0 : gs + k - 1) * 4;
+        if (strip >= plan.nstrips[l]) return;
+    }
+#else
     const int t = ((int)blockIdx.x - plan.cta_off[l]) * BM_THREADS + (int)threadIdx.x;
     const int strip = t / ncg, x0 = (t - strip * ncg) * 4;
     if (strip >= plan.nstrips[l]) return;
-    const int hs = plan.strip_h[l], ys = strip * hs;
-    const int nsteps = hs / 2 + 3;                                    // steps m = 0 .. hs/2 + 2; outputs from m = 3
+#endif
+    const int ys = strip * hs;
 
     BlurMarch S;
     S.h = L.h; S.pitch = L.pitch; S.two_h_m2 = 2 * L.h - 2;
@@ -1329,14 +1482,26 @@ int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfram
     for (int l = 0; l < ORB_MAX_LEVELS; ++l) {
         plan.cta_off[l] = cta;
         plan.strip_h[l] = 2; plan.nstrips[l] = 0;
+        plan.bulk_ctas[l] = 0; plan.gs[l] = 1;
         if (l >= g.nbuilt) continue;
         const LevelGeom &L = g.lv[l];
         const int ns = (L.h + hmax - 1) / hmax;
         const int hs = ((L.h + ns - 1) / ns + 1) & ~1;
         plan.nstrips[l] = (L.h + hs - 1) / hs;
         plan.strip_h[l] = hs;
-        const long long threads = (long long)((L.w + 3) / 4) * plan.nstrips[l];
+        const int ncg = (L.w + 3) / 4;
+#if ASLAM_BM_SPLIT
+        // first group that is not bulk: its window touches the right border (4g + 7 >= w) or its taps are not all fused
+        int gs = std::min(std::min(L.row_fused_end, L.col_fused_end) / 4, (L.w - 4) / 4);
+        if (gs < 2) gs = 1;                                           // no bulk group
+        plan.gs[l] = gs;
+        const long long bulk = (long long)(gs - 1) * plan.nstrips[l], special = (long long)(ncg - (gs - 1)) * plan.nstrips[l];
+        plan.bulk_ctas[l] = (int)((bulk + BM_THREADS - 1) / BM_THREADS);
+        cta += plan.bulk_ctas[l] + (int)((special + BM_THREADS - 1) / BM_THREADS);
+#else
+        const long long threads = (long long)ncg * plan.nstrips[l];
         cta += (int)((threads + BM_THREADS - 1) / BM_THREADS);
+#endif
     }
     plan.cta_off[ORB_MAX_LEVELS] = cta;
     dim3 grid(cta, nframes);
