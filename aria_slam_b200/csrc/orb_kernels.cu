@@ -1634,6 +1634,258 @@ __device__ __forceinline__ int warp_kth_bin_from_top(const int *hist, int k, int
     return __shfl_sync(0xffffffffu, bin, owner);
 }
 
+#ifndef ASLAM_SEL_V2
+#define ASLAM_SEL_V2 1          // 1: round 2's selection (12 barriers per CTA); 0: round 1's (about 30)
+#endif
+#if ASLAM_SEL_V2
+// K-th largest of the 32-bit keys key_of(i, key) (false = element i does not take part), i in [0, M), by
+// 4 x 8-bit radix passes; at least K >= 1 elements must take part.  Called by the whole CTA.  Returns that key;
+// k_left = how many of the elements equal to it are needed to reach K (>= 1).
+// One barrier per pass: each pass has a histogram of its own (hist4[pass][256], zeroed together up front), the first two
+// keys of a thread stay in registers, and EVERY warp finds the pass's bin from the finished histogram by itself, so the
+// prefix and the remaining count never travel through shared memory.
+template <class KeyFn>
+__device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of, int *hist4, int &k_left)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * 256; i += SEL_THREADS) hist4[i] = 0;
+    uint32_t kreg[2] = {0u, 0u};
+    bool kval[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * SEL_THREADS;
+        kval[j] = i < M && key_of(i, kreg[j]);
+    }
+    __syncthreads();
+    uint32_t maskbits = 0, prefix = 0;
+    int k = K;
+#pragma unroll 1
+    for (int pass = 3; pass >= 0; --pass) {
+        int *h = hist4 + pass * 256;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (kval[j] && (kreg[j] & maskbits) == prefix) atomicAdd(&h[(kreg[j] >> (8 * pass)) & 0xffu], 1);
+        for (int i = tid + 2 * SEL_THREADS; i < M; i += SEL_THREADS) {
+            uint32_t key;
+            if (key_of(i, key) && (key & maskbits) == prefix) atomicAdd(&h[(key >> (8 * pass)) & 0xffu], 1);
+        }
+        __syncthreads();
+        int above;
+        const int bin = warp_kth_bin_from_top(h, k, above);       // exists: the prefix class holds >= k keys
+        k -= above;
+        prefix |= (uint32_t)bin << (8 * pass);
+        maskbits |= 0xffu << (8 * pass);
+    }
+    k_left = k;
+    __syncthreads();          // all warps are done with hist4 before a next call zeroes it
+    return prefix;
+}
+
+// A warp's share of the candidate tiles [t_begin, t_end): visit(e, valid) is called for every slot in candidate order,
+// 32 slots per call, with the same trip count for all lanes.  The first 128 slots of a tile are loaded together with its
+// count (no dependent load; the slots exist whatever the count is) and the next tile's are requested before this one is
+// visited.
+template <class Visit>
+__device__ __forceinline__ void for_each_candidate(const uint32_t *__restrict__ cand, const uint32_t *__restrict__ ccnt,
+                                                   int t_begin, int t_end, int lane, Visit visit)
+{
+    if (t_begin >= t_end) return;
+    uint32_t e[4], ne[4] = {0u, 0u, 0u, 0u};
+    int n, nn = 0;
+    {
+        const uint32_t *ct = cand + (size_t)t_begin * FT_CAP + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = __ldg(ct + 32 * k);
+        n = (int)__ldg(ccnt + t_begin);
+    }
+    for (int t = t_begin; t < t_end; ++t) {
+        if (t + 1 < t_end) {
+            const uint32_t *ct = cand + (size_t)(t + 1) * FT_CAP + lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ne[k] = __ldg(ct + 32 * k);
+            nn = (int)__ldg(ccnt + t + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (32 * k < n) visit(e[k], lane + 32 * k < n);
+        for (int i0 = 128; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            visit(i < n ? __ldg(cand + (size_t)t * FT_CAP + i) : 0u, i < n);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = ne[k];
+        n = nn;
+    }
+}
+
+// BUCKET = the grid-bucketed second cull (g.grid_cell > 0), an extension cv::ORB does not have; its definition is
+// in include/aslam_b200.h (aslam_orb_params::grid_cell) and DESIGN.md section 4a.
+// Round 2: every warp owns a CONTIGUOUS range of the level's tiles, so the ordered compaction needs one exchange of 16
+// warp totals instead of per-tile counts through global memory and a scan over the tiles; the cut-off bins are found by
+// every warp for itself; the output pass hands every warp a contiguous range of survivors in the same way.
+template <bool BUCKET>
+__global__ void __launch_bounds__(SEL_THREADS, 2)
+select_kernel(OrbGeom g, OrbBuffers b)
+{
+    __shared__ int hist4[4 * 256];
+    __shared__ int warp_sums[SEL_THREADS / 32];
+    __shared__ int warp_sums2[SEL_THREADS / 32];
+
+    const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = SEL_THREADS / 32;
+    const LevelGeom L = g.lv[l];
+    const int ntiles = L.tiles_x * L.tiles_y;
+    int32_t *sel_cnt = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS + l;
+    if (ntiles == 0) {
+        if (tid == 0) *sel_cnt = 0;
+        return;
+    }
+    const size_t tile0 = (size_t)frame * g.tiles_per_frame + L.tile_off;
+    const uint32_t *cand = b.cand + tile0 * FT_CAP;
+    const uint32_t *ccnt = b.cand_cnt + tile0;
+    uint32_t *surv = b.surv + tile0 * FT_CAP;
+    float *hresp = b.hresp + tile0 * FT_CAP;
+    const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
+    const int tpw = (ntiles + NWARPS - 1) / NWARPS;
+    const int t_begin = min(warp * tpw, ntiles), t_end = min(t_begin + tpw, ntiles);
+
+    // --- retainBest(2N) threshold on the integer FAST score
+    int *hist = hist4;
+    for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+    __syncthreads();
+    for_each_candidate(cand, ccnt, t_begin, t_end, lane, [&](uint32_t e, bool valid) {
+        if (valid) atomicAdd(&hist[e >> 24], 1);
+    });
+    __syncthreads();
+    uint32_t thr = 0;
+    {
+        // keep everything if there are at most K1 candidates, else cut at the K1-th largest score (ties kept)
+        int above;
+        const int bin = warp_kth_bin_from_top(hist, 2 * L.quota + 1, above);      // >= K1+1 exist <=> total > K1
+        if (bin >= 0) thr = (uint32_t)warp_kth_bin_from_top(hist, 2 * L.quota, above);
+    }
+
+    // --- ordered compaction of the survivors: count, exchange the warp totals, ranked writes
+    int cnt = 0;
+    for_each_candidate(cand, ccnt, t_begin, t_end, lane, [&](uint32_t e, bool valid) {
+        cnt += __popc(__ballot_sync(0xffffffffu, valid && (e >> 24) >= thr));
+    });
+    if (lane == 0) warp_sums[warp] = cnt;
+    __syncthreads();
+    int base = 0, M1 = 0;
+#pragma unroll
+    for (int i = 0; i < NWARPS; ++i) {
+        const int v = warp_sums[i];
+        if (i < warp) base += v;
+        M1 += v;
+    }
+    for_each_candidate(cand, ccnt, t_begin, t_end, lane, [&](uint32_t e, bool valid) {
+        const bool pass = valid && (e >> 24) >= thr;
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        ASLAM_BOUNDS(!pass || base + 32 <= ntiles * FT_CAP + 32);
+        if (pass) surv[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        base += __popc(bal);
+    });
+    __syncthreads();
+
+    // --- Harris response of every survivor
+    for (int i = tid; i < M1; i += SEL_THREADS) {
+        const uint32_t e = surv[i];
+        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h);
+        hresp[i] = harris_response(img, L.pitch, (int)(e & 0xfffu), (int)((e >> 12) & 0xfffu));
+    }
+    __syncthreads();
+
+    // --- retainBest(N): K-th largest response by a radix select over the ordered key
+    uint32_t cut = 0;   // keep keys >= cut
+    const int K2 = L.quota;
+    int k_left;
+    [[maybe_unused]] uint32_t rank_cut = 0xffffffffu;     // BUCKET: keep ranks < rank_cut, and rank == rank_cut with key >= cut
+    [[maybe_unused]] uint32_t *rank = nullptr;
+    if constexpr (!BUCKET) {
+        if (M1 > K2)
+            cut = block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return true; }, hist4, k_left);
+    } else {
+        // Grid-bucketed cull: rank of a survivor = how many survivors of its cell have a greater response; order by
+        // (rank ascending, response descending), keep the first K2 and everything tied with the K2-th.
+        rank = b.rank + tile0 * FT_CAP;
+        if (M1 > K2) {
+            __shared__ uint2 s_ck[SEL_THREADS];        // (cell id, ordered response key) of a block of survivors
+            const int cell = g.grid_cell;
+            auto cell_of = [&](uint32_t e) { return ((e & 0xfffu) / (uint32_t)cell) | ((((e >> 12) & 0xfffu) / (uint32_t)cell) << 12); };
+            for (int i0 = 0; i0 < M1; i0 += SEL_THREADS) {
+                const int i = i0 + tid;
+                const uint32_t mycell = i < M1 ? cell_of(surv[i]) : 0xfffffffeu;
+                const uint32_t mykey = i < M1 ? float_order_key(hresp[i]) : 0u;
+                uint32_t r = 0;
+                for (int j0 = 0; j0 < M1; j0 += SEL_THREADS) {
+                    __syncthreads();
+                    const int j = j0 + tid;
+                    s_ck[tid] = j < M1 ? make_uint2(cell_of(surv[j]), float_order_key(hresp[j])) : make_uint2(0xffffffffu, 0u);
+                    __syncthreads();
+                    const int n = min(SEL_THREADS, M1 - j0);        // padding entries match no cell: whole groups of 4 are safe
+#pragma unroll 4
+                    for (int k = 0; k < ((n + 3) & ~3); ++k) {
+                        const uint2 o = s_ck[k];                    // one broadcast 64-bit load
+                        r += (o.x == mycell) & (o.y > mykey);
+                    }
+                }
+                if (i < M1) rank[i] = r;
+            }
+            __syncthreads();
+            rank_cut = ~block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = ~rank[i]; return true; }, hist4, k_left);
+            const uint32_t R = rank_cut;
+            cut = block_kth_largest(M1, k_left, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return rank[i] == R; },
+                                    hist4, k_left);
+        }
+    }
+
+    // --- ordered output: warp w takes survivors [w * spw, (w + 1) * spw)
+    uint32_t *sel_xy = b.sel_xy + (size_t)frame * g.kp_cap + L.sel_off;
+    float *sel_resp = b.sel_resp + (size_t)frame * g.kp_cap + L.sel_off;
+    const int spw = (M1 + NWARPS - 1) / NWARPS;
+    const int s_begin = min(warp * spw, M1), s_end = min(s_begin + spw, M1);
+    auto keeps = [&](int i, float &r) {
+        r = hresp[i];
+        bool pass = float_order_key(r) >= cut;
+        if constexpr (BUCKET)
+            if (M1 > K2) pass = rank[i] < rank_cut || (rank[i] == rank_cut && pass);
+        return pass;
+    };
+    int kept = 0;
+    for (int i0 = s_begin; i0 < s_end; i0 += 32) {
+        const int i = i0 + lane;
+        float r;
+        kept += __popc(__ballot_sync(0xffffffffu, i < s_end && keeps(i, r)));
+    }
+    if (lane == 0) warp_sums2[warp] = kept;
+    __syncthreads();
+    int pos = 0, written = 0;
+#pragma unroll
+    for (int i = 0; i < NWARPS; ++i) {
+        const int v = warp_sums2[i];
+        if (i < warp) pos += v;
+        written += v;
+    }
+    for (int i0 = s_begin; i0 < s_end; i0 += 32) {
+        const int i = i0 + lane;
+        float r = 0.f;
+        const bool pass = i < s_end && keeps(i, r);
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        const int at = pos + __popc(bal & ((1u << lane) - 1u));
+        if (pass && at < L.sel_cap) {
+            sel_xy[at] = surv[i] & 0xffffffu;
+            sel_resp[at] = r;
+        }
+        pos += __popc(bal);
+    }
+    if (tid == 0) {
+        *sel_cnt = min(written, L.sel_cap);
+        if (written > L.sel_cap) atomicOr(b.overflow + frame + 1, 1);
+    }
+}
+#else
 // K-th largest of the 32-bit keys key_of(i, key) (false = element i does not take part), i in [0, M), by
 // 4 x 8-bit radix passes; at least K >= 1 elements must take part.  Called by the whole CTA.  Returns that key;
 // k_left = how many of the elements equal to it are needed to reach K (>= 1).
@@ -1841,6 +2093,8 @@ select_kernel(OrbGeom g, OrbBuffers b)
         if (written > L.sel_cap) atomicOr(b.overflow + frame + 1, 1);
     }
 }
+
+#endif
 
 int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
 {
