@@ -488,12 +488,24 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int &total
 constexpr int FA_PITCH = 80;      // u16 per staged row (76 used), 160 B
 constexpr int FA_WORDS = 19;      // aligned 32-bit global words per staged row
 
-template <int DX, int DY>
-__device__ __forceinline__ uint32_t ring_pair(const uint16_t (*A)[FA_PITCH], const uint16_t (*Bc)[FA_PITCH], int r, int gp)
+// The two staged copies are one array (copy 0 = A, copy 1 = Bc) so that every pixel pair of a ring is ONE shared-memory
+// address plus a compile-time offset: `at` = address of the word (row r, pair column gp - 2) of copy A, where r is the
+// score row (= staged row of the window's top) -- all offsets below are >= 0.
+constexpr int FA_COPY_BYTES = FT_PIX_H * FA_PITCH * 2;
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32_off(uint32_t addr)
 {
-    // gp = g0/2 + p where g0 = staged column of score column 0
-    if ((DX & 1) == 0) return reinterpret_cast<const uint32_t *>(A[r + 3 + DY])[gp + DX / 2];
-    return reinterpret_cast<const uint32_t *>(Bc[r + 3 + DY])[gp + (DX - 1) / 2];
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int DX, int DY>
+__device__ __forceinline__ uint32_t ring_pair(uint32_t at)
+{
+    constexpr int word = (DX & 1) == 0 ? DX / 2 : (DX - 1) / 2;
+    constexpr int off = (DY + 3) * FA_PITCH * 2 + 4 * (word + 2) + ((DX & 1) == 0 ? 0 : FA_COPY_BYTES);
+    static_assert(off >= 0, "ring offsets are non-negative");
+    return lds_u32_off<off>(at);
 }
 
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
@@ -504,6 +516,21 @@ __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { r
 #endif
 #ifndef ASLAM_FAST_COMPACT
 #define ASLAM_FAST_COMPACT 1
+#endif
+#ifndef ASLAM_FAST_ZERO_S
+#define ASLAM_FAST_ZERO_S 1     // 1: the score block is zeroed by 16-byte stores before phase A instead of per warp and row
+#endif
+#ifndef ASLAM_FAST_A_UNROLL
+#define ASLAM_FAST_A_UNROLL 1   // rows of the quick test per loop trip
+#endif
+constexpr int FAST_A_UNROLL = ASLAM_FAST_A_UNROLL;
+#ifndef ASLAM_FAST_Q32
+#define ASLAM_FAST_Q32 1        // queue entries as 32-bit words: the loop variable is stored as it is (no 16-bit twin of it)
+#endif
+#if ASLAM_FAST_Q32
+typedef uint32_t FastQ;
+#else
+typedef uint16_t FastQ;
 #endif
 #ifndef ASLAM_FAST_NET
 #define ASLAM_FAST_NET 1     // 1: the 72-instruction score network (shared eight-pixel windows); 0: round 1's 80
@@ -518,19 +545,18 @@ __device__ __forceinline__ uint32_t imad32(uint32_t a, uint32_t b, uint32_t c)
 }
 
 // Corner score of the pixel pair at score row r, pair column gp - g0/2: relu(max(A, B) - t) per u16 lane.
-__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*A)[FA_PITCH], const uint16_t (*Bc)[FA_PITCH], int r, int gp,
-                                                    uint32_t neg_thr, const FastMul M)
+__device__ __forceinline__ uint32_t fast_score_pair(uint32_t at, uint32_t neg_thr, const FastMul M)
 {
     uint32_t v[16];
-    v[0] = ring_pair<0, 3>(A, Bc, r, gp);    v[1] = ring_pair<1, 3>(A, Bc, r, gp);
-    v[2] = ring_pair<2, 2>(A, Bc, r, gp);    v[3] = ring_pair<3, 1>(A, Bc, r, gp);
-    v[4] = ring_pair<3, 0>(A, Bc, r, gp);    v[5] = ring_pair<3, -1>(A, Bc, r, gp);
-    v[6] = ring_pair<2, -2>(A, Bc, r, gp);   v[7] = ring_pair<1, -3>(A, Bc, r, gp);
-    v[8] = ring_pair<0, -3>(A, Bc, r, gp);   v[9] = ring_pair<-1, -3>(A, Bc, r, gp);
-    v[10] = ring_pair<-2, -2>(A, Bc, r, gp); v[11] = ring_pair<-3, -1>(A, Bc, r, gp);
-    v[12] = ring_pair<-3, 0>(A, Bc, r, gp);  v[13] = ring_pair<-3, 1>(A, Bc, r, gp);
-    v[14] = ring_pair<-2, 2>(A, Bc, r, gp);  v[15] = ring_pair<-1, 3>(A, Bc, r, gp);
-    const uint32_t c = ring_pair<0, 0>(A, Bc, r, gp);
+    v[0] = ring_pair<0, 3>(at);    v[1] = ring_pair<1, 3>(at);
+    v[2] = ring_pair<2, 2>(at);    v[3] = ring_pair<3, 1>(at);
+    v[4] = ring_pair<3, 0>(at);    v[5] = ring_pair<3, -1>(at);
+    v[6] = ring_pair<2, -2>(at);   v[7] = ring_pair<1, -3>(at);
+    v[8] = ring_pair<0, -3>(at);   v[9] = ring_pair<-1, -3>(at);
+    v[10] = ring_pair<-2, -2>(at); v[11] = ring_pair<-3, -1>(at);
+    v[12] = ring_pair<-3, 0>(at);  v[13] = ring_pair<-3, 1>(at);
+    v[14] = ring_pair<-2, 2>(at);  v[15] = ring_pair<-1, 3>(at);
+    const uint32_t c = ring_pair<0, 0>(at);
 
 #if ASLAM_FAST_NET == 1
     // 72 min/max instead of 80.  The arcs starting at 2j and 2j+1 share the eight pixels 2j+1 .. 2j+8 (W) and differ in
@@ -611,12 +637,13 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t (*A)[FA_PITCH
 __global__ void __launch_bounds__(256, ASLAM_FAST_MINB)
 fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
 {
-    __shared__ __align__(16) uint16_t A[FT_PIX_H][FA_PITCH];
-    __shared__ __align__(16) uint16_t Bc[FT_PIX_H][FA_PITCH];
-    __shared__ uint32_t S[FT_SCORE_H][FT_SCORE_W / 2];      // two u16 scores per word
+    __shared__ __align__(16) uint16_t AB[2][FT_PIX_H][FA_PITCH];
+    uint16_t (*const A)[FA_PITCH] = AB[0], (*const Bc)[FA_PITCH] = AB[1];
+    static_assert(sizeof(AB[0]) == FA_COPY_BYTES, "copy stride");
+    __shared__ __align__(16) uint32_t S[FT_SCORE_H][FT_SCORE_W / 2];      // two u16 scores per word
     __shared__ int warp_tot[8];
 #if ASLAM_FAST_COMPACT
-    __shared__ uint16_t Q[8][FT_SCORE_H / 8 * 32 + 2];      // per warp: queued (row << 5 | lane) of pairs to score (+ a sink slot)
+    __shared__ FastQ Q[8][FT_SCORE_H / 8 * 32 + 2];         // per warp: queued (row << 5 | lane) of pairs to score (+ a sink slot)
 #endif
 
     const int tile = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
@@ -658,6 +685,16 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             }
         }
     }
+#if ASLAM_FAST_ZERO_S
+    // the score block starts out as zeros (two 16-byte stores per thread here instead of a store with its addressing per
+    // warp and row in phase A); phase B fills in the pairs that pass the quick test
+    {
+        uint4 *sz = reinterpret_cast<uint4 *>(&S[0][0]);
+        static_assert(sizeof(S) % (256 * sizeof(uint4)) == 0, "score block is a whole number of 16-byte stores per thread");
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(S) / (256 * sizeof(uint4))); ++i) sz[i * 256 + tid] = make_uint4(0u, 0u, 0u, 0u);
+    }
+#endif
     __syncthreads();
 
     const int warp = tid >> 5, p = tid & 31;
@@ -678,47 +715,49 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     // B: the full score runs on dense warps of queued pairs only (35 % of the pairs on the synthetic frames,
     // a few per cent on natural images); everything else scores 0, exactly as the full test would find.
     {
-        uint16_t *queue = Q[warp];
+        FastQ *queue = Q[warp];
         const uint32_t kq = (uint32_t)(32767 - g.fast_thr) * 0x00010001u;
         const uint32_t colbits = (px_x < L.w - 3 ? 0x8000u : 0u) | (px_x + 1 < L.w - 3 ? 0x80000000u : 0u);
         int nq = 0;
-#if ASLAM_FAST_NMS_QUEUE
-        // a warp owns FT_SCORE_H / 8 consecutive rows, so its queue -- and with it the emitted order -- is row-major
-        const int r_last = min(r_end, (warp + 1) * (FT_SCORE_H / 8));
-#pragma unroll 1
-        for (int r = warp * (FT_SCORE_H / 8); r < r_last; ++r) {
-#else
-#pragma unroll 1
-        for (int r = warp; r < r_end; r += 8) {
-#endif
-            const uint32_t c = ring_pair<0, 0>(A, Bc, r, gp);
-            const uint32_t p0 = ring_pair<0, 3>(A, Bc, r, gp), p8 = ring_pair<0, -3>(A, Bc, r, gp);
-            const uint32_t p4 = ring_pair<3, 0>(A, Bc, r, gp), p12 = ring_pair<-3, 0>(A, Bc, r, gp);
-            const uint32_t p2 = ring_pair<2, 2>(A, Bc, r, gp), p10 = ring_pair<-2, -2>(A, Bc, r, gp);
-            const uint32_t p6 = ring_pair<2, -2>(A, Bc, r, gp), p14 = ring_pair<-2, 2>(A, Bc, r, gp);
+        // a warp owns FT_SCORE_H / 8 consecutive rows, so its queue -- and with it the emitted order -- is row-major.
+        // The loop runs on the queue entry itself ((r << 5) | lane, + 32 per row) and on one shared-memory address.
+        const int r_first = warp * (FT_SCORE_H / 8), r_last = min(r_end, (warp + 1) * (FT_SCORE_H / 8));
+        const uint32_t val_end = (uint32_t)r_last << 5;
+        const uint32_t lt_mask = (1u << p) - 1u;
+        uint32_t at = smem_u32(&AB[0][r_first][0]) + 4u * (uint32_t)(gp - 2);
+#pragma unroll FAST_A_UNROLL
+        for (uint32_t val = ((uint32_t)r_first << 5) | (uint32_t)p; val < val_end; val += 32u, at += FA_PITCH * 2) {
+            const uint32_t c = ring_pair<0, 0>(at);
+            const uint32_t p0 = ring_pair<0, 3>(at), p8 = ring_pair<0, -3>(at);
+            const uint32_t p4 = ring_pair<3, 0>(at), p12 = ring_pair<-3, 0>(at);
+            const uint32_t p2 = ring_pair<2, 2>(at), p10 = ring_pair<-2, -2>(at);
+            const uint32_t p6 = ring_pair<2, -2>(at), p14 = ring_pair<-2, 2>(at);
             const uint32_t mb = __vminu2(min3(__vmaxu2(p0, p8), __vmaxu2(p4, p12), __vmaxu2(p2, p10)), __vmaxu2(p6, p14));
             const uint32_t md = __vmaxu2(max3(__vminu2(p0, p8), __vminu2(p4, p12), __vminu2(p2, p10)), __vminu2(p6, p14));
             // per lane: mb - c - t + 32767 and c - t - md + 32767 (lanes stay positive: no borrow); bit 15 <=> > 0
             const uint32_t ub = imad32(c, M.minus1, imad32(mb, M.one, kq));
             const uint32_t ud = imad32(md, M.minus1, imad32(c, M.one, kq));
             const bool pass = ((ub | ud) & colbits) != 0;
-            ASLAM_BOUNDS(r >= 0 && r + 6 < FT_PIX_H && gp - 2 >= 0 && 2 * (gp + 2) < FA_PITCH && nq <= FT_SCORE_H / 8 * 32);
-            S[r][p] = 0u;
+            ASLAM_BOUNDS((int)(val >> 5) >= 0 && (int)(val >> 5) + 6 < FT_PIX_H && gp - 2 >= 0 && 2 * (gp + 2) < FA_PITCH && nq <= FT_SCORE_H / 8 * 32);
+#if !ASLAM_FAST_ZERO_S
+            S[val >> 5][p] = 0u;
+#endif
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-            queue[pass ? nq + __popc(bal & ((1u << p) - 1u)) : FT_SCORE_H / 8 * 32] = (uint16_t)((r << 5) | p);      // branch-free: slot 256 is a sink
+            queue[pass ? nq + __popc(bal & lt_mask) : FT_SCORE_H / 8 * 32] = (FastQ)val;      // branch-free: slot 256 is a sink
             nq += __popc(bal);
         }
         __syncwarp();
 #if ASLAM_FAST_NMS_QUEUE
         n2 = 0;
 #endif
+        const uint32_t ab_base = smem_u32(&AB[0][0][0]) + 4u * (uint32_t)(g0 / 2 - 2);
 #pragma unroll 1
         for (int i0 = 0; i0 < nq; i0 += 32) {
             const int i = i0 + p;
             const int id = queue[min(i, nq - 1)];
             const int rr = id >> 5, pp = id & 31;
             const uint32_t thr = __shfl_sync(0xffffffffu, neg_thr, pp);
-            const uint32_t sc = fast_score_pair(A, Bc, rr, g0 / 2 + pp, thr, M);
+            const uint32_t sc = fast_score_pair(ab_base + (uint32_t)rr * (FA_PITCH * 2) + (uint32_t)pp * 4u, thr, M);
             ASLAM_BOUNDS(rr >= 0 && rr < FT_SCORE_H && pp >= 0 && pp < 32 && n2 <= i0);
             if (i < nq) S[rr][pp] = sc;
 #if ASLAM_FAST_NMS_QUEUE
@@ -726,14 +765,14 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
             const bool nz = i < nq && sc != 0u;
             const uint32_t bal = __ballot_sync(0xffffffffu, nz);
             __syncwarp();
-            if (nz) queue[n2 + __popc(bal & ((1u << p) - 1u))] = (uint16_t)id;
+            if (nz) queue[n2 + __popc(bal & ((1u << p) - 1u))] = (FastQ)id;
             n2 += __popc(bal);
 #endif
         }
     }
 #else
 #pragma unroll 1
-    for (int r = warp; r < r_end; r += 8) S[r][p] = fast_score_pair(A, Bc, r, gp, neg_thr, M);
+    for (int r = warp; r < r_end; r += 8) S[r][p] = fast_score_pair(smem_u32(&AB[0][r][0]) + 4u * (uint32_t)(gp - 2), neg_thr, M);
 #endif
     __syncthreads();
 
@@ -751,22 +790,26 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     const uint32_t resp_bias = (uint32_t)(g.fast_thr - 1);
     int local = 0;
     {
-        const uint16_t *queue = Q[warp];
+        const FastQ *queue = Q[warp];
+        // which of a pair column's two pixels may be emitted depends on the column only: lane p keeps the mask of column p
+        // and a queued pair fetches its column's by a shuffle (it was ~30 ALU instructions per trip when recomputed)
+        const uint32_t col_ok = ((p >= 1 && px_x >= g.edge && px_x < L.w - g.edge) ? 0xffffu : 0u) |
+                                ((p <= 30 && px_x + 1 >= g.edge && px_x + 1 < L.w - g.edge) ? 0xffff0000u : 0u);
+        const int r_hi = min(FT_OUT_H, L.h - g.edge - sy0 - 1);      // last score row that is an output row of the image
 #pragma unroll 1
         for (int i0 = 0; i0 < n2; i0 += 32) {
             const int i = i0 + p;
             const int id = queue[min(i, n2 - 1)];
             const int r = id >> 5, pp = id & 31;
+            const uint32_t ok = __shfl_sync(0xffffffffu, col_ok, pp);
             uint32_t e = 0;
-            if (i < n2 && r >= 1 && r <= FT_OUT_H && sy0 + r < L.h - g.edge) {
+            if (i < n2 && r >= 1 && r <= r_hi) {
                 const int pl = max(pp - 1, 0), pr = min(pp + 1, FT_SCORE_W / 2 - 1);     // clamped words feed masked lanes only
                 const uint32_t up = S[r - 1][pp], cur = S[r][pp], dn = S[r + 1][pp];
                 const uint32_t V = __vmaxu2(up, dn), C3 = max3(up, cur, dn);
                 const uint32_t Lw = max3(S[r - 1][pl], S[r][pl], S[r + 1][pl]), Rw = max3(S[r - 1][pr], S[r][pr], S[r + 1][pr]);
                 const uint32_t nb = max3(V, __byte_perm(Lw, C3, 0x5432), __byte_perm(C3, Rw, 0x5432));
                 const int x0 = sx0 + 2 * pp, y = sy0 + r;
-                const uint32_t ok = ((pp >= 1 && x0 >= g.edge && x0 < L.w - g.edge) ? 0xffffu : 0u) |
-                                    ((pp <= 30 && x0 + 1 >= g.edge && x0 + 1 < L.w - g.edge) ? 0xffff0000u : 0u);
                 const uint32_t d = __vimax_s16x2_relu(__vsub2(cur, nb), 0u) & ok;
                 if (d) {
                     const bool second = (d & 0xffffu) == 0;

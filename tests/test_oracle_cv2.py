@@ -212,3 +212,56 @@ def test_fast_quick_reject_is_a_necessary_condition():
         ys = np.array([int(k.pt[1]) for k in kps]) - 3
         assert passed[ys, xs].all()
         assert passed.mean() < 0.5                                # and it does reject most pixels
+
+
+def test_fast_score_network_of_72_equals_the_arc_definition(oracle):
+    """The GPU kernel's exact FAST score (fast_score_pair, ASLAM_FAST_NET 1) evaluates max over the sixteen 9-arcs of
+    the arc's minimum (and the mirrored min of max) with 36 min/max per polarity: the arcs starting at 2j and 2j+1 share
+    the eight pixels 2j+1 .. 2j+8, so their two minima combine to min(window, max(v[2j], v[2j+9])) -- the loop of
+    cv::cornerScore<16>.  Checked against the plain definition on random and on few-valued rings, and the resulting score
+    against the oracle's score map on a frame."""
+    rng = np.random.default_rng(7)
+    v = rng.integers(0, 256, size=(300000, 16))
+    v[:100000] = rng.integers(0, 4, size=(100000, 16)) * 85
+    v[100000:150000] = np.sort(v[100000:150000], axis=1)
+    arcs = [[(k + i) % 16 for i in range(9)] for k in range(16)]
+    want_mx = np.stack([v[:, a].min(1) for a in arcs], 1).max(1)
+    want_mn = np.stack([v[:, a].max(1) for a in arcs], 1).min(1)
+
+    def network(lo, hi):
+        p = [lo(v[:, (2 * j + 1) % 16], v[:, (2 * j + 2) % 16]) for j in range(8)]
+        q = [lo(p[j], p[(j + 1) % 8]) for j in range(8)]
+        r = [lo(lo(q[j], q[(j + 2) % 8]), hi(v[:, 2 * j], v[:, (2 * j + 9) % 16])) for j in range(8)]
+        out = r[0]
+        for x in r[1:]:
+            out = hi(out, x)
+        return out
+
+    assert (network(np.minimum, np.maximum) == want_mx).all()
+    assert (network(np.maximum, np.minimum) == want_mn).all()
+
+
+def test_harris_sums_by_byte_dot_products_equal_the_sobel_sums():
+    """select_kernel's Harris response takes the 9 x 9 window as seven 4-byte words per row and forms Sobel x / y as dot
+    products with (-1,0,1,0), (-2,0,2,0) and (-1,-2,-1,0), (1,2,1,0) (DP4A).  Same integers as the plain 3 x 3 Sobel."""
+    rng = np.random.default_rng(3)
+    win = rng.integers(0, 256, size=(2000, 9, 9)).astype(np.int64)
+    win[:200] = rng.integers(0, 2, size=(200, 9, 9)) * 255
+    A = np.zeros(len(win), np.int64); B = A.copy(); C = A.copy()
+    for dy in range(7):
+        r0, r1, r2 = win[:, dy], win[:, dy + 1], win[:, dy + 2]
+        for i in range(1, 8):
+            ix = (r1[:, i + 1] - r1[:, i - 1]) * 2 + (r0[:, i + 1] - r0[:, i - 1]) + (r2[:, i + 1] - r2[:, i - 1])
+            iy = (r2[:, i] - r0[:, i]) * 2 + (r2[:, i - 1] - r0[:, i - 1]) + (r2[:, i + 1] - r0[:, i + 1])
+            A += ix * ix; B += iy * iy; C += ix * iy
+    wx1, wx2, wy0, wy2 = (np.array(t, np.int64) for t in ((-1, 0, 1, 0), (-2, 0, 2, 0), (-1, -2, -1, 0), (1, 2, 1, 0)))
+    A2 = np.zeros(len(win), np.int64); B2 = A2.copy(); C2 = A2.copy()
+    pad = np.concatenate([win, np.full((len(win), 9, 1), 77, np.int64)], axis=2)       # byte 9 of a row: weight 0
+    for dy in range(7):
+        for k in range(7):
+            w0, w1, w2 = pad[:, dy, k:k + 4], pad[:, dy + 1, k:k + 4], pad[:, dy + 2, k:k + 4]
+            ix = w0 @ wx1 + w1 @ wx2 + w2 @ wx1
+            iy = w0 @ wy0 + w2 @ wy2
+            A2 += ix * ix; B2 += iy * iy; C2 += ix * iy
+    assert (A == A2).all() and (B == B2).all() and (C == C2).all()
+    assert int(max(A.max(), B.max())) < 2 ** 31                  # the kernel accumulates in int32
