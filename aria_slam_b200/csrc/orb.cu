@@ -47,10 +47,21 @@ struct aslam_orb {
     uint8_t *d_retained[2] = {nullptr, nullptr};
     int retain_next = 0;
     int last_count = -1;           // -1: nothing synced yet (or already retained)
+    // the extraction chain of (n frames, with / without masks) as an instantiated CUDA graph: one launch per call
+    // instead of 12 (memset, 7 resize levels, FAST, blur, selection, describe); dropped whenever the buffers are re-planned
+    struct ChainGraph { int n; bool with_mask; cudaGraphExec_t exec; int launches; };
+    std::vector<ChainGraph> chains;
 };
+
+static void orb_drop_graphs(aslam_orb *o)
+{
+    for (auto &c : o->chains) cudaGraphExecDestroy(c.exec);
+    o->chains.clear();
+}
 
 static void orb_free_buffers(aslam_orb *o)
 {
+    orb_drop_graphs(o);
     cudaFree(o->b.pyr); cudaFree(o->b.blur); cudaFree(o->b.mask); cudaFree(o->b.cand); cudaFree(o->b.cand_cnt);
     cudaFree(o->b.tile_base); cudaFree(o->b.surv); cudaFree(o->b.hresp); cudaFree(o->b.rank); cudaFree(o->b.sel_xy);
     cudaFree(o->b.sel_resp); cudaFree(o->b.sel_cnt); cudaFree(o->b.kps); cudaFree(o->b.desc);
@@ -314,7 +325,7 @@ int aslam_orb_level_size(const aslam_orb *o, int level, int *w, int *h)
 }  // extern "C"
 
 // Enqueue the whole extraction of n frames whose level-0 pixels (and masks) are already in place.
-static int orb_enqueue(aslam_orb *o, int n, bool with_mask)
+static int orb_enqueue_launches(aslam_orb *o, int n, bool with_mask)
 {
     aslam_ctx *ctx = o->ctx;
     const OrbGeom &g = o->g;
@@ -330,6 +341,50 @@ static int orb_enqueue(aslam_orb *o, int n, bool with_mask)
     if ((rc = launch_blur(ctx, g, b, n))) return rc;
     if ((rc = launch_select(ctx, g, b, n))) return rc;
     if ((rc = launch_describe(ctx, g, b, n))) return rc;
+    return ASLAM_OK;
+}
+
+// The chain's launches depend only on (n, masks or not) once the handle is planned -- every kernel argument is a value
+// or a pointer into the handle's own buffers -- so the first call with a given shape is captured into a CUDA graph and
+// later calls replay it: per-frame callers (the reference runs one frame per call) pay one launch instead of twelve.
+// Not used while per-kernel profiling is on (the event pairs belong between the launches), on the legacy default stream
+// (it cannot be captured), or with ASLAM_NO_GRAPH=1 (A/B runs).
+static int orb_enqueue(aslam_orb *o, int n, bool with_mask)
+{
+    aslam_ctx *ctx = o->ctx;
+    static const bool no_graph = [] { const char *e = getenv("ASLAM_NO_GRAPH"); return e && atoi(e) != 0; }();
+    if (no_graph || ctx->prof_on || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy || ctx->stream == cudaStreamPerThread)
+        return orb_enqueue_launches(o, n, with_mask);
+    for (auto &c : o->chains)
+        if (c.n == n && c.with_mask == with_mask) {
+            ASLAM_CUDA(cudaGraphLaunch(c.exec, ctx->stream));
+            aslam::count_launch(c.launches);
+            return ASLAM_OK;
+        }
+    if (with_mask && !o->b.mask) return orb_enqueue_launches(o, n, with_mask);
+    // make sure one-time function attributes are set outside the capture, then record the chain
+    cudaGraph_t graph = nullptr;
+    const uint64_t before = aslam::g_launches.load(std::memory_order_relaxed);
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        return orb_enqueue_launches(o, n, with_mask);
+    }
+    const int rc = orb_enqueue_launches(o, n, with_mask);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    const int launches = (int)(aslam::g_launches.load(std::memory_order_relaxed) - before);
+    aslam::g_launches.fetch_sub((uint64_t)launches, std::memory_order_relaxed);      // recorded, not launched
+    cudaGraphExec_t exec = nullptr;
+    if (rc != ASLAM_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != ASLAM_OK) return rc;
+        return orb_enqueue_launches(o, n, with_mask);
+    }
+    cudaGraphDestroy(graph);
+    if (o->chains.size() >= 4) { cudaGraphExecDestroy(o->chains.front().exec); o->chains.erase(o->chains.begin()); }
+    o->chains.push_back({n, with_mask, exec, launches});
+    ASLAM_CUDA(cudaGraphLaunch(exec, ctx->stream));
+    aslam::count_launch(launches);
     return ASLAM_OK;
 }
 

@@ -245,6 +245,34 @@ def test_set_max_features_and_determinism(ctx, oracle):
     ex.close()
 
 
+def test_replayed_launch_chains_give_the_first_runs_results(ctx, oracle):
+    """The extraction chain of a call shape (frames per call, masks or not) is captured into a CUDA graph on first use
+    and replayed afterwards (csrc/orb.cu: orb_enqueue; at most four shapes are kept).  Six shapes taken in turn, three
+    times over -- so chains are replayed, evicted and captured again -- must return what the first pass returned, and
+    one of them what the oracle says."""
+    from aria_slam_b200 import synth
+    frames = synth.frame_stream(6, 640, 480, 500)
+    mask = np.zeros((480, 640), np.uint8); mask[100:400, 50:600] = 255
+    tr = _tracker(ctx, 640, 480, 800, batch=6)
+    shapes = [(1, False), (2, False), (1, True), (3, False), (6, False), (2, True)]
+    first = {}
+    for rep in range(3):
+        for n, with_mask in shapes:
+            tr.extract_async(frames[:n], masks=np.stack([mask] * n) if with_mask else None)
+            kps, desc, cnt, _, _ = tr.results()
+            got = [(kps[i, :cnt[i]].copy(), desc[i, :cnt[i]].copy()) for i in range(n)]
+            if rep == 0:
+                first[(n, with_mask)] = got
+            else:
+                for (k0, d0), (k1, d1) in zip(first[(n, with_mask)], got):
+                    assert len(k0) == len(k1) and (k0 == k1).all() and (d0 == d1).all()
+    ko, do = oracle.orb(frames[1], 800)
+    assert set(kp_keys(first[(2, False)][1][0])) == set(kp_keys(ko))
+    km, dm = oracle.orb(frames[0], 800, mask=mask)
+    assert set(kp_keys(first[(1, True)][0][0])) == set(kp_keys(km))
+    tr.close()
+
+
 def test_batch_equals_single_frames(ctx, oracle):
     """A batch launch gives every frame exactly what a single-frame launch gives it."""
     from aria_slam_b200 import synth
