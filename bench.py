@@ -636,7 +636,6 @@ def run_ours(args):
     # ---- roofline of the dominant kernel + all stages
     hbm_peak, peak_src = measured_peaks()
     popc_peak = ctx.microbench(0)                      # G popc32/s, measured on this GPU now
-    vimnmx_peak = ctx.microbench(3)                    # G VIMNMX3.U16x2 lane-ops/s
     frames_total = BATCH * K
     stages = {}
     step_ms = sum(v[0] for v in prof.values()) / K
@@ -645,6 +644,10 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
+    pipes = {}
+    pp = os.path.join(ROOT, "profiles", "pipes.json")
+    if os.path.exists(pp):
+        pipes = {k: dict(v, source=json.load(open(pp)).get("_source")) for k, v in json.load(open(pp)).items() if not k.startswith("_")}
     POPC_EXECUTED, POPC_ALGORITHMIC = 4.0, 8.0         # per descriptor pair: the carry-save form executes 4 (match.cu), SURVEY 8d counts 8
     for name, (tot_ms, n) in prof.items():
         if n == 0:
@@ -664,12 +667,9 @@ def run_ours(args):
             # far below the HBM roofline, which is why the bound above is the POPC pipe
             kb = 32.0 * float(np.sum(cnt_np[1:].astype(np.float64) + cnt_np[:-1])) * K / (tot_ms * 1e-3) / 1e9
             ent["hbm_view"] = {"bound": "hbm", "achieved": kb, "peak": hbm_peak, "unit": "GB/s", "frac": kb / hbm_peak}
-        if name == "fast_nms":
-            # why FAST is not HBM-bound: >= 40 three-input u16x2 min/max per pixel, issued on the ALU pipe
-            ops = 40.0 * BYTES_PER_FRAME["fast_nms"] * frames_total / (tot_ms * 1e-3) / 1e9
-            ent["alu_pipe"] = {"achieved": ops, "peak": vimnmx_peak, "unit": "Gops/s (VIMNMX3.U16x2 lanes)", "frac": ops / vimnmx_peak,
-                               "note": "40 ops per pyramid pixel (the kernel evaluates only the border-free ROI, so this can overstate)"}
         ent["traffic"] = traffic.get(name)
+        if name in pipes:
+            ent["ncu"] = pipes[name]        # pipe / memory utilisation of this kernel kind from the committed ncu capture
         stages[name] = ent
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     roof = dict(stages[dom]); roof["kernel"] = dom; roof["peak_source"] = peak_src if roof.get("bound") == "hbm" else "aslam_microbench(POPC) on this GPU (MEASURED_PEAKS.json has no integer-pipe entry)"

@@ -26,7 +26,7 @@ with open(prefix + '_ncu_full_summary.csv', 'w', newline='') as f:
 num = lambda v: float(v.replace(',', ''))
 ri, wi = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
 scale = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}
-names = {'resize_kernel': 'resize', 'fast_kernel': 'fast_nms', 'blur_kernel': 'blur', 'select_kernel': 'select_harris',
+names = {'resize_kernel': 'resize', 'fast_kernel': 'fast_nms', 'blur_kernel': 'blur', 'blur_march_kernel': 'blur', 'select_kernel': 'select_harris',
          'describe_kernel': 'orient_brief', 'knn2_partial_v2_kernel': 'knn2_partial', 'knn2_finish_matches_kernel': 'knn2_finish'}
 acc = {}
 for r in rows[2:]:
@@ -37,3 +37,22 @@ tr['_source'] = '%s_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_wri
                 'ncu --set full, 256 frames of 752x480, 2000 keypoints' % prefix
 json.dump(tr, open(os.path.join(os.path.dirname(prefix) or '.', 'traffic.json'), 'w'), indent=1)
 print({k: round(v / 1e6, 1) for k, v in tr.items() if k != '_source'})
+# pipes.json: what ncu measured on the pipes of each kernel kind (time-weighted mean over the launches of a kind);
+# bench.py attaches it to the stage entries as "ncu" -- a kernel far below its HBM roofline shows here which unit holds it
+cols = {'alu_pct': 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'xu_pct': 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'fma_pct': 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'lsu_pct': 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'issue_active_pct': 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex_throughput_pct': 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+        'l2_throughput_pct': 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'dram_throughput_pct': 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'warps_active_pct': 'sm__warps_active.avg.pct_of_peak_sustained_active', 'registers_per_thread': 'launch__registers_per_thread'}
+ti = hdr.index('gpu__time_duration.sum')
+pipes = {}
+for r in rows[2:]:
+    k = names.get(short(r[ki]).split('<')[0], short(r[ki]).split('<')[0])
+    t = num(r[ti])
+    e = pipes.setdefault(k, {'_t': 0.0, **{c: 0.0 for c in cols}})
+    e['_t'] += t
+    for c, m in cols.items():
+        e[c] += t * num(r[hdr.index(m)])
+out = {k: {c: round(v[c] / v['_t'], 2) for c in cols} for k, v in pipes.items() if v['_t'] > 0}
+out['_source'] = '%s_ncu_full_summary.csv (ncu --set full --clock-control none, one 256-frame step of tools/ncu_target.py)' % prefix
+json.dump(out, open(os.path.join(os.path.dirname(prefix) or '.', 'pipes.json'), 'w'), indent=1)
