@@ -1835,7 +1835,8 @@ select_kernel(OrbGeom g, OrbBuffers b)
     // --- Harris response of every survivor
     for (int i = tid; i < M1; i += SEL_THREADS) {
         const uint32_t e = surv[i];
-        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h);
+        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h &&
+                     ((((int)(e & 0xfffu) - 4) & ~3) + 12 <= L.pitch));      // the three aligned words of a window row lie inside the padded row
         hresp[i] = harris_response(img, L.pitch, (int)(e & 0xfffu), (int)((e >> 12) & 0xfffu));
     }
     __syncthreads();
@@ -2057,7 +2058,8 @@ select_kernel(OrbGeom g, OrbBuffers b)
     // --- Harris response of every survivor
     for (int i = tid; i < M1; i += SEL_THREADS) {
         const uint32_t e = surv[i];
-        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h);
+        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h &&
+                     ((((int)(e & 0xfffu) - 4) & ~3) + 12 <= L.pitch));      // the three aligned words of a window row lie inside the padded row
         hresp[i] = harris_response(img, L.pitch, (int)(e & 0xfffu), (int)((e >> 12) & 0xfffu));
     }
     __syncthreads();

@@ -144,7 +144,10 @@ ASLAM_API int aslam_orb_capacity(const aslam_orb *orb);
  * (src/main.cpp:29-41) remove keypoints inside them after selection
  * (SlamPipeline::filterDynamicKeypoints, include/pipeline/SlamPipeline.hpp:96-99, using
  * Detection::contains, include/core/Types.hpp:109-111).
- * The pixel buffers must stay valid until aslam_orb_sync returns. */
+ * The pixel buffers must stay valid until aslam_orb_sync returns.
+ * The launch chain of a call shape (frames per call, masks or not) is captured into a CUDA graph on first use and replayed
+ * by later calls of the same shape (not on the legacy default stream, not while aslam_prof_* timing is on;
+ * ASLAM_NO_GRAPH=1 in the environment disables it). */
 ASLAM_API int aslam_orb_extract_async(aslam_orb *orb, const uint8_t *image, int width, int height,
                                       int row_stride, const uint8_t *mask,
                                       const aslam_box *boxes, int nboxes);
