@@ -333,9 +333,13 @@ static int orb_enqueue_launches(aslam_orb *o, int n, bool with_mask)
     if (!with_mask) b.mask = nullptr;
     int rc;
     ASLAM_CUDA(cudaMemsetAsync(o->b.overflow + 1, 0, sizeof(int32_t) * n, ctx->stream));
-    for (int l = 1; l < g.nbuilt; ++l) {
-        if ((rc = launch_resize_level(ctx, g, b, l, n, false))) return rc;
-        if (with_mask && (rc = launch_resize_level(ctx, g, b, l, n, true))) return rc;
+    if (g.nbuilt > 1 && pyramid_cluster_wanted(n)) {
+        if ((rc = launch_pyramid_cluster(ctx, g, b, n, with_mask))) return rc;
+    } else {
+        for (int l = 1; l < g.nbuilt; ++l) {
+            if ((rc = launch_resize_level(ctx, g, b, l, n, false))) return rc;
+            if (with_mask && (rc = launch_resize_level(ctx, g, b, l, n, true))) return rc;
+        }
     }
     if ((rc = launch_fast(ctx, g, b, n))) return rc;
     if ((rc = launch_blur(ctx, g, b, n))) return rc;

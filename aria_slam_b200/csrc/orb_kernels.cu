@@ -92,28 +92,32 @@ static_assert(ASLAM_RS_DEPTH == 2 || ASLAM_RS_DEPTH == 4, "resize prefetch depth
 
 // THRESH: the mask pyramid's levels are thresholded (threshold(254, TOZERO)); image levels skip those 12 instructions per
 // group of 4 pixels (the kernel is bound by instruction issue: 73 % issue-active at 44 % ALU and 34 % DRAM on level 1).
-template <bool THRESH>
-__global__ void __launch_bounds__(256)
-resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
-              LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs)
+// NC: the source level is read-only for the whole kernel (ld.global.nc); false inside pyramid_cluster_kernel, where a level
+// is written by the same launch that reads it.
+template <bool NC>
+__device__ __forceinline__ uint32_t rs_load(const uint32_t *p)
 {
-    // a CTA's warps sit side by side on the same strip of rows, so the CTA reads and writes whole row segments
-    const int cg = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y0 = blockIdx.y * RS_ROWS;
-    if (cg * 4 >= D.w || y0 >= D.h) return;
+    if (NC) return __ldg(p);
+    uint32_t v;         // an ordinary cached load that the compiler cannot turn into ld.global.nc or move across the cluster barrier
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <bool THRESH, bool NC>
+__device__ __forceinline__ void resize_strip_task(unsigned long long sbase, unsigned long long dbase, const LevelGeom &S, const LevelGeom &D,
+                                                  const uint32_t *__restrict__ tabs, int cg, int y0, int rows)
+{
     // CTA-uniform bases + 32-bit per-thread offsets (a frame's pyramid is far below 4 GB)
     // The frame's base pointers are CTA-uniform.  Passed through an empty asm they stay in ordinary registers; left to the
     // compiler they are re-derived from blockIdx.z and the parameters on the uniform datapath for every source row and
     // every emitted row (8 + 10 of the loop's ~60 instructions per group of 4 pixels).
-    unsigned long long sbase = reinterpret_cast<unsigned long long>(srcb + (size_t)blockIdx.z * stride + S.off);
-    unsigned long long dbase = reinterpret_cast<unsigned long long>(dstb + (size_t)blockIdx.z * stride + D.off);
     asm volatile("" : "+l"(sbase), "+l"(dbase));
     const uint32_t *src = reinterpret_cast<const uint32_t *>(sbase);
     uint32_t *dst = reinterpret_cast<uint32_t *>(dbase);
     const uint4 *ct = reinterpret_cast<const uint4 *>(tabs + D.xtab_off) + 2 * cg;
     const uint4 t0 = __ldg(ct), t1 = __ldg(ct + 1);
     const uint32_t *ytab = tabs + D.ytab_off;
-    const uint32_t yend = (uint32_t)min(y0 + RS_ROWS, D.h);
+    const uint32_t yend = (uint32_t)min(y0 + rows, D.h);
     const uint32_t pw = (uint32_t)S.pitch >> 2, dpw = (uint32_t)D.pitch >> 2;
     const uint32_t so_last = t0.x + (uint32_t)(S.h - 1) * pw;     // window offset in the last source row
 
@@ -124,14 +128,14 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
     // raw words of the next RS_DEPTH source rows are always in flight (the kernel waits on load latency -- 47 % of its
     // stall cycles are long-scoreboard -- not on instruction issue)
     uint32_t so = t0.x + (uint32_t)s_row * pw;
-    uint32_t a0 = __ldg(src + so), a1 = __ldg(src + so + 1), a2 = __ldg(src + so + 2);
+    uint32_t a0 = rs_load<NC>(src + so), a1 = rs_load<NC>(src + so + 1), a2 = rs_load<NC>(src + so + 2);
     so = min(so + pw, so_last);
-    uint32_t b0 = __ldg(src + so), b1 = __ldg(src + so + 1), b2 = __ldg(src + so + 2);
+    uint32_t b0 = rs_load<NC>(src + so), b1 = rs_load<NC>(src + so + 1), b2 = rs_load<NC>(src + so + 2);
 #if ASLAM_RS_DEPTH == 4
     so = min(so + pw, so_last);
-    uint32_t c0 = __ldg(src + so), c1 = __ldg(src + so + 1), c2 = __ldg(src + so + 2);
+    uint32_t c0 = rs_load<NC>(src + so), c1 = rs_load<NC>(src + so + 1), c2 = rs_load<NC>(src + so + 2);
     so = min(so + pw, so_last);
-    uint32_t d0 = __ldg(src + so), d1 = __ldg(src + so + 1), d2 = __ldg(src + so + 2);
+    uint32_t d0 = rs_load<NC>(src + so), d1 = rs_load<NC>(src + so + 1), d2 = rs_load<NC>(src + so + 2);
 #endif
     // per-thread running pointers (the destination word and the row-table entry advance by constants): without them the
     // compiler rebuilds both base addresses on the uniform datapath for every emitted row -- 17 of an emit's 42 instructions
@@ -144,7 +148,7 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
         H = resize_hrow(N0, N1, N2, t0, t1);                                \
         so = min(so + pw, so_last);                                         \
         ASLAM_BOUNDS((size_t)(so + 3) * 4 <= (size_t)S.pitch * S.h + 256);  /* the third word may touch the 256-B level padding */ \
-        N0 = __ldg(src + so); N1 = __ldg(src + so + 1); N2 = __ldg(src + so + 2); \
+        N0 = rs_load<NC>(src + so); N1 = rs_load<NC>(src + so + 1); N2 = rs_load<NC>(src + so + 2); \
     } while (0)
 #define ASLAM_RS_EMIT(OLD, NEW)                                             \
     while ((int)(e & 0xffffu) + 1 == s_row) {                               \
@@ -183,6 +187,19 @@ resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
     }
 #undef ASLAM_RS_HROW
 #undef ASLAM_RS_EMIT
+}
+
+template <bool THRESH>
+__global__ void __launch_bounds__(256)
+resize_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
+              LevelGeom S, LevelGeom D, const uint32_t *__restrict__ tabs)
+{
+    // a CTA's warps sit side by side on the same strip of rows, so the CTA reads and writes whole row segments
+    const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * RS_ROWS;
+    if (cg * 4 >= D.w || y0 >= D.h) return;
+    resize_strip_task<THRESH, true>(reinterpret_cast<unsigned long long>(srcb + (size_t)blockIdx.z * stride + S.off),
+                                    reinterpret_cast<unsigned long long>(dstb + (size_t)blockIdx.z * stride + D.off), S, D, tabs, cg, y0, RS_ROWS);
 }
 
 // ---- round 2, second form: the same march with its control flow taken off the memory system.  resize_kernel decides
@@ -397,6 +414,68 @@ resize_smem_kernel(const uint8_t *srcb, uint8_t *dstb, unsigned int stride,
 #ifndef ASLAM_RS_SMEM
 #define ASLAM_RS_SMEM 0         // 1: the staged form (kept for A/B runs and for GPUs where it wins); 0: direct loads
 #endif
+// ---- the whole level chain of a frame in ONE launch: a thread-block cluster per frame walks the levels, a cluster barrier
+// (release / acquire at cluster scope: the level just written is visible to, and its stale L1 lines dropped by, every CTA of
+// the cluster) between them.  For calls with few frames, where seven dependent launches of a few microseconds each are most
+// of the pyramid's latency (one 752 x 480 frame: 60 us of the 117 us of kernel time with per-level launches).  Same strip
+// march as resize_kernel (resize_strip_task), the strip height chosen per level so that a level is about one pass of the
+// cluster's threads; the mask pyramid's levels are further tasks of the same pass.
+constexpr int PYR_CLUSTER = 8, PYR_THREADS = 512;
+template <bool WITH_MASK>
+__global__ void __launch_bounds__(PYR_THREADS)
+pyramid_cluster_kernel(OrbGeom g, OrbBuffers b)
+{
+    const int frame = blockIdx.y;
+    const int tid_c = (int)blockIdx.x * PYR_THREADS + (int)threadIdx.x, nthr = PYR_CLUSTER * PYR_THREADS;
+    const unsigned long long ibase = reinterpret_cast<unsigned long long>(b.pyr + (size_t)frame * g.pyr_stride);
+    const unsigned long long mbase = WITH_MASK ? reinterpret_cast<unsigned long long>(b.mask + (size_t)frame * g.pyr_stride) : 0ull;
+#pragma unroll 1
+    for (int l = 1; l < g.nbuilt; ++l) {
+        const LevelGeom S = g.lv[l - 1], D = g.lv[l];
+        const int ncg = (D.w + 3) >> 2;
+        // rows per strip: a multiple of 4 in [4, RS_ROWS] that gives the cluster's threads about one task each
+        int rows = (int)(((long long)D.h * ncg * (WITH_MASK ? 2 : 1) + nthr - 1) / nthr);
+        rows = min(RS_ROWS, max(4, (rows + 3) & ~3));
+        const int nstrips = (D.h + rows - 1) / rows, ntasks = ncg * nstrips;
+        for (int t = tid_c; t < (WITH_MASK ? 2 : 1) * ntasks; t += nthr) {
+            const bool is_mask = WITH_MASK && t >= ntasks;
+            const int tt = is_mask ? t - ntasks : t;
+            const int strip = tt / ncg, cg = tt - strip * ncg;
+            if (is_mask) resize_strip_task<true, false>(mbase + S.off, mbase + D.off, S, D, b.tabs, cg, strip * rows, rows);
+            else resize_strip_task<false, false>(ibase + S.off, ibase + D.off, S, D, b.tabs, cg, strip * rows, rows);
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+}
+
+#ifndef ASLAM_PYR_CLUSTER_MAX
+#define ASLAM_PYR_CLUSTER_MAX 8     // calls with at most this many frames build the pyramid with pyramid_cluster_kernel (0 = never).  Alone on the GPU the
+                                    // cluster form wins up to ~32 frames per call (resize 76 -> 38 us at 32), but under 8 concurrent frame streams of 32
+                                    // frames its CTAs idle at the barriers while other streams wait for SM slots: 88.4 k vs 91.9 k frames/s in bench.py
+#endif
+int launch_pyramid_cluster(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes, bool with_mask)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PYR_CLUSTER, nframes, 1);
+    cfg.blockDim = dim3(PYR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PYR_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ProfScope ps(ctx, PK_RESIZE);
+    if (with_mask) ASLAM_CUDA(cudaLaunchKernelEx(&cfg, pyramid_cluster_kernel<true>, g, b));
+    else ASLAM_CUDA(cudaLaunchKernelEx(&cfg, pyramid_cluster_kernel<false>, g, b));
+    ASLAM_LAUNCH_CHECK();
+    return ASLAM_OK;
+}
+bool pyramid_cluster_wanted(int nframes)
+{
+    static const int lim = [] { const char *e = getenv("ASLAM_PYR_CLUSTER_MAX"); return e ? atoi(e) : ASLAM_PYR_CLUSTER_MAX; }();
+    return nframes <= lim;
+}
+
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask)
 {
     const LevelGeom &D = g.lv[level], &S = g.lv[level - 1];

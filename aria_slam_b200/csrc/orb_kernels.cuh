@@ -37,6 +37,9 @@ struct OrbBuffers {
 };
 
 int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int level, int nframes, bool is_mask);
+// all levels (and the mask's) of every frame in one launch, a thread-block cluster per frame; for calls with few frames
+int launch_pyramid_cluster(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes, bool with_mask);
+bool pyramid_cluster_wanted(int nframes);
 int launch_fast(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);
 int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);
 int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes);

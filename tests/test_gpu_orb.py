@@ -54,10 +54,11 @@ def test_pyramid_levels_bit_exact(ctx, oracle, w, h, seed):
     tr.close()
 
 
-@pytest.mark.parametrize("w,h,batch", [(752, 480, 17), (333, 257, 16), (161, 203, 33)])
+@pytest.mark.parametrize("w,h,batch", [(752, 480, 17), (333, 257, 16), (161, 203, 33), (752, 480, 3), (333, 257, 8), (161, 203, 2)])
 def test_pyramid_levels_bit_exact_in_batches(ctx, oracle, w, h, batch):
-    """Batches of 16 frames or more go through the resize two frames per thread (an odd batch repeats its last frame):
-    every level of the first, a middle and the last frame against the oracle, with a mask pyramid alongside."""
+    """Calls with up to 8 frames build the pyramid in one launch (a thread-block cluster per frame walks the levels,
+    pyramid_cluster_kernel), larger ones level by level: every level of the first, a middle and the last frame against the
+    oracle, with a mask pyramid alongside, in both forms."""
     from aria_slam_b200 import synth
     from aria_slam_b200.frontend import OrbBatchTracker
     imgs = np.stack([synth.frame(w, h, 70 + i) for i in range(3)])
