@@ -43,7 +43,9 @@ static_assert(BL_W % 8 == 0 && BL_ROWS % 2 == 0 && BL_W * BL_ROWS * 4 <= 48 * 10
 #define ASLAM_DESC_TMA 1       // 1: patches arrive by TMA box loads (the shipped kernel); 0: round 1's LDG staging, kept for A/B runs
 #endif
 #ifndef ASLAM_DESC_WARPS
-#define ASLAM_DESC_WARPS (ASLAM_DESC_TMA ? 4 : 8)
+// TMA form: warps are independent (own rings, own mbarriers, no CTA barrier), so a CTA is ONE warp: 27 CTAs fit an SM by shared
+// memory where six 4-warp CTAs gave 24 warps, and single warps slot in beside other streams' kernels (0.305 -> 0.289 ms; 2 warps 0.296)
+#define ASLAM_DESC_WARPS (ASLAM_DESC_TMA ? 1 : 8)
 #endif
 constexpr int DESC_KPW = ASLAM_DESC_KPW, DESC_WARPS = ASLAM_DESC_WARPS;
 static_assert(DESC_KPW >= 1 && DESC_KPW <= 32, "a lane owns one of the warp's keypoints");

@@ -448,6 +448,9 @@ pyramid_cluster_kernel(OrbGeom g, OrbBuffers b)
     }
 }
 
+#ifndef ASLAM_RS_WARPS
+#define ASLAM_RS_WARPS 8           // warps per resize CTA (side by side on a strip of rows)
+#endif
 #ifndef ASLAM_PYR_CLUSTER_MAX
 #define ASLAM_PYR_CLUSTER_MAX 8     // calls with at most this many frames build the pyramid with pyramid_cluster_kernel (0 = never).  Alone on the GPU the
                                     // cluster form wins up to ~32 frames per call (resize 76 -> 38 us at 32), but under 8 concurrent frame streams of 32
@@ -500,7 +503,7 @@ int launch_resize_level(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, i
         return ASLAM_OK;
     }
 #endif
-    const int warps = min(8, (cgs + 31) / 32);
+    const int warps = min(ASLAM_RS_WARPS, (cgs + 31) / 32);
 #if ASLAM_RS_MARCH
     if (D.rs_fast) {
         // several frames per thread only once there are enough of them to fill the GPU anyway
@@ -1645,7 +1648,6 @@ int launch_blur(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfram
 // Harris response for the survivors, retainBest(N) via a radix select on the float bits; ties
 // with the cut-off are all kept, as KeyPointsFilter::retainBest does.  Survivor order is the
 // candidate order (tile-major, row-major inside a tile): deterministic, no atomics on positions.
-constexpr int SEL_THREADS = 512;
 
 // HarrisResponses(blockSize 7, k 0.04f): integer sums, then a fixed unfused float expression.
 #ifndef ASLAM_HARRIS_DP4A
@@ -1756,26 +1758,24 @@ __device__ __forceinline__ int warp_kth_bin_from_top(const int *hist, int k, int
     return __shfl_sync(0xffffffffu, bin, owner);
 }
 
-#ifndef ASLAM_SEL_V2
-#define ASLAM_SEL_V2 1          // 1: round 2's selection (12 barriers per CTA); 0: round 1's (about 30)
-#endif
-#if ASLAM_SEL_V2
+// (round 1's form of this kernel -- per-tile counts through global memory, a scan over tiles, three barriers per radix pass,
+// 512-thread CTAs only -- measured 0.157 ms per 256 frames against 0.148 for this one at 512 threads and 0.121 at 256.)
 // K-th largest of the 32-bit keys key_of(i, key) (false = element i does not take part), i in [0, M), by
 // 4 x 8-bit radix passes; at least K >= 1 elements must take part.  Called by the whole CTA.  Returns that key;
 // k_left = how many of the elements equal to it are needed to reach K (>= 1).
 // One barrier per pass: each pass has a histogram of its own (hist4[pass][256], zeroed together up front), the first two
 // keys of a thread stay in registers, and EVERY warp finds the pass's bin from the finished histogram by itself, so the
 // prefix and the remaining count never travel through shared memory.
-template <class KeyFn>
+template <int THREADS, class KeyFn>
 __device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of, int *hist4, int &k_left)
 {
     const int tid = threadIdx.x;
-    for (int i = tid; i < 4 * 256; i += SEL_THREADS) hist4[i] = 0;
+    for (int i = tid; i < 4 * 256; i += THREADS) hist4[i] = 0;
     uint32_t kreg[2] = {0u, 0u};
     bool kval[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const int i = tid + j * SEL_THREADS;
+        const int i = tid + j * THREADS;
         kval[j] = i < M && key_of(i, kreg[j]);
     }
     __syncthreads();
@@ -1787,7 +1787,7 @@ __device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of
 #pragma unroll
         for (int j = 0; j < 2; ++j)
             if (kval[j] && (kreg[j] & maskbits) == prefix) atomicAdd(&h[(kreg[j] >> (8 * pass)) & 0xffu], 1);
-        for (int i = tid + 2 * SEL_THREADS; i < M; i += SEL_THREADS) {
+        for (int i = tid + 2 * THREADS; i < M; i += THREADS) {
             uint32_t key;
             if (key_of(i, key) && (key & maskbits) == prefix) atomicAdd(&h[(key >> (8 * pass)) & 0xffu], 1);
         }
@@ -1845,17 +1845,17 @@ __device__ __forceinline__ void for_each_candidate(const uint32_t *__restrict__ 
 // Round 2: every warp owns a CONTIGUOUS range of the level's tiles, so the ordered compaction needs one exchange of 16
 // warp totals instead of per-tile counts through global memory and a scan over the tiles; the cut-off bins are found by
 // every warp for itself; the output pass hands every warp a contiguous range of survivors in the same way.
-template <bool BUCKET>
-__global__ void __launch_bounds__(SEL_THREADS, 2)
+template <bool BUCKET, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 select_kernel(OrbGeom g, OrbBuffers b)
 {
     __shared__ int hist4[4 * 256];
-    __shared__ int warp_sums[SEL_THREADS / 32];
-    __shared__ int warp_sums2[SEL_THREADS / 32];
+    __shared__ int warp_sums[THREADS / 32];
+    __shared__ int warp_sums2[THREADS / 32];
 
     const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = SEL_THREADS / 32;
+    constexpr int NWARPS = THREADS / 32;
     const LevelGeom L = g.lv[l];
     const int ntiles = L.tiles_x * L.tiles_y;
     int32_t *sel_cnt = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS + l;
@@ -1874,7 +1874,7 @@ select_kernel(OrbGeom g, OrbBuffers b)
 
     // --- retainBest(2N) threshold on the integer FAST score
     int *hist = hist4;
-    for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+    for (int i = tid; i < 256; i += THREADS) hist[i] = 0;
     __syncthreads();
     for_each_candidate(cand, ccnt, t_begin, t_end, lane, [&](uint32_t e, bool valid) {
         if (valid) atomicAdd(&hist[e >> 24], 1);
@@ -1912,7 +1912,7 @@ select_kernel(OrbGeom g, OrbBuffers b)
     __syncthreads();
 
     // --- Harris response of every survivor
-    for (int i = tid; i < M1; i += SEL_THREADS) {
+    for (int i = tid; i < M1; i += THREADS) {
         const uint32_t e = surv[i];
         ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h &&
                      ((((int)(e & 0xfffu) - 4) & ~3) + 12 <= L.pitch));      // the three aligned words of a window row lie inside the padded row
@@ -1928,26 +1928,26 @@ select_kernel(OrbGeom g, OrbBuffers b)
     [[maybe_unused]] uint32_t *rank = nullptr;
     if constexpr (!BUCKET) {
         if (M1 > K2)
-            cut = block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return true; }, hist4, k_left);
+            cut = block_kth_largest<THREADS>(M1, K2, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return true; }, hist4, k_left);
     } else {
         // Grid-bucketed cull: rank of a survivor = how many survivors of its cell have a greater response; order by
         // (rank ascending, response descending), keep the first K2 and everything tied with the K2-th.
         rank = b.rank + tile0 * FT_CAP;
         if (M1 > K2) {
-            __shared__ uint2 s_ck[SEL_THREADS];        // (cell id, ordered response key) of a block of survivors
+            __shared__ uint2 s_ck[THREADS];        // (cell id, ordered response key) of a block of survivors
             const int cell = g.grid_cell;
             auto cell_of = [&](uint32_t e) { return ((e & 0xfffu) / (uint32_t)cell) | ((((e >> 12) & 0xfffu) / (uint32_t)cell) << 12); };
-            for (int i0 = 0; i0 < M1; i0 += SEL_THREADS) {
+            for (int i0 = 0; i0 < M1; i0 += THREADS) {
                 const int i = i0 + tid;
                 const uint32_t mycell = i < M1 ? cell_of(surv[i]) : 0xfffffffeu;
                 const uint32_t mykey = i < M1 ? float_order_key(hresp[i]) : 0u;
                 uint32_t r = 0;
-                for (int j0 = 0; j0 < M1; j0 += SEL_THREADS) {
+                for (int j0 = 0; j0 < M1; j0 += THREADS) {
                     __syncthreads();
                     const int j = j0 + tid;
                     s_ck[tid] = j < M1 ? make_uint2(cell_of(surv[j]), float_order_key(hresp[j])) : make_uint2(0xffffffffu, 0u);
                     __syncthreads();
-                    const int n = min(SEL_THREADS, M1 - j0);        // padding entries match no cell: whole groups of 4 are safe
+                    const int n = min(THREADS, M1 - j0);        // padding entries match no cell: whole groups of 4 are safe
 #pragma unroll 4
                     for (int k = 0; k < ((n + 3) & ~3); ++k) {
                         const uint2 o = s_ck[k];                    // one broadcast 64-bit load
@@ -1957,9 +1957,9 @@ select_kernel(OrbGeom g, OrbBuffers b)
                 if (i < M1) rank[i] = r;
             }
             __syncthreads();
-            rank_cut = ~block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = ~rank[i]; return true; }, hist4, k_left);
+            rank_cut = ~block_kth_largest<THREADS>(M1, K2, [&](int i, uint32_t &key) { key = ~rank[i]; return true; }, hist4, k_left);
             const uint32_t R = rank_cut;
-            cut = block_kth_largest(M1, k_left, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return rank[i] == R; },
+            cut = block_kth_largest<THREADS>(M1, k_left, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return rank[i] == R; },
                                     hist4, k_left);
         }
     }
@@ -2008,225 +2008,28 @@ select_kernel(OrbGeom g, OrbBuffers b)
         if (written > L.sel_cap) atomicOr(b.overflow + frame + 1, 1);
     }
 }
-#else
-// K-th largest of the 32-bit keys key_of(i, key) (false = element i does not take part), i in [0, M), by
-// 4 x 8-bit radix passes; at least K >= 1 elements must take part.  Called by the whole CTA.  Returns that key;
-// k_left = how many of the elements equal to it are needed to reach K (>= 1).
-template <class KeyFn>
-__device__ __forceinline__ uint32_t block_kth_largest(int M, int K, KeyFn key_of, int *hist, uint32_t *s_prefix, int *s_k,
-                                                      int &k_left)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { *s_prefix = 0; *s_k = K; }
-    uint32_t maskbits = 0;
-    for (int pass = 3; pass >= 0; --pass) {
-        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-        __syncthreads();
-        const uint32_t prefix = *s_prefix;
-        for (int i = tid; i < M; i += SEL_THREADS) {
-            uint32_t key;
-            if (key_of(i, key) && (key & maskbits) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 0xffu], 1);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            int above;
-            const int bin = warp_kth_bin_from_top(hist, *s_k, above);     // exists: the prefix class holds >= s_k keys
-            if (lane == 0) {
-                *s_k -= above;
-                *s_prefix = prefix | ((uint32_t)bin << (8 * pass));
-            }
-        }
-        maskbits |= 0xffu << (8 * pass);
-        __syncthreads();
-    }
-    const uint32_t kth = *s_prefix;
-    k_left = *s_k;
-    __syncthreads();          // the next call re-arms s_prefix / s_k
-    return kth;
-}
 
-// BUCKET = the grid-bucketed second cull (g.grid_cell > 0), an extension cv::ORB does not have; its definition is
-// in include/aslam_b200.h (aslam_orb_params::grid_cell) and DESIGN.md section 4a.
-// (58 registers, 2 CTAs per SM.  Measured: forcing 3 CTAs per SM spills Harris' rows and gains nothing, 0.214 ms either way;
-// 4 CTAs: 0.236; "at least 1" lets the compiler take 119 registers: 0.292.)
-template <bool BUCKET>
-__global__ void __launch_bounds__(SEL_THREADS, 2)
-select_kernel(OrbGeom g, OrbBuffers b)
-{
-    __shared__ int hist[256];
-    __shared__ int warp_sums[SEL_THREADS / 32];
-    __shared__ int s_thr;
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_k;
-
-    const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = SEL_THREADS / 32;
-    const LevelGeom L = g.lv[l];
-    const int ntiles = L.tiles_x * L.tiles_y;
-    int32_t *sel_cnt = b.sel_cnt + (size_t)frame * ORB_MAX_LEVELS + l;
-    if (ntiles == 0) {
-        if (tid == 0) *sel_cnt = 0;
-        return;
-    }
-    const size_t tile0 = (size_t)frame * g.tiles_per_frame + L.tile_off;
-    const uint32_t *cand = b.cand + tile0 * FT_CAP;
-    const uint32_t *ccnt = b.cand_cnt + tile0;
-    uint32_t *tbase = b.tile_base + tile0;
-    uint32_t *surv = b.surv + tile0 * FT_CAP;
-    float *hresp = b.hresp + tile0 * FT_CAP;
-    const uint8_t *img = b.pyr + (size_t)frame * g.pyr_stride + L.off;
-
-    // --- retainBest(2N) threshold on the integer FAST score
-    for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-    __syncthreads();
-    for (int t = warp; t < ntiles; t += NWARPS) {
-        const int n = (int)ccnt[t];
-        for (int i = lane; i < n; i += 32) atomicAdd(&hist[cand[(size_t)t * FT_CAP + i] >> 24], 1);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // keep everything if there are at most K1 candidates, else cut at the K1-th largest score (ties kept)
-        int above;
-        const int bin = warp_kth_bin_from_top(hist, 2 * L.quota + 1, above);      // >= K1+1 exist <=> total > K1
-        int thr = 0;
-        if (bin >= 0) thr = warp_kth_bin_from_top(hist, 2 * L.quota, above);
-        if (lane == 0) s_thr = thr;
-    }
-    __syncthreads();
-    const uint32_t thr = (uint32_t)s_thr;
-
-    // --- ordered compaction of the survivors: per-tile counts, scan over tiles, ranked writes
-    for (int t = warp; t < ntiles; t += NWARPS) {
-        const int n = (int)ccnt[t];
-        int cnt = 0;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const bool pass = i < n && (cand[(size_t)t * FT_CAP + i] >> 24) >= thr;
-            cnt += __popc(__ballot_sync(0xffffffffu, pass));
-        }
-        if (lane == 0) tbase[t] = (uint32_t)cnt;
-    }
-    __syncthreads();
-    int running = 0;
-    for (int t0 = 0; t0 < ntiles; t0 += SEL_THREADS) {
-        const int t = t0 + tid;
-        const int v = t < ntiles ? (int)tbase[t] : 0;
-        int total;
-        const int ex = block_excl_scan<SEL_THREADS>(v, warp_sums, total);
-        if (t < ntiles) tbase[t] = (uint32_t)(running + ex);
-        running += total;
-    }
-    const int M1 = running;
-    __syncthreads();
-    for (int t = warp; t < ntiles; t += NWARPS) {
-        const int n = (int)ccnt[t];
-        int base = (int)tbase[t];
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const uint32_t e = i < n ? cand[(size_t)t * FT_CAP + i] : 0u;
-            const bool pass = i < n && (e >> 24) >= thr;
-            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-            ASLAM_BOUNDS(!pass || base + 32 <= ntiles * FT_CAP + 32);
-            if (pass) surv[base + __popc(bal & ((1u << lane) - 1u))] = e;
-            base += __popc(bal);
-        }
-    }
-    __syncthreads();
-
-    // --- Harris response of every survivor
-    for (int i = tid; i < M1; i += SEL_THREADS) {
-        const uint32_t e = surv[i];
-        ASLAM_BOUNDS((int)(e & 0xfffu) >= 4 && (int)(e & 0xfffu) + 4 < L.w && (int)((e >> 12) & 0xfffu) >= 4 && (int)((e >> 12) & 0xfffu) + 4 < L.h &&
-                     ((((int)(e & 0xfffu) - 4) & ~3) + 12 <= L.pitch));      // the three aligned words of a window row lie inside the padded row
-        hresp[i] = harris_response(img, L.pitch, (int)(e & 0xfffu), (int)((e >> 12) & 0xfffu));
-    }
-    __syncthreads();
-
-    // --- retainBest(N): K-th largest response by a radix select over the ordered key
-    uint32_t cut = 0;   // keep keys >= cut
-    const int K2 = L.quota;
-    int k_left;
-    [[maybe_unused]] uint32_t rank_cut = 0xffffffffu;     // BUCKET: keep ranks < rank_cut, and rank == rank_cut with key >= cut
-    [[maybe_unused]] uint32_t *rank = nullptr;
-    if constexpr (!BUCKET) {
-        if (M1 > K2)
-            cut = block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return true; },
-                                    hist, &s_prefix, &s_k, k_left);
-    } else {
-        // Grid-bucketed cull: rank of a survivor = how many survivors of its cell have a greater response; order by
-        // (rank ascending, response descending), keep the first K2 and everything tied with the K2-th.
-        rank = b.rank + tile0 * FT_CAP;
-        if (M1 > K2) {
-            __shared__ uint2 s_ck[SEL_THREADS];        // (cell id, ordered response key) of a block of survivors
-            const int cell = g.grid_cell;
-            auto cell_of = [&](uint32_t e) { return ((e & 0xfffu) / (uint32_t)cell) | ((((e >> 12) & 0xfffu) / (uint32_t)cell) << 12); };
-            for (int i0 = 0; i0 < M1; i0 += SEL_THREADS) {
-                const int i = i0 + tid;
-                const uint32_t mycell = i < M1 ? cell_of(surv[i]) : 0xfffffffeu;
-                const uint32_t mykey = i < M1 ? float_order_key(hresp[i]) : 0u;
-                uint32_t r = 0;
-                for (int j0 = 0; j0 < M1; j0 += SEL_THREADS) {
-                    __syncthreads();
-                    const int j = j0 + tid;
-                    s_ck[tid] = j < M1 ? make_uint2(cell_of(surv[j]), float_order_key(hresp[j])) : make_uint2(0xffffffffu, 0u);
-                    __syncthreads();
-                    const int n = min(SEL_THREADS, M1 - j0);        // padding entries match no cell: whole groups of 4 are safe
-#pragma unroll 4
-                    for (int k = 0; k < ((n + 3) & ~3); ++k) {
-                        const uint2 o = s_ck[k];                    // one broadcast 64-bit load
-                        r += (o.x == mycell) & (o.y > mykey);
-                    }
-                }
-                if (i < M1) rank[i] = r;
-            }
-            __syncthreads();
-            rank_cut = ~block_kth_largest(M1, K2, [&](int i, uint32_t &key) { key = ~rank[i]; return true; },
-                                          hist, &s_prefix, &s_k, k_left);
-            const uint32_t R = rank_cut;
-            cut = block_kth_largest(M1, k_left, [&](int i, uint32_t &key) { key = float_order_key(hresp[i]); return rank[i] == R; },
-                                    hist, &s_prefix, &s_k, k_left);
-        }
-    }
-
-    // --- ordered output
-    uint32_t *sel_xy = b.sel_xy + (size_t)frame * g.kp_cap + L.sel_off;
-    float *sel_resp = b.sel_resp + (size_t)frame * g.kp_cap + L.sel_off;
-    int written = 0;
-    for (int i0 = 0; i0 < M1; i0 += SEL_THREADS) {
-        const int i = i0 + tid;
-        float r = 0.f;
-        bool pass = false;
-        if (i < M1) {
-            r = hresp[i];
-            pass = float_order_key(r) >= cut;
-            if constexpr (BUCKET)
-                if (M1 > K2) pass = rank[i] < rank_cut || (rank[i] == rank_cut && pass);
-        }
-        int total;
-        const int ex = block_excl_scan<SEL_THREADS>(pass ? 1 : 0, warp_sums, total);
-        const int pos = written + ex;
-        if (pass && pos < L.sel_cap) {
-            sel_xy[pos] = surv[i] & 0xffffffu;
-            sel_resp[pos] = r;
-        }
-        written += total;
-    }
-    if (tid == 0) {
-        *sel_cnt = min(written, L.sel_cap);
-        if (written > L.sel_cap) atomicOr(b.overflow + frame + 1, 1);
-    }
-}
-
+#ifndef ASLAM_SEL_SMALL_THREADS
+#define ASLAM_SEL_SMALL_THREADS 128
 #endif
-
 int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes)
 {
     if (g.nbuilt == 0) return ASLAM_OK;
     dim3 grid(g.nbuilt, nframes);
     ProfScope ps(ctx, PK_SELECT);
-    if (g.grid_cell > 0) select_kernel<true><<<grid, SEL_THREADS, 0, ctx->stream>>>(g, b);
-    else select_kernel<false><<<grid, SEL_THREADS, 0, ctx->stream>>>(g, b);
+    // CTA size by call size.  A level's CTA is a chain of short phases; with enough (frame, level) pairs to fill the GPU,
+    // four 256-thread CTAs per SM interleave their phases better than two of 512 (0.149 -> 0.121 ms per 256 frames; 128
+    // threads: 0.123), while a call with few frames wants the most threads per level (one frame: 21 us with 512 threads,
+    // 25 with 256, 35 with 128; 1024 threads gain nothing: 24 us).
+    static const int small_from = [] { const char *e = getenv("ASLAM_SEL_SMALL_FROM"); return e ? atoi(e) : 16; }();
+    const bool small = nframes >= small_from;
+    if (g.grid_cell > 0) {
+        if (small) select_kernel<true, ASLAM_SEL_SMALL_THREADS><<<grid, ASLAM_SEL_SMALL_THREADS, 0, ctx->stream>>>(g, b);
+        else select_kernel<true, 512><<<grid, 512, 0, ctx->stream>>>(g, b);
+    } else {
+        if (small) select_kernel<false, ASLAM_SEL_SMALL_THREADS><<<grid, ASLAM_SEL_SMALL_THREADS, 0, ctx->stream>>>(g, b);
+        else select_kernel<false, 512><<<grid, 512, 0, ctx->stream>>>(g, b);
+    }
     ASLAM_LAUNCH_CHECK();
     return ASLAM_OK;
 }

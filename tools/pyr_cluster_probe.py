@@ -27,6 +27,6 @@ for B in (1, 2, 4, 8, 16, 32, 64, 256):
     ctx.sync()
     st = ctx.prof_read(reset=True)
     ctx.prof_enable(False)
-    out[str(B)] = {"extract_wall_ms": round(wall, 4), "resize_ms_events": round(st["resize"][0] / K, 4)}
+    out[str(B)] = {"extract_wall_ms": round(wall, 4), "resize_ms_events": round(st["resize"][0] / K, 4), "select_ms_events": round(st["select_harris"][0] / K, 4)}
     tr.close()
 print(json.dumps(out))
