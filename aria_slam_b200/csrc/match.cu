@@ -12,7 +12,7 @@
 
 namespace aslam {
 
-constexpr int KNN_TILE = 128;   // train rows per shared-memory stage (4 KB)
+constexpr int KNN_TILE = KNN_THREADS;   // train rows per shared-memory stage (48 B each: one staged row per thread)
 
 // popcount(q ^ t) over 256 bits.  POPC issues at 16 lanes/clk/SM (measured 4.38 Tpopc/s), LOP3 at 64:
 // carry-save adders (2 LOP3 each) compress three equal-weight words into a sum and a carry word and so
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(KNN_THREADS, ASLAM_KNN_MINB)
 knn2_partial_v2_kernel(const KnnProblem *__restrict__ probs, uint2 *partial, int q_stride, const KnnMul M, int merge_div,
                        const ExchangeArgs X)
 {
-    static_assert(KNN_TILE == KNN_THREADS && KNN_TILE == 128 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
+    static_assert(KNN_TILE == KNN_THREADS && KNN_TILE <= 128 && KNN_TILE % 32 == 0 && (KNN_RQ & 1) == 0, "one staged row per thread, 7-bit row-in-tile");
     __shared__ uint4 tile[2][KNN_TILE * 3];
 
     // Pipelined queries (programmatic dependent launch): the next query's kernel may be scheduled while this one's

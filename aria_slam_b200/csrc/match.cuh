@@ -21,7 +21,10 @@ constexpr int KEY_IDX_BITS = 23;
 constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
 constexpr int KNN_MAX_ROWS = 1 << KEY_IDX_BITS;
 
-constexpr int KNN_THREADS = 128;
+#ifndef ASLAM_KNN_THREADS
+#define ASLAM_KNN_THREADS 128
+#endif
+constexpr int KNN_THREADS = ASLAM_KNN_THREADS;
 constexpr int KNN_RQ = 4;                          // queries held in registers per thread
 constexpr int KNN_QBLOCK = KNN_THREADS * KNN_RQ;   // queries per CTA
 

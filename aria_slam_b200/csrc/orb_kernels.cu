@@ -1216,7 +1216,12 @@ struct BlurPlan {
     int gs[ORB_MAX_LEVELS];
 };
 struct BlurTapsM { float k[4]; float one; };
-constexpr int BM_THREADS = 128;
+// one warp per CTA: a finished warp frees its registers at once instead of waiting for three siblings with other strip
+// lengths (0.287 -> 0.269 ms; 64 threads 0.282; bench.py 96.9 k -> 97.6 k frames/s)
+#ifndef ASLAM_BM_THREADS
+#define ASLAM_BM_THREADS 32
+#endif
+constexpr int BM_THREADS = ASLAM_BM_THREADS;
 
 // Packed f32x2 values live in 64-bit registers from birth to death (inline PTX with "l" operands): held as float2 the
 // halves are two 32-bit values to the register allocator, which then assembles an aligned pair with MOVs for every packed
@@ -1485,7 +1490,7 @@ __device__ __forceinline__ void blur_bulk_march(const uint8_t *col, uint8_t *dp,
 }
 
 #ifndef ASLAM_BM_MINB
-#define ASLAM_BM_MINB 5         // 96 registers (8 bytes of spill) and 20 warps per SM: 0.369 ms; 4 (120 registers, 16 warps): 0.380; 3: 0.380
+#define ASLAM_BM_MINB (640 / ASLAM_BM_THREADS)     // 96 registers (8 bytes of spill) and 20 warps per SM; 16 warps (120 registers): 0.303 ms, 24 (80): 0.291
 #endif
 __global__ void __launch_bounds__(BM_THREADS, ASLAM_BM_MINB)
 blur_march_kernel(OrbGeom g, OrbBuffers b, BlurTapsM T, BlurPlan plan)
