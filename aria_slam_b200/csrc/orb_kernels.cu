@@ -772,9 +772,9 @@ fast_kernel(OrbGeom g, OrbBuffers b, const FastMul M)
     // warp and row in phase A); phase B fills in the pairs that pass the quick test
     {
         uint4 *sz = reinterpret_cast<uint4 *>(&S[0][0]);
-        static_assert(sizeof(S) % (256 * sizeof(uint4)) == 0, "score block is a whole number of 16-byte stores per thread");
+        static_assert(sizeof(S) % sizeof(uint4) == 0, "score block is a whole number of 16-byte stores");
 #pragma unroll
-        for (int i = 0; i < (int)(sizeof(S) / (256 * sizeof(uint4))); ++i) sz[i * 256 + tid] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < (int)(sizeof(S) / sizeof(uint4)); i += 256) sz[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 #endif
     __syncthreads();
