@@ -55,6 +55,7 @@ struct aslam_orb {
     // pyramid alone, so in the graph it is a branch beside FAST -> selection and joins before describe
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool no_cluster = false;       // a cluster launch was refused once on this device
 };
 
 static void orb_drop_graphs(aslam_orb *o)
@@ -340,9 +341,12 @@ static int orb_enqueue_launches(aslam_orb *o, int n, bool with_mask, bool fork_b
     if (!with_mask) b.mask = nullptr;
     int rc;
     ASLAM_CUDA(cudaMemsetAsync(o->b.overflow + 1, 0, sizeof(int32_t) * n, ctx->stream));
-    if (g.nbuilt > 1 && pyramid_cluster_wanted(n)) {
-        if ((rc = launch_pyramid_cluster(ctx, g, b, n, with_mask))) return rc;
-    } else {
+    bool levels_done = false;
+    if (g.nbuilt > 1 && pyramid_cluster_wanted(n) && !o->no_cluster) {
+        if (launch_pyramid_cluster(ctx, g, b, n, with_mask) == ASLAM_OK) levels_done = true;
+        else { cudaGetLastError(); o->no_cluster = true; }      // no cluster launches here (e.g. a partitioned GPU): level by level from now on
+    }
+    if (!levels_done) {
         for (int l = 1; l < g.nbuilt; ++l) {
             if ((rc = launch_resize_level(ctx, g, b, l, n, false))) return rc;
             if (with_mask && (rc = launch_resize_level(ctx, g, b, l, n, true))) return rc;
@@ -414,7 +418,8 @@ static int orb_enqueue(aslam_orb *o, int n, bool with_mask)
     if (rc != ASLAM_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
-        if (rc != ASLAM_OK) return rc;
+        // whatever went wrong while recording (a refused launch invalidates the capture and every launch after it): issue
+        // the chain directly; a genuine failure shows up again there and is reported
         return orb_enqueue_launches(o, n, with_mask);
     }
     cudaGraphDestroy(graph);

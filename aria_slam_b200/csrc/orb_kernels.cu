@@ -458,6 +458,9 @@ pyramid_cluster_kernel(OrbGeom g, OrbBuffers b)
 #endif
 int launch_pyramid_cluster(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nframes, bool with_mask)
 {
+    // test hook: behave like a device that refuses cluster launches (tests/test_gpu_errors.py checks the level-by-level path takes over)
+    static const bool refuse = [] { const char *e = getenv("ASLAM_TEST_REFUSE_CLUSTER"); return e && atoi(e) != 0; }();
+    if (refuse) return fail(ASLAM_E_CUDA, "cluster launch refused (ASLAM_TEST_REFUSE_CLUSTER)");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(PYR_CLUSTER, nframes, 1);
     cfg.blockDim = dim3(PYR_THREADS, 1, 1);

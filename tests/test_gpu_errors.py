@@ -99,3 +99,31 @@ def test_loopdb_grows_instead_of_refusing_and_a_failed_add_changes_nothing(ctx, 
         _lib.check(_lib.lib().aslam_loopdb_add(db.h, None, 5, 99))
     assert e.value.code == _lib.E_INVALID and (db.num_keyframes, db.num_rows) == before
     db.close()
+
+
+def test_a_refused_cluster_launch_falls_back_to_level_by_level():
+    """Calls with few frames build the pyramid with one thread-block-cluster launch and record their chain into a CUDA graph.
+    On a device that refuses the cluster launch (simulated: ASLAM_TEST_REFUSE_CLUSTER=1 in a child process) the recording
+    fails, the chain is issued directly, the level-by-level launches take over for good -- and the results are the oracle's."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys; sys.path.insert(0, %r)
+        import numpy as np
+        from aria_slam_b200 import synth
+        from aria_slam_b200._lib import Context
+        from aria_slam_b200.frontend import OrbB200Extractor, Frame
+        from oracle import oracle as O
+        ctx = Context(0)
+        ex = OrbB200Extractor(600, ctx)
+        img = synth.frame(640, 480, 77)
+        key = lambda k: sorted(zip(k["octave"].tolist(), k["x"].tolist(), k["y"].tolist()))
+        ko, do = O.orb(img, 600)
+        for _ in range(3):
+            f = Frame(); ex.extract(img, 640, 480, f)
+            assert key(f.keypoints) == key(ko)
+        print("fallback ok", f.numKeypoints())
+    """ % root)
+    env = dict(os.environ, ASLAM_TEST_REFUSE_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout + r.stderr
