@@ -2030,7 +2030,11 @@ int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfr
     // threads: 0.123), while a call with few frames wants the most threads per level (one frame: 21 us with 512 threads,
     // 25 with 256, 35 with 128; 1024 threads gain nothing: 24 us).
     static const int small_from = [] { const char *e = getenv("ASLAM_SEL_SMALL_FROM"); return e ? atoi(e) : 16; }();
-    const bool small = nframes >= small_from;
+    // ... and only while a level's survivors are a few rounds of a small CTA (2 x the largest quota <= 1024, i.e. up to ~2300
+    // keypoints per frame): at 1408 x 1408 / 4000 keypoints in calls of 16 frames the small CTAs lose 5 % (12 % with grid bucketing)
+    int max_quota = 0;
+    for (int l = 0; l < g.nbuilt; ++l) max_quota = max_quota > g.lv[l].quota ? max_quota : g.lv[l].quota;
+    const bool small = nframes >= small_from && 2 * max_quota <= 1024;
     if (g.grid_cell > 0) {
         if (small) select_kernel<true, ASLAM_SEL_SMALL_THREADS><<<grid, ASLAM_SEL_SMALL_THREADS, 0, ctx->stream>>>(g, b);
         else select_kernel<true, 512><<<grid, 512, 0, ctx->stream>>>(g, b);
