@@ -2026,9 +2026,10 @@ int launch_select(aslam_ctx *ctx, const OrbGeom &g, const OrbBuffers &b, int nfr
     dim3 grid(g.nbuilt, nframes);
     ProfScope ps(ctx, PK_SELECT);
     // CTA size by call size.  A level's CTA is a chain of short phases; with enough (frame, level) pairs to fill the GPU,
-    // four 256-thread CTAs per SM interleave their phases better than two of 512 (0.149 -> 0.121 ms per 256 frames; 128
-    // threads: 0.123), while a call with few frames wants the most threads per level (one frame: 21 us with 512 threads,
-    // 25 with 256, 35 with 128; 1024 threads gain nothing: 24 us).
+    // many small CTAs per SM interleave their phases better than two of 512 threads (0.149 -> 0.121 ms per 256 frames with 256
+    // threads, 0.123 with 128) and hand their slots to other streams' kernels sooner (bench.py, eight concurrent streams of 32
+    // frames: 91.6 k / 94.7 k / 96.5 k frames/s with 512 / 256 / 128 threads), while a call with few frames wants the most
+    // threads per level (one frame: 21 us with 512 threads, 25 with 256, 35 with 128; 1024 threads gain nothing: 24 us).
     static const int small_from = [] { const char *e = getenv("ASLAM_SEL_SMALL_FROM"); return e ? atoi(e) : 16; }();
     // ... and only while a level's survivors are a few rounds of a small CTA (2 x the largest quota <= 1024, i.e. up to ~2300
     // keypoints per frame): at 1408 x 1408 / 4000 keypoints in calls of 16 frames the small CTAs lose 5 % (12 % with grid bucketing)
